@@ -1,0 +1,467 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement ("port") of the POY5 dynamic-homology
+ * pairwise alignment hot path.  Nothing in poy5_b200/ may link, import or call
+ * this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and only as the checker.
+ *
+ * Parity status: PINNED against the unmodified reference C compiled from
+ * /root/reference/src into oracle/_ref/libpoyref.so (tests/test_oracle_vs_ref.py,
+ * run in the build container) and against the golden vectors generated from that
+ * library (tests/golden/, generator tests/golden/make_golden.py).  The reference
+ * ships no tests or fixtures of its own for this path.
+ *
+ * Conventions: sequences are uint8 DNA bitsets
+ * A=1 C=2 G=4 T=8 gap=16, element 0 is always the gap code and takes part in
+ * the DP as row/column 0.  `len` counts that element.  All arithmetic is plain
+ * wrapping int32; DO_INF (the reference's HIGH_NUM, src/algn.c:37) is added to,
+ * never saturated.
+ *
+ * Every function cites the reference lines it restates.  The restatement keeps
+ * the reference's *memory semantics* where they are observable (the row-buffer
+ * aliasing of the cost-only entry point, the never-cleared unsigned-short
+ * gap-count rows of the banded entry point) by laying its scratch out the same
+ * way, but it is written from the recurrences, not transcribed.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+
+#define DO_INF 1000000
+#define GAPBIT 16
+#define NOGAP 15
+
+typedef unsigned char u8;
+typedef unsigned short u16;
+
+/* Flat cost model for the 5-letter bitset alphabet (struct cm, src/cm.h:33-76,
+ * restricted to combinations=1, level=0, lcm=5, gap=16). Tables indexed (a<<5)+b. */
+typedef struct {
+    int cost[1024];
+    int worst[1024];
+    u8 median[1024];
+    int prepend[32];
+    int tail[32];
+    int gap_open;
+    int cost_model_type; /* 0 linear, 1 affine, 2 no alignment */
+    int min_non0;        /* cm_get_min_non0_cost, src/cm.c:1063-1089 */
+} do_cm;
+
+int do_cm_sizeof(void) { return (int)sizeof(do_cm); }
+
+void do_cm_init(do_cm *c, const int *cost, const int *worst, const u8 *median, const int *prepend,
+                const int *tail, int gap_open, int cost_model_type) {
+    int i, m = 0x3fffffff; /* INT_MAX/2 */
+    memcpy(c->cost, cost, sizeof c->cost);
+    memcpy(c->worst, worst, sizeof c->worst);
+    memcpy(c->median, median, sizeof c->median);
+    memcpy(c->prepend, prepend, sizeof c->prepend);
+    memcpy(c->tail, tail, sizeof c->tail);
+    c->gap_open = gap_open;
+    c->cost_model_type = cost_model_type;
+    for (i = 0; i < 1024; i++)
+        if (c->cost[i] > 0 && c->cost[i] < m) m = c->cost[i];
+    c->min_non0 = m;
+}
+
+/* ---- per-position gap parameters ---------------------------------------- */
+/* HAS_GAP_OPENING, src/algn.c:1240-1253 (gap_startNO = 0 branch) */
+static int gap_opening_at(int idx, int prev, int cur, int go) {
+    if (idx == 1 && (cur & GAPBIT)) return 0;
+    if (idx > 1 && !(prev & GAPBIT) && (cur & GAPBIT)) return 0;
+    return go;
+}
+
+/* Column parameters shared by both affine entry points
+ * (src/algn.c:2026-2035 and :2225-2236): go_j, and the horizontal extension
+ * cost *as computed inside the loop* (i.e. before hext[1] is overwritten). */
+static void column_params(const do_cm *c, const u8 *sj, int lastj, int *gop, int *hext) {
+    int j;
+    hext[0] = 0;
+    for (j = 1; j <= lastj; j++) {
+        int ge = c->prepend[sj[j]]; /* gap_row = prec row 0 = prepend, A4 */
+        gop[j] = gap_opening_at(j, sj[j - 1], sj[j], c->gap_open);
+        hext[j] = ((sj[j - 1] & GAPBIT) && !(sj[j] & GAPBIT)) ? gop[j] + ge : ge;
+    }
+}
+
+typedef struct { int ge, go, vext, nogap, hasgap, prevgap; const int *row; } rowp;
+
+/* Row parameters (src/algn.c:2058-2065, 2273-2283) */
+static rowp row_params(const do_cm *c, const u8 *si, int i) {
+    rowp r;
+    int ic = si[i], ip = si[i - 1];
+    r.ge = c->cost[(ic << 5) + GAPBIT];               /* HAS_GAP_EXTENSION :1220 */
+    r.go = gap_opening_at(i, ip, ic, c->gap_open);
+    r.nogap = ic & NOGAP;
+    r.hasgap = (ic & GAPBIT) != 0;
+    r.prevgap = (ip & GAPBIT) != 0;
+    r.vext = (i > 1 && (ip & GAPBIT) && !(ic & GAPBIT)) ? r.go + r.ge : r.ge;
+    r.row = c->cost + (r.nogap << 5);
+    return r;
+}
+
+/* ======================================================================== */
+/* 1. cost-only affine: algn_CAML_cost_affine_3 -> algn_fill_plane_3_aff_nobt */
+/*    (src/algn.c:2457-2515, 1822-1863, 1987-2110)                           */
+/* ======================================================================== */
+int do_cost_affine(const do_cm *c, const u8 *s1, int len1, const u8 *s2, int len2) {
+    const u8 *si, *sj;
+    int leni, lenj, L, lasti, lastj, stride, i, j, go = c->gap_open, res;
+    int *M, *gop, *hext;
+    int *cb[2], *eb[2], *ev[2], *eh[2];
+    if (len1 <= len2) { si = s1; leni = len1; sj = s2; lenj = len2; }
+    else { si = s2; leni = len2; sj = s1; lenj = len1; }
+    L = lenj;              /* `largest`, :2479-2481 */
+    lasti = leni - 1;
+    lastj = lenj - 1;
+    stride = lastj + 2;    /* `offset`, :2005 -- one more than the 2-row spacing L */
+    /* Same flat layout as the reference scratch (:2489-2494); the second row of
+     * each pair starts at +stride, so X_row1[lastj] IS Y_row0[0] for the
+     * matrix Y laid out after X. */
+    M = (int *)calloc((size_t)13 * L + 16, sizeof(int));
+    cb[0] = M;          cb[1] = cb[0] + stride;
+    eb[0] = M + 2 * L;  eb[1] = eb[0] + stride;
+    ev[0] = M + 4 * L;  ev[1] = ev[0] + stride;
+    eh[0] = M + 6 * L;  eh[1] = eh[0] + stride;
+    gop = M + 10 * L;
+    hext = M + 11 * L;
+    /* row 0 (:1831-1852) */
+    cb[0][0] = 0; eb[0][0] = DO_INF; eh[0][0] = go; ev[0][0] = go;
+    for (j = 1; j <= lastj; j++) {
+        eh[0][j] = eh[0][j - 1] + c->prepend[sj[j]];
+        cb[0][j] = DO_INF; eb[0][j] = DO_INF; ev[0][j] = DO_INF;
+    }
+    column_params(c, sj, lastj, gop, hext);
+    if (lastj >= 1) hext[1] = c->prepend[sj[1]]; /* :2035, A2 */
+    for (i = 1; i <= lasti; i++) {
+        int cur = i & 1, prv = cur ^ 1; /* row 0 lives in buffer 0 */
+        int *CB = cb[cur], *EB = eb[cur], *EV = ev[cur], *EH = eh[cur];
+        const int *pCB = cb[prv], *pEB = eb[prv], *pEV = ev[prv], *pEH = eh[prv];
+        rowp r = row_params(c, si, i);
+        int r0;
+        /* column 0 (:2057-2072), in the reference's store order */
+        EH[0] = DO_INF;
+        r0 = pEV[0] + r.vext;
+        EH[0] = DO_INF; CB[0] = r0; EB[0] = DO_INF; EV[0] = r0; CB[0] = DO_INF;
+        for (j = 1; j <= lastj; j++) {
+            int jc = sj[j], jp = sj[j - 1];
+            int ge_j = c->prepend[jc], go_j = gop[j];
+            int ext, opn, both, clean, dg, od, diag, a, v, h, d, xgo;
+            /* extend horizontal (:1260-1273): ties take the opening */
+            ext = EH[j - 1] + hext[j];
+            opn = CB[j - 1] + go_j + ge_j;
+            EH[j] = ext < opn ? ext : opn;
+            /* extend vertical (:1306-1318) */
+            ext = pEV[j] + r.vext;
+            opn = pCB[j] + r.go + r.ge;
+            EV[j] = ext < opn ? ext : opn;
+            /* extend block diagonal (:1351-1369) */
+            both = r.hasgap && (jc & GAPBIT);
+            clean = !r.prevgap && !(jp & GAPBIT);
+            dg = both ? 0 : DO_INF;
+            od = both ? (clean ? 0 : 2 * go) : DO_INF;
+            ext = pEB[j - 1] + dg;
+            opn = pCB[j - 1] + od;
+            EB[j] = ext < opn ? ext : opn;
+            /* close block diagonal (:1401-1433) */
+            diag = r.row[jc & NOGAP];
+            xgo = go_j < r.go ? r.go : go_j;
+            a = pCB[j - 1] + diag;
+            v = r.hasgap ? pEV[j - 1] + diag + go_j : pEV[j - 1] + diag;
+            h = (jc & GAPBIT) ? pEH[j - 1] + diag + r.go : pEH[j - 1] + diag;
+            d = pEB[j - 1] + diag + xgo;
+            if (a > v) a = v;
+            if (a > h) a = h;
+            if (a > d) a = d;
+            CB[j] = a;
+        }
+    }
+    {
+        int cur = lasti >= 1 ? (lasti & 1) : 0;
+        res = eh[cur][lastj];
+        if (res > ev[cur][lastj]) res = ev[cur][lastj];
+        if (res > eb[cur][lastj]) res = eb[cur][lastj];
+        if (res > cb[cur][lastj]) res = cb[cur][lastj];
+    }
+    free(M);
+    return res;
+}
+
+/* ======================================================================== */
+/* 2. banded affine with traceback: algn_CAML_align_affine_3                 */
+/*    (src/algn.c:2359-2447, 1866-1899, 2113-2354, 1715-1819, 126-176)       */
+/* ======================================================================== */
+/* 15-bit direction mask, src/algn.c:1185-1199 */
+enum {
+    A2A = 1, A2V = 2, A2H = 4, A2D = 8, BEG_B = 16, END_B = 32, BEG_V = 64, END_V = 128,
+    BEG_H = 256, END_H = 512, DO_A = 1024, DO_V = 2048, DO_H = 4096, H_EQ_V = 8192, DO_D = 16384
+};
+
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/* algn_fill_gapnum (src/algn.c:126-176): max-plus over unsigned short rows;
+ * evaluated in int, truncated on store (A7). p* = previous row, g* = current. */
+static void gapnum(int j, int al, int ins, int del, const u16 *p1, u16 *g1, const u16 *p2, u16 *g2) {
+    if (al) {
+        if (del && ins) {
+            g1[j] = (u16)imax(imax(p1[j - 1], g1[j - 1] + 1), imax(g1[j - 1] + 1, p1[j]));
+            g2[j] = (u16)imax(imax(p2[j - 1], g2[j - 1]), imax(g2[j - 1], p2[j] + 1));
+        } else if (del) {
+            g1[j] = (u16)imax(p1[j], p1[j - 1]);
+            g2[j] = (u16)imax(p2[j - 1], p2[j] + 1);
+        } else if (ins) {
+            g1[j] = (u16)imax(g1[j - 1] + 1, p1[j - 1]);
+            g2[j] = (u16)imax(p2[j - 1], g2[j - 1]);
+        } else {
+            g1[j] = p1[j - 1];
+            g2[j] = p2[j - 1];
+        }
+    } else if (ins) {
+        if (del) {
+            g1[j] = (u16)imax(g1[j - 1] + 1, p1[j]);
+            g2[j] = (u16)imax(p2[j] + 1, g2[j - 1]);
+        } else {
+            g1[j] = (u16)(g1[j - 1] + 1);
+            g2[j] = g2[j - 1];
+        }
+    } else {
+        g1[j] = p1[j];
+        g2[j] = (u16)(p2[j] + 1);
+    }
+}
+
+typedef struct {
+    int iterations;        /* number of band fills (T, 2T, 4T, ...) */
+    int final_T, final_k;  /* threshold / half band of the accepted fill */
+    long long cells;       /* band cells computed over all fills */
+} do_align_stats;
+
+/* One band fill with half-width parameter p: algn_newkk_test_aff (:2186-2306)
+ * + algn_newkk_fill_a_row_aff (:2113-2180) + ASSIGN_MINIMUM (:1936-1981).
+ * Scratch rows W (2 rows x 4 states), gm (4 u16 rows) and the direction matrix
+ * persist across fills exactly like the reference's global scratch.         */
+static int band_fill(const do_cm *c, const u8 *si, int lasti, const u8 *sj, int lastj, int p,
+                     int *W, int *gop, int *hext, u16 **gmbuf, u16 *dir, int *res_cost, long long *cells) {
+    int go = c->gap_open, stride = lastj + 2, i, j;
+    int k = p >= lasti ? lasti - 1 : p; /* :2195-2196 */
+    int delta = lastj - lasti;
+    int *cb[2], *eb[2], *ev[2], *eh[2];
+    u16 *g1 = gmbuf[0], *n1 = gmbuf[1], *g2 = gmbuf[2], *n2 = gmbuf[3]; /* gap_num1..4, :2415-2418 */
+    cb[0] = W;              cb[1] = cb[0] + stride;
+    eb[0] = W + 2 * stride; eb[1] = eb[0] + stride;
+    ev[0] = W + 4 * stride; ev[1] = ev[0] + stride;
+    eh[0] = W + 6 * stride; eh[1] = eh[0] + stride;
+    /* row 0 as re-initialised by the band fill (:2222-2248, A1): finite CB */
+    ev[0][0] = DO_INF; cb[0][0] = 0; g1[0] = 0; g2[0] = 0;
+    column_params(c, sj, lastj, gop, hext);
+    for (j = 1; j <= lastj; j++) {
+        g1[j] = (u16)j; g2[j] = 0; n1[j] = (u16)-1; n2[j] = (u16)-1;
+        dir[j] = DO_H;
+        ev[0][j] = DO_INF;
+        cb[0][j] = cb[0][j - 1] + hext[j];
+        eh[0][j] = cb[0][j];
+    }
+    if (lastj >= 1) hext[1] = c->prepend[sj[1]]; /* :2248, A2 */
+    for (i = 1; i <= lasti; i++) {
+        int cur = i & 1, prv = cur ^ 1;
+        int *CB = cb[cur], *EB = eb[cur], *EV = ev[cur], *EH = eh[cur];
+        const int *pCB = cb[prv], *pEB = eb[prv], *pEV = ev[prv], *pEH = eh[prv];
+        u16 *drow = dir + (size_t)i * stride;
+        rowp r = row_params(c, si, i);
+        int startj = i - k > 0 ? i - k : 0;
+        int endj = (i + delta + k <= lastj - 1) ? i + delta + k : lastj; /* :2256-2257, A8 */
+        for (j = startj; j <= endj; j++) {
+            /* the reference primes jc with sj[startj] before the loop, so at the
+             * left-border cell "previous column symbol" is sj[j] itself (:2126-2133) */
+            int jc = sj[j], jp = j == startj ? sj[j] : sj[j - 1];
+            int right = (j - i - (delta + 1) + 1 == k), left = (j == startj);
+            int ge_j = c->prepend[jc], go_j = gop[j];
+            int mask = 0, ext, opn, fin, m;
+            if (!left) {
+                ext = EH[j - 1] + hext[j];
+                opn = CB[j - 1] + go_j + ge_j;
+                if (ext < opn) { mask |= BEG_H; EH[j] = ext; } else { mask |= END_H; EH[j] = opn; }
+            } else EH[j] = DO_INF;
+            if (!right) {
+                ext = pEV[j] + r.vext;
+                opn = pCB[j] + r.go + r.ge;
+                if (ext < opn) { mask |= BEG_V; EV[j] = ext; } else { mask |= END_V; EV[j] = opn; }
+            } else EV[j] = DO_INF;
+            if (j > 0) {
+                int both = r.hasgap && (jc & GAPBIT), clean = !r.prevgap && !(jp & GAPBIT);
+                int dg = both ? 0 : DO_INF, od = both ? (clean ? 0 : 2 * go) : DO_INF;
+                int diag, xgo, a, v, h, d, cm;
+                ext = pEB[j - 1] + dg;
+                opn = pCB[j - 1] + od;
+                if (ext < opn) { mask |= BEG_B; EB[j] = ext; } else { mask |= END_B; EB[j] = opn; }
+                /* close block diagonal with tie mask, order A,V,H,D (:1436-1492, A6) */
+                diag = r.row[jc & NOGAP];
+                xgo = go_j < r.go ? r.go : go_j;
+                a = pCB[j - 1] + diag;
+                v = r.hasgap ? pEV[j - 1] + diag + go_j : pEV[j - 1] + diag;
+                h = (jc & GAPBIT) ? pEH[j - 1] + diag + r.go : pEH[j - 1] + diag;
+                d = pEB[j - 1] + diag + xgo;
+                cm = A2A;
+                if (a >= v) { if (a > v) { a = v; cm = A2V; } else cm |= A2V; }
+                if (a >= h) { if (a > h) { a = h; cm = A2H; } else cm |= A2H; }
+                if (a >= d) { if (a > d) { a = d; cm = A2D; } else cm |= A2D; }
+                CB[j] = a;
+                mask |= cm;
+            } else { CB[j] = DO_INF; EB[j] = DO_INF; }
+            /* final minimum with tie mask, order H,V,D,A (:1936-1977) */
+            m = DO_H; fin = EH[j];
+            if (fin >= EV[j]) { if (fin > EV[j]) { fin = EV[j]; m = DO_V; } else m |= DO_V; }
+            if (fin >= EB[j]) { if (fin > EB[j]) { fin = EB[j]; m = DO_D; } else m |= DO_D; }
+            if (fin >= CB[j]) { if (fin > CB[j]) { fin = CB[j]; m = DO_A; } else m |= DO_A; }
+            if (fin == EH[j] && EH[j] == EV[j]) m |= H_EQ_V;
+            mask |= m;
+            gapnum(j, (mask & (DO_A | DO_D)) != 0, (mask & DO_H) != 0, (mask & DO_V) != 0, g1, n1, g2, n2);
+            drow[j] = (u16)mask;
+            if (j == lastj) *res_cost = fin; /* final_cost_matrix is one row (:2168, :2302) */
+            (*cells)++;
+        }
+        if (i <= lasti - 1) { u16 *t = g1; g1 = n1; n1 = t; t = g2; g2 = n2; n2 = t; } /* :2293-2300 */
+    }
+    return imax(n1[lastj], n2[lastj]); /* :2305 */
+}
+
+/* traceback state machine backtrace_aff (src/algn.c:1715-1819, 1531-1619).
+ * Outputs are produced by prepending; here they are written right-to-left into
+ * caller buffers of capacity cap and then shifted to the front.             */
+typedef struct { u8 *buf; int cap, pos; } rseq;
+static void rprep(rseq *s, int v) { s->buf[--s->pos] = (u8)v; }
+static int rfinish(rseq *s) {
+    int n = s->cap - s->pos;
+    memmove(s->buf, s->buf + s->pos, (size_t)n);
+    return n;
+}
+
+static void indel_emit(rseq *med, rseq *medwg, int sym) {
+    if (!(sym & GAPBIT)) { rprep(med, sym | GAPBIT); rprep(medwg, sym | GAPBIT); }
+    else rprep(medwg, GAPBIT);
+}
+
+static int pick_mode(int dg, int al, int v, int h, int swaped) {
+    /* choose_dir (:1594-1619): 1 vertical, 2 horizontal, 3 diagonal, 4 align */
+    (void)al;
+    if (!swaped) {
+        if (v) return 1;
+        if (h) return 2;
+    } else {
+        if (h) return 2;
+        if (v) return 1;
+    }
+    return dg ? 3 : 4;
+}
+
+static void traceback(const do_cm *c, const u16 *dir, const u8 *si, int leni, const u8 *sj, int lenj,
+                      int swaped, rseq *med, rseq *medwg, rseq *ri, rseq *rj) {
+    int stride = lenj + 1, i = leni - 1, j = lenj - 1, mode = 0;
+    const u16 *dp = dir + ((size_t)leni * stride - 2); /* :1735 == cell (leni-1, lenj-1) */
+    int ic = si[i], jc = sj[j];
+    while (i != 0 && j != 0) {
+        int m = *dp;
+        if (mode == 0) {
+            mode = pick_mode(m & DO_D, m & DO_A, m & DO_V, m & DO_H, swaped);
+        } else if (mode == 1) { /* vertical run (:1553-1572) */
+            if (m & (END_V | H_EQ_V)) mode = 0;
+            indel_emit(med, medwg, ic);
+            rprep(ri, ic); rprep(rj, GAPBIT);
+            i--; dp -= stride; ic = si[i];
+        } else if (mode == 2) { /* horizontal run (:1531-1550) */
+            if (m & (END_H | H_EQ_V)) mode = 0;
+            indel_emit(med, medwg, jc);
+            rprep(ri, GAPBIT); rprep(rj, jc);
+            j--; dp -= 1; jc = sj[j];
+        } else if (mode == 3) { /* block diagonal (:1752-1762) */
+            if (m & END_B) mode = 0;
+            rprep(ri, ic); rprep(rj, jc); rprep(medwg, GAPBIT);
+            i--; j--; dp -= stride + 1; jc = sj[j]; ic = si[i];
+        } else { /* align (:1763-1781) */
+            int prep = c->median[((ic & NOGAP) << 5) + (jc & NOGAP)];
+            mode = pick_mode(m & A2D, m & A2A, m & A2V, m & A2H, swaped);
+            rprep(med, prep); rprep(medwg, prep);
+            rprep(ri, ic); rprep(rj, jc);
+            i--; j--; dp -= stride + 1; jc = sj[j]; ic = si[i];
+        }
+    }
+    while (i != 0) { /* :1784-1797 */
+        indel_emit(med, medwg, ic);
+        rprep(ri, ic); rprep(rj, GAPBIT);
+        i--; ic = si[i];
+    }
+    while (j != 0) { /* :1798-1811 */
+        indel_emit(med, medwg, jc);
+        rprep(ri, GAPBIT); rprep(rj, jc);
+        j--; jc = sj[j];
+    }
+    rprep(ri, GAPBIT); rprep(rj, GAPBIT); rprep(medwg, GAPBIT);
+    if (med->pos == med->cap || med->buf[med->pos] != GAPBIT) rprep(med, GAPBIT); /* :1815 */
+}
+
+/* Persistent scratch standing in for the reference's process-global
+ * Matrix.default (grow-only, never cleared; src/matrix.ml:34).              */
+typedef struct { int *W; u16 *gm[4]; u16 *dir; size_t wcap, gcap, dcap; } do_scratch;
+
+do_scratch *do_scratch_new(void) { return (do_scratch *)calloc(1, sizeof(do_scratch)); }
+void do_scratch_free(do_scratch *s) {
+    if (s) { int k; free(s->W); for (k = 0; k < 4; k++) free(s->gm[k]); free(s->dir); free(s); }
+}
+
+static void scratch_fit(do_scratch *s, int leni, int lenj) {
+    size_t w = (size_t)12 * (lenj + 2) + 16, g = (size_t)lenj + 2, d = (size_t)(leni + 1) * (lenj + 2);
+    int k;
+    if (s->wcap < w) { s->W = (int *)realloc(s->W, w * sizeof(int)); memset(s->W + s->wcap, 0, (w - s->wcap) * sizeof(int)); s->wcap = w; }
+    if (s->gcap < g) {
+        for (k = 0; k < 4; k++) { s->gm[k] = (u16 *)realloc(s->gm[k], g * sizeof(u16)); memset(s->gm[k] + s->gcap, 0, (g - s->gcap) * sizeof(u16)); }
+        s->gcap = g;
+    }
+    if (s->dcap < d) { s->dir = (u16 *)realloc(s->dir, d * sizeof(u16)); memset(s->dir + s->dcap, 0, (d - s->dcap) * sizeof(u16)); s->dcap = d; }
+}
+
+/* requires leni <= lenj (the OCaml caller passes the shorter first and tells us
+ * through `swaped` whether it exchanged them, src/sequence.ml:633-649).
+ * Output buffers need capacity leni+lenj+2.  lens = {median, medianwg, resi, resj}.
+ * Returns the cost, or INT_MIN if leni > lenj ("pass the shorter one as first"). */
+int do_align_affine(const do_cm *c, do_scratch *sc, const u8 *si, int leni, const u8 *sj, int lenj,
+                    int swaped, u8 *median, u8 *medianwg, u8 *resi, u8 *resj, int *lens,
+                    do_align_stats *st) {
+    int lasti = leni - 1, lastj = lenj - 1, delta = lastj - lasti, cap = leni + lenj + 2;
+    int T, res = 0, j, stride = lastj + 2;
+    int *W, *gop, *hext;
+    do_align_stats local;
+    rseq med = { median, cap, cap }, medwg = { medianwg, cap, cap }, ri = { resi, cap, cap }, rj = { resj, cap, cap };
+    if (!st) st = &local;
+    if (lenj < leni) return (-2147483647 - 1);
+    scratch_fit(sc, leni, lenj);
+    W = sc->W; gop = W + 8 * stride + 4; hext = gop + stride + 4;
+    st->iterations = 0; st->cells = 0;
+    /* initialize_matrices_affine (:1866-1899): its row-0 costs are overwritten by
+     * the band fill except when there are no rows at all (leni == 1); the
+     * final-cost row it writes is what an empty first sequence returns. */
+    res = 0;
+    {
+        /* Only EB row 0 and EH[0][0] survive the band fill's own row-0 setup; they
+         * are NOT refreshed between fills, so from the second fill on row 1 sees
+         * whatever the previous fill left in row buffer 0 (kept in sc->W). */
+        int *eb0 = W + 2 * stride, *eh0p = W + 6 * stride, eh0 = c->gap_open;
+        eh0p[0] = c->gap_open;
+        for (j = 0; j <= lastj; j++) eb0[j] = DO_INF;
+        for (j = 1; j <= lastj; j++) { eh0 += c->prepend[sj[j]]; }
+        if (lastj >= 1) res = eh0;
+    }
+    sc->dir[0] = 0xFFFF;
+    T = (delta + 1) * c->min_non0; /* algn_fill_plane_3_aff :2348-2349 */
+    for (;;) { /* algn_newkk_increaseT_aff :2311-2336 */
+        int p = (T - delta) / 2, gap_num, newp;
+        gap_num = band_fill(c, si, lasti, sj, lastj, p, W, gop, hext, sc->gm, sc->dir, &res, &st->cells);
+        st->iterations++;
+        st->final_T = T;
+        st->final_k = p >= lasti ? lasti - 1 : p;
+        newp = (2 * T - delta) / 2;
+        if (gap_num < p || newp - lastj + 1 >= 0) break;
+        T *= 2;
+    }
+    traceback(c, sc->dir, si, leni, sj, lenj, swaped, &med, &medwg, &ri, &rj);
+    lens[0] = rfinish(&med); lens[1] = rfinish(&medwg); lens[2] = rfinish(&ri); lens[3] = rfinish(&rj);
+    return res;
+}

@@ -1,0 +1,67 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/libdooracle.so (the plain-C
+restatement oracle/do_oracle.c)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libdooracle.so")
+_u8p = C.POINTER(C.c_ubyte)
+_i32p = C.POINTER(C.c_int)
+INT_MIN = -2**31
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "do_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-o", _SO, src])
+    return _SO
+
+
+class AlignStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("final_T", C.c_int), ("final_k", C.c_int), ("cells", C.c_longlong)]
+
+
+def _p8(a):
+    return a.ctypes.data_as(_u8p)
+
+
+class Port:
+    def __init__(self):
+        self.lib = L = C.CDLL(build())
+        L.do_cm_sizeof.restype = C.c_int
+        L.do_cm_init.argtypes = [C.c_void_p, _i32p, _i32p, _u8p, _i32p, _i32p, C.c_int, C.c_int]
+        L.do_cost_affine.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p, C.c_int]
+        L.do_scratch_new.restype = C.c_void_p
+        L.do_scratch_free.argtypes = [C.c_void_p]
+        L.do_align_affine.argtypes = [C.c_void_p, C.c_void_p, _u8p, C.c_int, _u8p, C.c_int, C.c_int,
+                                      _u8p, _u8p, _u8p, _u8p, _i32p, C.POINTER(AlignStats)]
+        self.scratch = L.do_scratch_new()
+
+    def cm(self, m):
+        """do_cm from a CostMatrix2D-like object (32x32 tables)."""
+        buf = C.create_string_buffer(self.lib.do_cm_sizeof())
+        cost = np.ascontiguousarray(m.cost, np.int32); worst = np.ascontiguousarray(m.worst, np.int32)
+        med = np.ascontiguousarray(m.median, np.uint8)
+        pre = np.ascontiguousarray(m.prepend, np.int32); tail = np.ascontiguousarray(m.tail, np.int32)
+        self.lib.do_cm_init(buf, cost.ctypes.data_as(_i32p), worst.ctypes.data_as(_i32p), _p8(med),
+                            pre.ctypes.data_as(_i32p), tail.ctypes.data_as(_i32p), m.gap_open, m.cost_model_type)
+        return buf
+
+    def cost_affine(self, cm, s1, s2):
+        s1 = np.ascontiguousarray(s1, np.uint8); s2 = np.ascontiguousarray(s2, np.uint8)
+        return self.lib.do_cost_affine(cm, _p8(s1), len(s1), _p8(s2), len(s2))
+
+    def align_affine(self, cm, si, sj, swaped=0, with_stats=False):
+        si = np.ascontiguousarray(si, np.uint8); sj = np.ascontiguousarray(sj, np.uint8)
+        cap = len(si) + len(sj) + 2
+        outs = [np.zeros(cap, np.uint8) for _ in range(4)]
+        lens = (C.c_int * 4)()
+        st = AlignStats()
+        r = self.lib.do_align_affine(cm, self.scratch, _p8(si), len(si), _p8(sj), len(sj), int(swaped),
+                                     _p8(outs[0]), _p8(outs[1]), _p8(outs[2]), _p8(outs[3]), lens, C.byref(st))
+        if r == INT_MIN:
+            raise RuntimeError("pass the shorter one as first")
+        res = (r,) + tuple(o[:n].copy() for o, n in zip(outs, lens))
+        return res + (st,) if with_stats else res
