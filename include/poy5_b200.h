@@ -1,0 +1,152 @@
+/* poy5_b200 -- B200-native batched direct-optimization (DO) alignment for POY5.
+ *
+ * C ABI of libpoy5b200.so.  This is the drop-in boundary for the hot path of
+ * amnh/poy5's libpoycside C stubs (src/libpoycside.clib): every entry point is
+ * the BATCH twin of one reference stub and cites the stub it replaces.  Plain
+ * pointers and sizes only; no CUDA, torch or OCaml types appear here.
+ *
+ * Data conventions (identical to the reference):
+ *   - a sequence is an array of uint8 DNA bitset codes A=1 C=2 G=4 T=8 gap=16
+ *     (ambiguity = OR); element 0 is always the gap code and `len` counts it
+ *     (struct seq, src/seq.h:52-61);
+ *   - sequences live in a POOL: one packed byte buffer plus nseq+1 offsets;
+ *     pairs name pool entries by index, so a node sequence used by thousands
+ *     of candidate pairs is uploaded once (the Parmap candidate list of
+ *     src/ptree.ml:1356-1408 is exactly such a batch);
+ *   - costs are int32; there is no saturation (HIGH_NUM = 1000000 sentinel
+ *     arithmetic of src/algn.c:37 is reproduced bit for bit).
+ *
+ * Errors: every call returns a poy_status (0 = OK).  The reference raises
+ * OCaml `Failure` (failwith); here the same conditions come back as codes and
+ * poy_last_error() holds the reference's message text.  There is NO CPU
+ * fallback: without a usable CUDA device the context cannot be created.
+ */
+#ifndef POY5_B200_H
+#define POY5_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#define POY_API __attribute__((visibility("default")))
+#else
+#define POY_API
+#endif
+
+typedef int poy_status;
+enum {
+    POY_OK = 0,
+    POY_ERR_CUDA = -1,          /* CUDA runtime failure (message in poy_last_error) */
+    POY_ERR_NO_DEVICE = -2,     /* no CUDA device: the product path refuses to run */
+    POY_ERR_ARG = -3,           /* bad argument (null pointer, index out of range, ...) */
+    POY_ERR_ORDER = -4,         /* "pass the shorter one as first" (src/algn.c:2396) */
+    POY_ERR_COST_RANGE = -5,    /* cost model outside the domain in which the reference is defined:
+                                   negative entries, or path costs that can reach HIGH_NUM */
+    POY_ERR_MODEL = -6,         /* entry point does not match cm.cost_model_type */
+    POY_ERR_NOMEM = -7
+};
+
+typedef struct poy_ctx poy_ctx;     /* one per process per GPU: stream, scratch pools */
+typedef struct poy_cm poy_cm;       /* device-resident 2-D cost model (struct cm, src/cm.h:33-76) */
+typedef struct poy_cm3d poy_cm3d;   /* device-resident 3-D cost model (struct cm_3d, src/cm.h:253-280) */
+typedef struct poy_pool poy_pool;   /* device-resident packed sequences + per-base gap parameters */
+
+/* ---- context ------------------------------------------------------------- */
+/* `stream` is a cudaStream_t passed as void* (0 = the library creates its own
+ * non-blocking stream).  All device work of this context is ordered on it. */
+POY_API poy_status poy_ctx_create(int device, void *stream, poy_ctx **out);
+POY_API void poy_ctx_destroy(poy_ctx *ctx);
+POY_API const char *poy_last_error(const poy_ctx *ctx);
+POY_API const char *poy_status_string(poy_status s);
+/* cap (bytes) on the direction-matrix arena used by the traceback entry points;
+ * batches larger than the cap are processed in waves.  Default 8 GiB. */
+POY_API poy_status poy_ctx_set_arena_limit(poy_ctx *ctx, uint64_t bytes);
+POY_API poy_status poy_ctx_synchronize(poy_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py: gpu_launches) */
+POY_API uint64_t poy_ctx_launch_count(const poy_ctx *ctx);
+
+/* ---- cost model: replaces the cm_CAML_* setters + cm.c tables --------------
+ * Host-side image of `struct cm` for the 5-letter bitset alphabet
+ * (combinations = 1, level = 0, lcm = 5, gap = 16, all_elements = 31).  Tables
+ * are indexed (a << 5) + b like cm_calc_cost_position (src/cm.c:903-911). */
+typedef struct {
+    int32_t cost[1024];      /* c->cost   */
+    int32_t worst[1024];     /* c->worst  */
+    uint8_t median[1024];    /* c->median */
+    int32_t prepend[32];     /* c->prepend_cost (src/cost_matrix.ml:994-1001) */
+    int32_t tail[32];        /* c->tail_cost */
+    int32_t gap_open;        /* c->gap_open */
+    int32_t cost_model_type; /* 0 linear, 1 affine, 2 no alignment (c->cost_model_type) */
+} poy_cm_host;
+
+/* Cost_matrix.Two_D construction restated in C++ (src/cost_matrix.ml:721-804,
+ * 862-897, 994-1016, 1140-1189): fills `full` (c2_full) and `original`
+ * (c2_original) from a 5x5 single-letter matrix in row-major order
+ * (A,C,G,T,gap).  gap_open < 0 means "linear" (no set_cost_model call);
+ * otherwise the affine re-fill of src/data.ml:5937-5964 is applied. */
+POY_API poy_status poy_cm_fill(const int32_t single[25], int32_t gap_open, poy_cm_host *full, poy_cm_host *original);
+/* cm_get_min_non0_cost (src/cm.c:1063-1089) */
+POY_API int32_t poy_cm_min_non0(const poy_cm_host *cm);
+/* Cost_matrix.Two_D.get_closest (src/cost_matrix.ml:1387-1428) */
+POY_API int32_t poy_cm_get_closest(const poy_cm_host *cm, int32_t a, int32_t b);
+
+POY_API poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *cm, poy_cm **out);
+POY_API void poy_cm_free(poy_ctx *ctx, poy_cm *cm);
+
+/* ---- sequence pool: replaces seq_CAML_create/prepend for batch inputs ------
+ * `data` holds nseq sequences back to back; sequence s is
+ * data[offsets[s] .. offsets[s+1]).  The *_dev variant takes DEVICE pointers
+ * (already resident in HBM); the plain variant takes HOST pointers and copies. */
+POY_API poy_status poy_pool_upload(poy_ctx *ctx, const uint8_t *data, const int64_t *offsets, int32_t nseq, poy_pool **out);
+POY_API poy_status poy_pool_from_device(poy_ctx *ctx, const uint8_t *d_data, const int64_t *d_offsets,
+                                const int64_t *h_offsets, int32_t nseq, poy_pool **out);
+POY_API void poy_pool_free(poy_ctx *ctx, poy_pool *pool);
+
+/* ---- batch twin of algn_CAML_cost_affine_3 (src/algn.c:2457-2515) ----------
+ * cost[p] = Sequence.Align.cost_2 (affine) of pool[a[p]] vs pool[b[p]]:
+ * full-matrix 4-state affine DO cost, either argument order, including the
+ * reference's even-row/last-column EV behaviour.
+ * a, b, cost are HOST arrays of n entries (the *_dev variant: DEVICE arrays). */
+POY_API poy_status poy_batch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                 const int32_t *a, const int32_t *b, int32_t *cost);
+POY_API poy_status poy_batch_cost_affine_dev(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                     const int32_t *d_a, const int32_t *d_b, int32_t *d_cost);
+
+/* ---- batch twin of algn_CAML_align_affine_3 (src/algn.c:2359-2447) ---------
+ * Ukkonen-banded affine DO alignment with the reference's threshold-doubling
+ * schedule, on-device traceback (backtrace_aff, src/algn.c:1715-1819) and
+ * median construction.  Requires len(pool[si[p]]) <= len(pool[sj[p]])
+ * (POY_ERR_ORDER otherwise); swaped[p] is the flag the OCaml caller passes
+ * (src/sequence.ml:636) and selects the traceback tie-break.
+ *
+ * Outputs, per pair p, exactly like the four result `struct seq`s the caller
+ * allocates with capacity cap_p = len_i + len_j + 2 and the stub fills by
+ * prepending: each of median / medianwg / resi / resj is a packed byte buffer;
+ * pair p owns the slot [out_off[p], out_off[p] + cap_p) and its sequence is
+ * RIGHT-justified in that slot (begin = slot_end - len), out_len[4*p + {0,1,2,3}]
+ * = lengths of median, medianwg, resi, resj.  Any output pointer may be NULL.
+ * stats (optional, n x 4 int32): iterations, final T, final k, band cells / 1024. */
+POY_API poy_status poy_batch_align_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                  const int32_t *si, const int32_t *sj, const uint8_t *swaped,
+                                  const int64_t *out_off, int32_t *cost, uint8_t *median,
+                                  uint8_t *medianwg, uint8_t *resi, uint8_t *resj, int32_t *out_len,
+                                  int32_t *stats);
+/* same, all array arguments are DEVICE pointers except out_off_host (needed to size waves) */
+POY_API poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                      const int32_t *d_si, const int32_t *d_sj, const uint8_t *d_swaped,
+                                      const int32_t *h_si, const int32_t *h_sj,
+                                      const int64_t *d_out_off, int32_t *d_cost, uint8_t *d_median,
+                                      uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
+                                      int32_t *d_out_len, int32_t *d_stats);
+
+/* ---- INT32 / DPX issue-rate micro-benchmark (roofline denominator) ---------
+ * Runs independent chains of one instruction class at full occupancy and
+ * returns thread-level operations per second.  kind: 0 IADD3, 1 IMNMX (min),
+ * 2 VIADDMNMX (__viaddmin_s32), 3 VIMNMX3 (__vimin3_s32), 4 mixed add+viaddmin
+ * in the ratio of the cost-only cell. */
+POY_API poy_status poy_microbench_int(poy_ctx *ctx, int32_t kind, double *ops_per_second, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POY5_B200_H */

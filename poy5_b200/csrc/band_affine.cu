@@ -1,0 +1,444 @@
+// Ukkonen-banded affine DO alignment with direction matrix, and the traceback that
+// builds the median: batch twin of algn_CAML_align_affine_3 (src/algn.c:2359-2447) =
+// algn_newkk_test_aff / algn_newkk_fill_a_row_aff / ASSIGN_MINIMUM / algn_fill_gapnum
+// (src/algn.c:2186-2306, 2113-2180, 1936-1981, 126-176) + backtrace_aff (:1715-1819).
+//
+// Band geometry (src/algn.c:2256-2257, 2130-2131): row i covers columns
+// [max(i-k,0), min(i+delta+k, lastj)], delta = lastj-lasti; the first cell of a row is
+// a "left border" (EH = INF), the cell j = i+delta+k a "right border" (EV = INF).
+// In diagonal coordinates d = j - i + k the band is d in [0, B), B = delta + 2k + 1.
+//
+// Parallelisation: one WARP per pair, anti-diagonal wavefront.  Lane t owns the D
+// consecutive diagonals [t*D, (t+1)*D) and keeps, per diagonal, only the state of the
+// LATEST cell on it (CB, EV, EH, EB and the two gap counters) in registers.  Cells of
+// one anti-diagonal a = i + j all have d = a + k (mod 2), so a step updates every
+// other diagonal in place: the left neighbour (i, j-1) is the latest cell of diagonal
+// d-1, the upper neighbour (i-1, j) the latest cell of d+1, the diagonal neighbour the
+// previous cell of d itself.  Only the strip edges cross lanes: one __shfl_up (even
+// sub-step) or one __shfl_down (odd sub-step) of four values.
+//
+// Direction storage: the reference keeps a (leni x (lenj+1)) unsigned-short matrix
+// (0.2 GB at 10 kb); here only band cells are stored, one byte each, anti-diagonal
+// major so that a warp's stores of one step are contiguous: cell (i,j) lives at
+// dir[(i+j) * stride + ((j-i+k) >> 1)].  The 15-bit mask of src/algn.c:1185-1199 is
+// reduced, using the per-pair `swaped` flag that fixes the traceback priorities
+// (choose_dir, :1594-1619), to the 7 bits the traceback can observe:
+//   bits 0-1  mode chosen from `todo`   (0 vertical, 1 horizontal, 2 block diagonal, 3 align)
+//   bits 2-3  mode chosen after an align step (same coding, from the ALIGN_TO_* ties)
+//   bit 4     vertical run stops here   (END_VERTICAL | HORIZONTAL_EQ_VERTICAL)
+//   bit 5     horizontal run stops here (END_HORIZONTAL | HORIZONTAL_EQ_VERTICAL)
+//   bit 6     block-diagonal run stops here (END_BLOCK)
+//
+// State that the reference leaves behind from one band fill to the next (its row
+// buffers are not re-initialised between threshold doublings): row 0 of EB and
+// EH[0][0].  Both are carried explicitly per pair (PairState.eh00, the eb row).
+#include <type_traits>
+#include "common.cuh"
+
+struct CellIn {
+    int lCB, lEH, lG1, lG2;   // (i, j-1)
+    int uCB, uEV, uG1, uG2;   // (i-1, j)
+    int dCB, dEV, dEH, dEB, dG1, dG2;  // (i-1, j-1)
+};
+struct CellOut {
+    int CB, EV, EH, EB, G1, G2;
+    int fin;
+    unsigned dirbyte;
+};
+
+// compile-time loop: indices reach the body as constants, so the per-diagonal state arrays are
+// scalar-replaced into registers (a plain `#pragma unroll` loop left them in local memory)
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (N > 0) {
+        static_for<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
+
+__device__ __forceinline__ int imax_(int a, int b) { return a > b ? a : b; }
+__device__ __forceinline__ int imin_(int a, int b) { return a < b ? a : b; }
+
+// One band cell.  r = row parameters of i, c = column parameters of j.
+__device__ __forceinline__ void band_cell(const CellIn &in, const int4 r, const int4 c, const int *s_cost16, int GO,
+                                          bool lb, bool rb, bool jpos, int swaped, CellOut &o) {
+    unsigned stopH = 0, stopV = 0, stopB = 0;
+    int EH, EV, EB, CB;
+    if (!lb) {
+        const int ext = in.lEH + c.x, opn = in.lCB + c.y;
+        if (ext < opn) EH = ext; else { EH = opn; stopH = 1; }
+    } else EH = POY_INF;
+    if (!rb) {
+        const int ext = in.uEV + r.x, opn = in.uCB + r.y;
+        if (ext < opn) EV = ext; else { EV = opn; stopV = 1; }
+    } else EV = POY_INF;
+    unsigned a2 = 0;  // bit0 A2A, bit1 A2V, bit2 A2H, bit3 A2D
+    if (jpos) {
+        // at the left border the reference's "previous column symbol" is the column symbol itself
+        const bool pg_j = lb ? ((c.w & PF_HASGAP) != 0) : ((c.w & PF_PREVGAP) != 0);
+        const bool both = (r.w & c.w & PF_HASGAP) != 0;
+        const bool clean = !(r.w & PF_PREVGAP) && !pg_j;
+        const int dg = both ? 0 : POY_INF;
+        const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
+        {
+            const int ext = in.dEB + dg, opn = in.dCB + od;
+            if (ext < opn) EB = ext; else { EB = opn; stopB = 1; }
+        }
+        const int diag = s_cost16[(r.w & 15) * 16 + (c.w & 15)];
+        const int xgo = c.z < r.z ? r.z : c.z;
+        int a = in.dCB + diag;
+        const int v = (r.w & PF_HASGAP) ? in.dEV + diag + c.z : in.dEV + diag;
+        const int h = (c.w & PF_HASGAP) ? in.dEH + diag + r.z : in.dEH + diag;
+        const int d = in.dEB + diag + xgo;
+        a2 = 1;
+        if (a >= v) { if (a > v) { a = v; a2 = 2; } else a2 |= 2; }
+        if (a >= h) { if (a > h) { a = h; a2 = 4; } else a2 |= 4; }
+        if (a >= d) { if (a > d) { a = d; a2 = 8; } else a2 |= 8; }
+        CB = a;
+    } else { CB = POY_INF; EB = POY_INF; }
+    // final minimum, order H, V, D, A (ASSIGN_MINIMUM)
+    unsigned m = 4;  // bit0 DO_A, bit1 DO_V, bit2 DO_H, bit3 DO_D
+    int fin = EH;
+    if (fin >= EV) { if (fin > EV) { fin = EV; m = 2; } else m |= 2; }
+    if (fin >= EB) { if (fin > EB) { fin = EB; m = 8; } else m |= 8; }
+    if (fin >= CB) { if (fin > CB) { fin = CB; m = 1; } else m |= 1; }
+    if (fin == EH && EH == EV) { stopH = 1; stopV = 1; }
+    // gap counters (algn_fill_gapnum): max-plus over the chosen predecessors, unsigned short
+    int c1 = -1, c2 = -1;
+    if (m & 9) { c1 = in.dG1; c2 = in.dG2; }
+    if (m & 4) { c1 = imax_(c1, in.lG1 + 1); c2 = imax_(c2, in.lG2); }
+    if (m & 2) { c1 = imax_(c1, in.uG1); c2 = imax_(c2, in.uG2 + 1); }
+    o.G1 = c1 & 0xFFFF; o.G2 = c2 & 0xFFFF;
+    // compress to the traceback byte
+    unsigned todo, nxt;
+    if (!swaped) {
+        todo = (m & 2) ? 0u : (m & 4) ? 1u : (m & 8) ? 2u : 3u;
+        nxt = (a2 & 2) ? 0u : (a2 & 4) ? 1u : (a2 & 8) ? 2u : 3u;
+    } else {
+        todo = (m & 4) ? 1u : (m & 2) ? 0u : (m & 8) ? 2u : 3u;
+        nxt = (a2 & 4) ? 1u : (a2 & 2) ? 0u : (a2 & 8) ? 2u : 3u;
+    }
+    o.dirbyte = todo | (nxt << 2) | (stopV << 4) | (stopH << 5) | (stopB << 6);
+    o.CB = CB; o.EV = EV; o.EH = EH; o.EB = EB; o.fin = fin;
+}
+
+// ---- warp-per-pair register-resident band fill ------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+k_band_fill(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
+            const int *__restrict__ h0v, const BandJob *__restrict__ jobs, int njobs, int *counter,
+            PairState *state, int *ebrow, uint8_t *dir) {
+    constexpr int H = D / 2;  // cells per lane per sub-step
+    __shared__ int s_cost16[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_cost16[x] = cm->cost16[x];
+    __syncthreads();
+    const int GO = cm->gap_open;
+    const int lane = threadIdx.x & 31;
+
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= njobs) break;
+        const BandJob J = jobs[job];
+        const int lasti = J.lasti, lastj = J.lastj, k = J.k, swaped = J.swaped;
+        if (lasti == 0) continue;  // no rows: nothing to fill (k_band_finish supplies the cost)
+        const int delta = lastj - lasti, B = delta + 2 * k + 1;
+        const int4 *rp = rowp + J.off_i;
+        const int4 *cp = colp + J.off_j;
+        const int *h0 = h0v + J.off_j;
+        int *eb = ebrow + J.eb_off;
+        PairState *st = state + J.pair;
+        uint8_t *dbase = dir + J.dir_off;
+        const int stride = J.stride;
+        const int d0 = lane * D;
+        const int eh00 = st->eh00;
+
+        int CB[D], EV[D], EH[D], EB[D], G1[D], G2[D];
+        static_for<D>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const int d = d0 + u, j0 = d - k;
+            if (d < B && j0 >= 0 && j0 <= lastj) {  // row 0 as set up by the band fill (src/algn.c:2222-2247, A1)
+                CB[u] = h0[j0];
+                EH[u] = j0 == 0 ? eh00 : h0[j0];
+                EV[u] = POY_INF;
+                EB[u] = eb[j0];
+                G1[u] = j0 & 0xFFFF; G2[u] = 0;
+            } else {
+                CB[u] = EV[u] = EH[u] = EB[u] = POY_INF; G1[u] = G2[u] = 0;
+            }
+        });
+        __syncwarp();
+
+        const int a_end = lasti + lastj;
+        for (int a = (k & 1); a <= a_end; a += 2) {
+            // ---- even diagonals: anti-diagonal a; left neighbour of slot 0 comes from lane-1 ----
+            {
+                int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
+                int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
+                int sG1 = __shfl_up_sync(0xffffffffu, G1[D - 1], 1);
+                int sG2 = __shfl_up_sync(0xffffffffu, G2[D - 1], 1);
+                unsigned long long packed = 0;
+                static_for<H>([&](auto hc) {
+                    constexpr int h = decltype(hc)::value;
+                    constexpr int u = 2 * h;
+                    const int d = d0 + u;
+                    const int i = (a - d + k) >> 1, j = a - i;
+                    if (d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) {
+                        CellIn in;
+                        if constexpr (u == 0) { in.lCB = sCB; in.lEH = sEH; in.lG1 = sG1; in.lG2 = sG2; }
+                        else { constexpr int ul = u > 0 ? u - 1 : 0; in.lCB = CB[ul]; in.lEH = EH[ul]; in.lG1 = G1[ul]; in.lG2 = G2[ul]; }
+                        in.uCB = CB[u + 1]; in.uEV = EV[u + 1]; in.uG1 = G1[u + 1]; in.uG2 = G2[u + 1];
+                        in.dCB = CB[u]; in.dEV = EV[u]; in.dEH = EH[u]; in.dEB = EB[u]; in.dG1 = G1[u]; in.dG2 = G2[u];
+                        CellOut o;
+                        band_cell(in, rp[i], cp[j], s_cost16, GO, d == 0 || j == 0, d == B - 1, j > 0, swaped, o);
+                        CB[u] = o.CB; EV[u] = o.EV; EH[u] = o.EH; EB[u] = o.EB; G1[u] = o.G1; G2[u] = o.G2;
+                        packed |= (unsigned long long)o.dirbyte << (8 * h);
+                        if (!(i & 1) && (d <= 1 || i >= lasti - 1)) eb[j] = o.EB;
+                    }
+                });
+                if (a >= 1) {
+                    uint8_t *p = dbase + (size_t)a * stride + lane * H;
+                    if (H == 1) *p = (uint8_t)packed;
+                    else if (H == 2) *(uint16_t *)p = (uint16_t)packed;
+                    else if (H == 4) *(uint32_t *)p = (uint32_t)packed;
+                    else *(unsigned long long *)p = packed;
+                }
+            }
+            // ---- odd diagonals: anti-diagonal a+1; upper neighbour of slot D-1 comes from lane+1 ----
+            if (a + 1 <= a_end) {
+                int sCB = __shfl_down_sync(0xffffffffu, CB[0], 1);
+                int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
+                int sG1 = __shfl_down_sync(0xffffffffu, G1[0], 1);
+                int sG2 = __shfl_down_sync(0xffffffffu, G2[0], 1);
+                unsigned long long packed = 0;
+                static_for<H>([&](auto hc) {
+                    constexpr int h = decltype(hc)::value;
+                    constexpr int u = 2 * h + 1;
+                    const int d = d0 + u;
+                    const int i = (a + 1 - d + k) >> 1, j = a + 1 - i;
+                    if (d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) {
+                        CellIn in;
+                        in.lCB = CB[u - 1]; in.lEH = EH[u - 1]; in.lG1 = G1[u - 1]; in.lG2 = G2[u - 1];
+                        if constexpr (u == D - 1) { in.uCB = sCB; in.uEV = sEV; in.uG1 = sG1; in.uG2 = sG2; }
+                        else { constexpr int uu = u < D - 1 ? u + 1 : u; in.uCB = CB[uu]; in.uEV = EV[uu]; in.uG1 = G1[uu]; in.uG2 = G2[uu]; }
+                        in.dCB = CB[u]; in.dEV = EV[u]; in.dEH = EH[u]; in.dEB = EB[u]; in.dG1 = G1[u]; in.dG2 = G2[u];
+                        CellOut o;
+                        band_cell(in, rp[i], cp[j], s_cost16, GO, j == 0, d == B - 1, j > 0, swaped, o);
+                        CB[u] = o.CB; EV[u] = o.EV; EH[u] = o.EH; EB[u] = o.EB; G1[u] = o.G1; G2[u] = o.G2;
+                        packed |= (unsigned long long)o.dirbyte << (8 * h);
+                        if (!(i & 1) && (d <= 1 || i >= lasti - 1)) eb[j] = o.EB;
+                    }
+                });
+                uint8_t *p = dbase + (size_t)(a + 1) * stride + lane * H;
+                if (H == 1) *p = (uint8_t)packed;
+                else if (H == 2) *(uint16_t *)p = (uint16_t)packed;
+                else if (H == 4) *(uint32_t *)p = (uint32_t)packed;
+                else *(unsigned long long *)p = packed;
+            }
+        }
+        // result: the cell (lasti, lastj) is the latest cell of diagonal delta + k
+        const int dstar = delta + k;
+        if (lane == dstar / D) {
+            static_for<D>([&](auto uc) {
+                constexpr int u = decltype(uc)::value;
+                if (u == dstar % D) {
+                    st->cost = imin_(imin_(EH[u], EV[u]), imin_(EB[u], CB[u]));
+                    st->gapnum = imax_(G1[u], G2[u]);
+                }
+            });
+        }
+        if (lane == 0 && imin_(k, lasti) >= 2) st->eh00 = POY_INF;  // an even row wrote EH[.][0] = INF into row buffer 0
+        __syncwarp();
+    }
+}
+
+// ---- generic fallback: one CTA per pair, diagonal state in global memory -------------------
+// Used for bands wider than the register-resident kernel covers (very dissimilar pairs).
+// work layout per job: 6 planes of `wstride` ints (CB, EV, EH, EB, G1, G2).
+__global__ void __launch_bounds__(256)
+k_band_generic(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
+               const int *__restrict__ h0v, const BandJob *__restrict__ jobs, int njobs, PairState *state, int *ebrow,
+               uint8_t *dir, int *work, size_t work_stride) {
+    __shared__ int s_cost16[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_cost16[x] = cm->cost16[x];
+    __syncthreads();
+    const int GO = cm->gap_open;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        const BandJob J = jobs[job];
+        const int lasti = J.lasti, lastj = J.lastj, k = J.k, swaped = J.swaped;
+        if (lasti == 0) continue;
+        const int delta = lastj - lasti, B = delta + 2 * k + 1;
+        const int4 *rp = rowp + J.off_i;
+        const int4 *cp = colp + J.off_j;
+        const int *h0 = h0v + J.off_j;
+        int *eb = ebrow + J.eb_off;
+        PairState *st = state + J.pair;
+        uint8_t *dbase = dir + J.dir_off;
+        const int stride = J.stride;
+        const size_t ws = work_stride / 6;
+        int *wCB = work + (size_t)blockIdx.x * work_stride, *wEV = wCB + ws, *wEH = wEV + ws, *wEB = wEH + ws,
+            *wG1 = wEB + ws, *wG2 = wG1 + ws;
+        const int eh00 = st->eh00;
+        for (int d = threadIdx.x; d < B; d += blockDim.x) {
+            const int j0 = d - k;
+            if (j0 >= 0 && j0 <= lastj) {
+                wCB[d] = h0[j0]; wEH[d] = j0 == 0 ? eh00 : h0[j0]; wEV[d] = POY_INF; wEB[d] = eb[j0];
+                wG1[d] = j0 & 0xFFFF; wG2[d] = 0;
+            } else {
+                wCB[d] = wEV[d] = wEH[d] = wEB[d] = POY_INF; wG1[d] = wG2[d] = 0;
+            }
+        }
+        __syncthreads();
+        const int a_end = lasti + lastj;
+        for (int a = 1; a <= a_end; ++a) {
+            const int par = (a + k) & 1;
+            // valid diagonals: i = (a-d+k)/2 in [1,lasti], j = a-i in [0,lastj]
+            for (int d = 2 * threadIdx.x + par; d < B; d += 2 * blockDim.x) {
+                const int i = (a - d + k) >> 1, j = a - i;
+                if (i >= 1 && i <= lasti && j >= 0 && j <= lastj) {
+                    CellIn in;
+                    if (d > 0) { in.lCB = wCB[d - 1]; in.lEH = wEH[d - 1]; in.lG1 = wG1[d - 1]; in.lG2 = wG2[d - 1]; }
+                    else { in.lCB = in.lEH = POY_INF; in.lG1 = in.lG2 = 0; }
+                    if (d + 1 < B) { in.uCB = wCB[d + 1]; in.uEV = wEV[d + 1]; in.uG1 = wG1[d + 1]; in.uG2 = wG2[d + 1]; }
+                    else { in.uCB = in.uEV = POY_INF; in.uG1 = in.uG2 = 0; }
+                    in.dCB = wCB[d]; in.dEV = wEV[d]; in.dEH = wEH[d]; in.dEB = wEB[d]; in.dG1 = wG1[d]; in.dG2 = wG2[d];
+                    CellOut o;
+                    band_cell(in, rp[i], cp[j], s_cost16, GO, d == 0 || j == 0, d == B - 1, j > 0, swaped, o);
+                    wCB[d] = o.CB; wEV[d] = o.EV; wEH[d] = o.EH; wEB[d] = o.EB; wG1[d] = o.G1; wG2[d] = o.G2;
+                    dbase[(size_t)a * stride + (d >> 1)] = (uint8_t)o.dirbyte;
+                    if (!(i & 1) && (d <= 1 || i >= lasti - 1)) eb[j] = o.EB;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int d = delta + k;
+            st->cost = imin_(imin_(wEH[d], wEV[d]), imin_(wEB[d], wCB[d]));
+            st->gapnum = imax_(wG1[d], wG2[d]);
+            if (imin_(k, lasti) >= 2) st->eh00 = POY_INF;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- traceback: backtrace_aff (src/algn.c:1715-1819) -------------------------------------------
+// One thread per pair.  Results are written right to left into the caller's
+// capacity-(leni+lenj+2) slots, i.e. exactly like seq_prepend fills a struct seq.
+__global__ void __launch_bounds__(128)
+k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, const BandJob *__restrict__ jobs, int njobs,
+            const uint8_t *__restrict__ done, const uint8_t *__restrict__ dir, const int64_t *__restrict__ out_off, uint8_t *median, uint8_t *medianwg,
+            uint8_t *resi, uint8_t *resj, int *out_len) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= njobs) return;
+    const BandJob J = jobs[t];
+    if (done && !done[J.pair]) return;  // this pair's band is not final yet
+    const uint8_t *si = data + J.off_i, *sj = data + J.off_j;
+    const int k = J.k, swaped = J.swaped;
+    (void)swaped;
+    const int B = (J.lastj - J.lasti) + 2 * k + 1;
+    const uint8_t *db = dir + J.dir_off;
+    const int stride = J.stride;
+    const int cap = J.lasti + J.lastj + 4;  // len_i + len_j + 2
+    const int64_t base = out_off[J.pair];
+    uint8_t *pm = median ? median + base + cap : nullptr;
+    uint8_t *pw = medianwg ? medianwg + base + cap : nullptr;
+    uint8_t *pi = resi ? resi + base + cap : nullptr;
+    uint8_t *pj = resj ? resj + base + cap : nullptr;
+    int nm = 0, nw = 0, ni = 0, nj = 0;
+    int first_m = -1;  // value currently at the front of median
+#define PUT(ptr, cnt, v) do { ++(cnt); if (ptr) *(--(ptr)) = (uint8_t)(v); } while (0)
+#define PUT_M(v) do { first_m = (v); PUT(pm, nm, v); } while (0)
+#define INDEL(sym) do { if (!((sym) & POY_GAP)) { PUT_M((sym) | POY_GAP); PUT(pw, nw, (sym) | POY_GAP); } else PUT(pw, nw, POY_GAP); } while (0)
+    int i = J.lasti, j = J.lastj;
+    int ic = si[i], jc = sj[j];
+    int mode = 4;  // 0 vertical, 1 horizontal, 2 diagonal, 3 align, 4 todo
+    while (i != 0 && j != 0) {
+        int d = j - i + k;
+        d = d < 0 ? 0 : (d >= B ? B - 1 : d);
+        const unsigned b = db[(size_t)(i + j) * stride + (d >> 1)];
+        if (mode == 4) mode = b & 3;
+        if (mode == 0) {
+            if (b & 16) mode = 4;
+            INDEL(ic);
+            PUT(pi, ni, ic); PUT(pj, nj, POY_GAP);
+            --i; ic = si[i];
+        } else if (mode == 1) {
+            if (b & 32) mode = 4;
+            INDEL(jc);
+            PUT(pi, ni, POY_GAP); PUT(pj, nj, jc);
+            --j; jc = sj[j];
+        } else if (mode == 2) {
+            if (b & 64) mode = 4;
+            PUT(pi, ni, ic); PUT(pj, nj, jc); PUT(pw, nw, POY_GAP);
+            --i; --j; ic = si[i]; jc = sj[j];
+        } else {
+            mode = (b >> 2) & 3;
+            const int prep = cm->median32[((ic & POY_NOGAP) << 5) + (jc & POY_NOGAP)];
+            PUT_M(prep); PUT(pw, nw, prep);
+            PUT(pi, ni, ic); PUT(pj, nj, jc);
+            --i; --j; ic = si[i]; jc = sj[j];
+        }
+    }
+    while (i != 0) {
+        INDEL(ic);
+        PUT(pi, ni, ic); PUT(pj, nj, POY_GAP);
+        --i; ic = si[i];
+    }
+    while (j != 0) {
+        INDEL(jc);
+        PUT(pi, ni, POY_GAP); PUT(pj, nj, jc);
+        --j; jc = sj[j];
+    }
+    PUT(pi, ni, POY_GAP); PUT(pj, nj, POY_GAP); PUT(pw, nw, POY_GAP);
+    if (first_m != POY_GAP) PUT_M(POY_GAP);
+#undef PUT
+#undef PUT_M
+#undef INDEL
+    if (out_len) {
+        out_len[4 * J.pair + 0] = nm; out_len[4 * J.pair + 1] = nw;
+        out_len[4 * J.pair + 2] = ni; out_len[4 * J.pair + 3] = nj;
+    }
+}
+
+cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                             int dclass, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+    if (njobs <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
+    if (e != cudaSuccess) return e;
+    int blocks = (njobs + 3) / 4;
+    const int maxb = ctx->sm_count * 4;
+    if (blocks > maxb) blocks = maxb;
+#define LAUNCH_BAND(DD) k_band_fill<DD><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, \
+                                        d_jobs, njobs, d_counter, d_state, d_ebrow, d_dir)
+    switch (dclass) {
+        case 2: LAUNCH_BAND(2); break;
+        case 4: LAUNCH_BAND(4); break;
+        case 8: LAUNCH_BAND(8); break;
+        case 16: LAUNCH_BAND(16); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef LAUNCH_BAND
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_band_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                                PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_work, size_t work_stride,
+                                int blocks) {
+    if (njobs <= 0) return cudaSuccess;
+    k_band_generic<<<blocks, 256, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs, d_state,
+                                                     d_ebrow, d_dir, d_work, work_stride);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_traceback(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                             const uint8_t *d_done, const uint8_t *d_dir, const int64_t *d_out_off, uint8_t *d_median,
+                             uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj, int *d_out_len) {
+    if (njobs <= 0) return cudaSuccess;
+    k_traceback<<<(njobs + 127) / 128, 128, 0, ctx->stream>>>(cm->d, pool->d_data, d_jobs, njobs, d_done, d_dir, d_out_off, d_median,
+                                                              d_medianwg, d_resi, d_resj, d_out_len);
+    ctx->launches++;
+    return cudaGetLastError();
+}

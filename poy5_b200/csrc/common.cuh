@@ -1,0 +1,121 @@
+// Internal declarations shared by the kernels and the host side of libpoy5b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/poy5_b200.h"
+
+#define POY_INF 1000000  // HIGH_NUM, src/algn.c:37 -- added to, never saturated
+#define POY_GAP 16       // TMPGAP, src/algn.c:1202
+#define POY_NOGAP 15     // NTMPGAP
+
+// ---- device-resident cost model ------------------------------------------------
+struct DevCM {
+    int cost16[256];     // cost[(a&15)][(b&15)], the only part the affine kernels index (src/algn.c:2073, A5)
+    int cost32[1024];    // full table (linear-gap kernels, worst/verify)
+    int worst32[1024];
+    uint8_t median32[1024];
+    int prepend[32];
+    int tail[32];
+    int gapext[32];      // cost[a][gap]  (HAS_GAP_EXTENSION, src/algn.c:1220)
+    int gap_open;
+    int model;
+    int min_non0;
+    int max_entry;       // largest table entry; host-side domain check
+};
+
+// ---- per-base gap parameters, one int4 per base per role ------------------------
+// x = extension cost when the gap continues through this base
+//     (row role: si_vertical_extension, src/algn.c:2063-2065; column role:
+//      sj_horizontal_extension after the [1] overwrite, :2028-2035)
+// y = opening cost: go + ge  (si_gap_opening + si_gap_extension)
+// z = go                     (HAS_GAP_OPENING, :1240-1253)
+// w = flags: bits 0-3 code&15, bit 4 code has the gap bit, bit 5 previous base has the gap bit
+#define PF_HASGAP 16
+#define PF_PREVGAP 32
+
+struct poy_cm {
+    DevCM *d;
+    poy_cm_host h;
+    int min_non0, max_entry;
+};
+
+struct poy_pool {
+    uint8_t *d_data;       // packed codes
+    int64_t *d_off;        // nseq+1 offsets
+    int4 *d_rowp;          // per-base parameters, row role
+    int4 *d_colp;          // per-base parameters, column role
+    int *d_h0;             // banded entry point: CB[0][j] = sum of in-loop hext (src/algn.c:2244)
+    int *d_g0;             // cost-only entry point: EH[0][j] - GO = sum of prepend (src/algn.c:1847)
+    uint8_t *d_gapfree;    // per sequence: 1 if no base at index >= 1 carries the gap bit
+    int64_t *h_off;        // host copy of the offsets
+    int32_t nseq;
+    int64_t nbytes;
+    bool owns_data;
+    const poy_cm *params_for;  // cost model the parameters were computed for
+};
+
+struct poy_ctx {
+    int device;
+    cudaStream_t stream;
+    bool owns_stream;
+    int sm_count;
+    uint64_t arena_limit;
+    uint64_t launches;
+    char err[512];
+    // grow-only device scratch
+    void *d_scratch[8];
+    size_t scratch_cap[8];
+    void *h_pinned[4];
+    size_t pinned_cap[4];
+};
+
+// ---- work descriptors ----------------------------------------------------------------
+struct CostJob {          // one cost-only alignment; rows = shorter sequence
+    int64_t off_i, off_j; // pool offsets of the row / column sequence
+    int lasti, lastj;     // last valid index (= len - 1)
+    int out;              // index into the cost output array
+    int gapfree;          // both sequences free of gap bits
+};
+
+struct BandJob {          // one band fill of one pair
+    int64_t off_i, off_j;
+    int lasti, lastj;
+    int k;                // half band (already clamped, src/algn.c:2195-2196)
+    int pair;             // index into the per-pair state arrays
+    int swaped;
+    int stride;           // bytes per anti-diagonal in the direction arena
+    int64_t dir_off;      // byte offset of this pair's direction block in the arena
+    int64_t eb_off;       // int offset of this pair's stale-EB row in the state arena
+};
+
+struct PairState {        // survives across band fills of the same pair
+    int T;                // current threshold
+    int eh00;             // EH[0][0] as left behind by the previous fill
+    int cost;             // result of the latest fill
+    int gapnum;           // max gap-count of the latest fill
+    int iterations;
+    int done;
+    long long cells;
+};
+
+// launchers (defined in the .cu files)
+cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool);
+cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, const int *d_a, const int *d_b,
+                                   CostJob *d_free, CostJob *d_gen, int *d_counts);
+cudaError_t launch_cost_affine_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs_free,
+                                     const CostJob *d_jobs_gen, const int *d_counts, int *d_counters, int4 *d_bound,
+                                     size_t bound_stride, int blocks, int *d_cost);
+cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                             int dclass, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
+cudaError_t launch_band_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                                PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_work, size_t work_stride,
+                                int blocks);
+cudaError_t launch_band_finish(poy_ctx *ctx, const BandJob *d_jobs, int njobs, PairState *d_state, uint8_t *d_done,
+                               const int *d_g0, int gap_open);
+cudaError_t launch_traceback(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                             const uint8_t *d_done, const uint8_t *d_dir, const int64_t *d_out_off, uint8_t *d_median,
+                             uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj, int *d_out_len);
+cudaError_t launch_gather_cost(poy_ctx *ctx, const PairState *d_state, int n, int *d_cost);
+cudaError_t launch_fill_int(poy_ctx *ctx, int *d, int64_t n, int v);
+cudaError_t launch_microbench(poy_ctx *ctx, int kind, int iters, unsigned long long *d_cycles, int *d_sink,
+                              float *ms, double *ops);

@@ -1,0 +1,271 @@
+// Batched cost-only affine DO alignment: the batch twin of algn_CAML_cost_affine_3 ->
+// algn_fill_plane_3_aff_nobt (src/algn.c:2457-2515, 1822-1863, 1987-2110).
+//
+// One WARP per pair.  The full leni x lenj plane is swept in column blocks of
+// W = 32*C columns; inside a block lane t owns the C columns [t*C, (t+1)*C) and
+// the warp runs a skewed wavefront: at step s lane t computes row s - t + 1 of
+// its strip, so the value a lane needs from its left neighbour (same row, one
+// column to the left) was produced exactly one step earlier and arrives through
+// __shfl_up_sync.  All DP state (the previous row of CB/EV/EH/EB for the C
+// owned columns) lives in registers; the only memory traffic per step is one
+// 16-byte row-parameter load per lane, and -- for sequences wider than W -- one
+// 16-byte boundary-column store/load per step per warp.
+//
+// Recurrences per cell (i,j), ' = cell (i-1,j-1)   (src/algn.c:1260-1433):
+//   EH = min(EH[i][j-1] + hext_j, CB[i][j-1] + go_j + ge_j)
+//   EV = min(EV[i-1][j] + vext_i, CB[i-1][j] + go_i + ge_i)
+//   EB = min(EB' + (both gaps ? 0 : INF), CB' + (both ? (clean ? 0 : 2GO) : INF))
+//   CB = diag + min(CB', EV' + [ic has gap]go_j, EH' + [jc has gap]go_i, EB' + max(go_i,go_j))
+// evaluated with the DPX fused add-min instructions (__viaddmin_s32, __vimin3_s32).
+//
+// Two instantiations: GAPFREE (neither sequence contains a gap-bit symbol, the
+// case of all leaf/observed DNA) drops the EB state -- provably EB >= CB in every
+// cell when every table entry is <= INF, so it can never win a minimum -- and
+// folds min3(CB,EV,EH) of the diagonal cell into one carried value; the general
+// instantiation keeps all four states.
+//
+// The reference's row-buffer aliasing is reproduced in closed
+// form: for lenj >= 3 its only observable effect is that on every even row i>=2
+// EV[i][lastj] is computed from clobbered predecessors (both INF), i.e.
+// EV[i][lastj] = INF + min(vext_i, go_i+ge_i).  Pairs with lenj <= TINY_L are run
+// through an exact emulation of the reference's flat scratch layout instead.
+#include "common.cuh"
+
+#define TINY_L 8
+
+__device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+
+// ---- exact emulation for tiny pairs (lane 0 only) -------------------------------
+__device__ int cost_affine_tiny(const DevCM *cm, const int *s_cost16, const int4 *rp, const int4 *cp, const int *g0,
+                                int lasti, int lastj) {
+    const int L = lastj + 1, stride = lastj + 2, go = cm->gap_open;
+    int M[9 * TINY_L + 16];  // CB, EB, EV, EH row pairs at 0, 2L, 4L, 6L (src/algn.c:2489-2492)
+    for (int x = 0; x < 9 * TINY_L + 16; ++x) M[x] = 0;
+    int *cb0 = M, *eb0 = M + 2 * L, *ev0 = M + 4 * L, *eh0 = M + 6 * L;
+    cb0[0] = 0; eb0[0] = POY_INF; eh0[0] = go; ev0[0] = go;
+    for (int j = 1; j <= lastj; ++j) {
+        eh0[j] = go + g0[j];
+        cb0[j] = POY_INF; eb0[j] = POY_INF; ev0[j] = POY_INF;
+    }
+    for (int i = 1; i <= lasti; ++i) {
+        const int cur = (i & 1) * stride, prv = ((i & 1) ^ 1) * stride;
+        int *CB = cb0 + cur, *EB = eb0 + cur, *EV = ev0 + cur, *EH = eh0 + cur;
+        const int *pCB = cb0 + prv, *pEB = eb0 + prv, *pEV = ev0 + prv, *pEH = eh0 + prv;
+        const int4 r = rp[i];
+        EH[0] = POY_INF;
+        const int r0 = pEV[0] + r.x;
+        EH[0] = POY_INF; CB[0] = r0; EB[0] = POY_INF; EV[0] = r0; CB[0] = POY_INF;
+        for (int j = 1; j <= lastj; ++j) {
+            const int4 c = cp[j];
+            int ext = EH[j - 1] + c.x, opn = CB[j - 1] + c.y;
+            EH[j] = ext < opn ? ext : opn;
+            ext = pEV[j] + r.x; opn = pCB[j] + r.y;
+            EV[j] = ext < opn ? ext : opn;
+            const bool both = (r.w & c.w & PF_HASGAP) != 0, clean = ((r.w | c.w) & PF_PREVGAP) == 0;
+            ext = pEB[j - 1] + (both ? 0 : POY_INF);
+            opn = pCB[j - 1] + (both ? (clean ? 0 : 2 * go) : POY_INF);
+            EB[j] = ext < opn ? ext : opn;
+            const int diag = s_cost16[(r.w & 15) * 16 + (c.w & 15)];
+            int a = pCB[j - 1] + diag;
+            const int v = pEV[j - 1] + diag + ((r.w & PF_HASGAP) ? c.z : 0);
+            const int h = pEH[j - 1] + diag + ((c.w & PF_HASGAP) ? r.z : 0);
+            const int d = pEB[j - 1] + diag + (c.z < r.z ? r.z : c.z);
+            if (a > v) a = v;
+            if (a > h) a = h;
+            if (a > d) a = d;
+            CB[j] = a;
+        }
+    }
+    const int cur = lasti >= 1 ? (lasti & 1) * stride : 0;
+    int res = eh0[cur + lastj];
+    res = imin(res, ev0[cur + lastj]);
+    res = imin(res, eb0[cur + lastj]);
+    res = imin(res, cb0[cur + lastj]);
+    return res;
+}
+
+// ---- the wavefront kernel ------------------------------------------------------------
+template <int C, bool GAPFREE>
+__global__ void __launch_bounds__(128)
+k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
+              const int *__restrict__ g0v, const CostJob *__restrict__ jobs, const int *__restrict__ njobs_ptr, int *counter,
+              int4 *bound, size_t bound_stride, int *__restrict__ cost_out) {
+    constexpr int W = 32 * C;
+    __shared__ int s_cost16[256];
+    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_cost16[x] = cm->cost16[x];
+    __syncthreads();
+    const int GO = cm->gap_open;
+    const int njobs = *njobs_ptr;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int4 *bnd0 = bound + (size_t)warp_global * 2 * bound_stride;
+    int4 *bnd1 = bnd0 + bound_stride;
+
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(counter, 1);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= njobs) break;
+        const CostJob J = jobs[job];
+        const int lasti = J.lasti, lastj = J.lastj;
+        const int4 *rp = rowp + J.off_i;
+        const int4 *cp = colp + J.off_j;
+        const int *g0 = g0v + J.off_j;
+
+        if (lastj + 1 <= TINY_L) {
+            if (lane == 0) cost_out[J.out] = cost_affine_tiny(cm, s_cost16, rp, cp, g0, lasti, lastj);
+            continue;
+        }
+        if (lasti == 0) {  // no rows: minimum over row 0 at the last column (src/algn.c:2105-2109)
+            if (lane == 0) cost_out[J.out] = imin(GO + g0[lastj], POY_INF);
+            continue;
+        }
+
+        const int nb = (lastj + W - 1) / W;
+        const int jres = lastj - 1 - (nb - 1) * W;  // position of column lastj inside the last block
+        const int tl = jres / C, cl = jres % C;
+        for (int b = 0; b < nb; ++b) {
+            const int jb = b * W + lane * C;  // slot c <-> column jb + c + 1
+            const int4 *bin = (b & 1) ? bnd0 : bnd1;
+            int4 *bout = (b & 1) ? bnd1 : bnd0;
+            const bool last_block = (b == nb - 1);
+            const bool owns_last = last_block && lane == tl;
+
+            // per-column constants
+            int c_ext[C], c_opn[C], c_go[C], c_fl[C];
+            // previous-row state of the owned columns
+            int CBu[C], EVu[C], EHu[C], EBu[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jb + c + 1;
+                if (j <= lastj) {
+                    const int4 v = cp[j];
+                    c_ext[c] = v.x; c_opn[c] = v.y; c_go[c] = v.z;
+                    c_fl[c] = GAPFREE ? ((v.w & 15) << 2) : v.w;
+                    EHu[c] = GO + g0[j];
+                } else {
+                    c_ext[c] = 0; c_opn[c] = 0; c_go[c] = 0; c_fl[c] = 0;
+                    EHu[c] = POY_INF;
+                }
+                CBu[c] = POY_INF; EVu[c] = POY_INF; EBu[c] = POY_INF;
+                if (GAPFREE) EBu[c] = __vimin3_s32(CBu[c], EVu[c], EHu[c]);  // M = min3 of the cell
+            }
+            // cell (i-1, jb): diagonal predecessor of slot 0
+            int dCB, dEV, dEH, dEB;
+            if (jb == 0) { dCB = 0; dEV = GO; dEH = GO; dEB = POY_INF; }
+            else { dCB = POY_INF; dEV = POY_INF; dEH = GO + g0[jb]; dEB = POY_INF; }
+            if (GAPFREE) dEB = __vimin3_s32(dCB, dEV, dEH);
+            int ev_col0 = GO;  // EV[i][0] running sum (lane 0 of block 0), src/algn.c:2066-2070
+            int oCB = POY_INF, oEH = POY_INF, oEV = POY_INF, oEB = POY_INF;
+            int4 rnext = rp[1 <= lasti ? 1 : 0];
+            int4 bnext = make_int4(0, 0, 0, 0);
+            if (b > 0 && lane == 0) bnext = bin[1];
+
+            const int nsteps = lasti + 31;
+            for (int s = 0; s < nsteps; ++s) {
+                const int i = s - lane + 1;
+                int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
+                int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
+                int lEV = GAPFREE ? 0 : __shfl_up_sync(0xffffffffu, oEV, 1);
+                int lEB = __shfl_up_sync(0xffffffffu, oEB, 1);
+                if (i >= 1 && i <= lasti) {
+                    const int4 r = rnext;
+                    if (i < lasti) rnext = rp[i + 1];
+                    if (lane == 0) {
+                        if (b == 0) {
+                            ev_col0 += r.x;
+                            lCB = POY_INF; lEH = POY_INF; lEV = ev_col0;
+                            lEB = GAPFREE ? __vimin3_s32(POY_INF, ev_col0, POY_INF) : POY_INF;
+                        } else {
+                            lCB = bnext.x; lEH = bnext.y; lEV = bnext.z; lEB = bnext.w;
+                            if (i < lasti) bnext = bin[i + 1];
+                        }
+                    }
+                    int cbL = lCB, ehL = lEH;
+                    if (GAPFREE) {
+                        const int *rowbase = s_cost16 + (r.w & 15) * 16;
+                        const int ge_i = r.x;
+                        int mD = dEB;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const int diag = *(const int *)((const char *)rowbase + c_fl[c]);
+                            const int cb = mD + diag;
+                            const int eh = __viaddmin_s32(cbL, GO, ehL) + c_ext[c];
+                            const int ev = __viaddmin_s32(CBu[c], GO, EVu[c]) + ge_i;
+                            mD = EBu[c];
+                            EBu[c] = __vimin3_s32(cb, eh, ev);
+                            CBu[c] = cb; EVu[c] = ev; EHu[c] = eh;
+                            cbL = cb; ehL = eh;
+                        }
+                    } else {
+                        const int *rowbase = s_cost16 + (r.w & 15) * 16;
+                        const int vext = r.x, opnV = r.y, go_i = r.z;
+                        const int mask_i = (r.w & PF_HASGAP) ? -1 : 0;
+                        int xCB = dCB, xEV = dEV, xEH = dEH, xEB = dEB;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const int fl = c_fl[c];
+                            const int go_j = c_go[c];
+                            const int eh = __viaddmin_s32(ehL, c_ext[c], cbL + c_opn[c]);
+                            const int ev = __viaddmin_s32(EVu[c], vext, CBu[c] + opnV);
+                            const bool both = (r.w & fl & PF_HASGAP) != 0;
+                            const bool clean = ((r.w | fl) & PF_PREVGAP) == 0;
+                            const int dg = both ? 0 : POY_INF;
+                            const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
+                            const int eb = __viaddmin_s32(xEB, dg, xCB + od);
+                            const int diag = rowbase[fl & 15];
+                            const int gv = go_j & mask_i;
+                            const int gh = (fl & PF_HASGAP) ? go_i : 0;
+                            const int xgo = go_j < go_i ? go_i : go_j;
+                            int m = __viaddmin_s32(xEV, gv, xCB);
+                            m = __viaddmin_s32(xEH, gh, m);
+                            m = __viaddmin_s32(xEB, xgo, m);
+                            const int cb = m + diag;
+                            xCB = CBu[c]; xEV = EVu[c]; xEH = EHu[c]; xEB = EBu[c];
+                            CBu[c] = cb; EVu[c] = ev; EHu[c] = eh; EBu[c] = eb;
+                            cbL = cb; ehL = eh;
+                        }
+                    }
+                    // F5: EV at the last column of an even row comes from clobbered predecessors
+                    if (owns_last && !(i & 1)) {
+                        const int pv = POY_INF + imin(r.x, r.y);
+#pragma unroll
+                        for (int c = 0; c < C; ++c)
+                            if (c == cl) {
+                                EVu[c] = pv;
+                                if (GAPFREE) EBu[c] = __vimin3_s32(CBu[c], EHu[c], pv);
+                            }
+                    }
+                    dCB = lCB; dEV = lEV; dEH = lEH; dEB = lEB;
+                    oCB = CBu[C - 1]; oEH = EHu[C - 1]; oEV = EVu[C - 1]; oEB = EBu[C - 1];
+                    if (lane == 31 && !last_block) bout[i] = make_int4(oCB, oEH, oEV, oEB);
+                }
+            }
+            if (owns_last) {
+                int res = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (c == cl) {
+                        res = imin(imin(EHu[c], EVu[c]), CBu[c]);
+                        if (!GAPFREE) res = imin(res, EBu[c]);
+                    }
+                cost_out[J.out] = res;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Two launches: gap-free jobs with the 3-state kernel, the rest with the 4-state kernel.  The job
+// lists are built on the device (misc.cu: k_build_cost_jobs); d_counts[0..1] hold their lengths.
+cudaError_t launch_cost_affine_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs_free,
+                                     const CostJob *d_jobs_gen, const int *d_counts, int *d_counters, int4 *d_bound,
+                                     size_t bound_stride, int blocks, int *d_cost) {
+    k_cost_affine<16, true><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_g0, d_jobs_free,
+                                                              d_counts, d_counters, d_bound, bound_stride, d_cost);
+    ctx->launches++;
+    k_cost_affine<8, false><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_g0, d_jobs_gen,
+                                                              d_counts + 1, d_counters + 1, d_bound, bound_stride, d_cost);
+    ctx->launches++;
+    return cudaGetLastError();
+}

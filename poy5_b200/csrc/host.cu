@@ -1,0 +1,718 @@
+// Host side of libpoy5b200.so: context / pool / cost-model objects, batch orchestration
+// (job construction, band-doubling schedule, direction-arena waves) and the C ABI of
+// include/poy5_b200.h.  No CPU implementation of any alignment lives here: every
+// alignment result comes from the kernels in cost_affine.cu / band_affine.cu.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+
+// ---- error plumbing ---------------------------------------------------------------------
+static poy_status fail(poy_ctx *ctx, poy_status s, const char *msg) {
+    if (ctx) { strncpy(ctx->err, msg, sizeof(ctx->err) - 1); ctx->err[sizeof(ctx->err) - 1] = 0; }
+    return s;
+}
+static poy_status cuda_fail(poy_ctx *ctx, cudaError_t e, const char *where) {
+    char buf[400];
+    snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
+    return fail(ctx, e == cudaErrorMemoryAllocation ? POY_ERR_NOMEM : POY_ERR_CUDA, buf);
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+extern "C" const char *poy_status_string(poy_status s) {
+    switch (s) {
+        case POY_OK: return "ok";
+        case POY_ERR_CUDA: return "CUDA runtime error";
+        case POY_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case POY_ERR_ARG: return "bad argument";
+        case POY_ERR_ORDER: return "pass the shorter one as first";
+        case POY_ERR_COST_RANGE: return "cost model outside the reference's HIGH_NUM domain";
+        case POY_ERR_MODEL: return "entry point does not match the cost model type";
+        case POY_ERR_NOMEM: return "out of device memory";
+    }
+    return "unknown";
+}
+extern "C" const char *poy_last_error(const poy_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+// ---- context -------------------------------------------------------------------------------
+extern "C" poy_status poy_ctx_create(int device, void *stream, poy_ctx **out) {
+    if (!out) return POY_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return POY_ERR_NO_DEVICE;
+    poy_ctx *ctx = (poy_ctx *)calloc(1, sizeof(poy_ctx));
+    if (!ctx) return POY_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return POY_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return POY_ERR_NO_DEVICE; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->owns_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return POY_ERR_CUDA; }
+        ctx->owns_stream = true;
+    }
+    ctx->arena_limit = 8ull << 30;
+    *out = ctx;
+    return POY_OK;
+}
+
+extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < 8; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
+    for (int s = 0; s < 4; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+extern "C" poy_status poy_ctx_set_arena_limit(poy_ctx *ctx, uint64_t bytes) {
+    if (!ctx || bytes < (1u << 20)) return POY_ERR_ARG;
+    ctx->arena_limit = bytes;
+    return POY_OK;
+}
+extern "C" poy_status poy_ctx_synchronize(poy_ctx *ctx) {
+    if (!ctx) return POY_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+extern "C" uint64_t poy_ctx_launch_count(const poy_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// grow-only scratch slots
+static poy_status scratch(poy_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (ctx->scratch_cap[slot] < bytes) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_scratch[slot]) { cudaFree(ctx->d_scratch[slot]); ctx->d_scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&ctx->d_scratch[slot], want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&ctx->d_scratch[slot], want); }
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scratch)");
+        ctx->scratch_cap[slot] = want;
+    }
+    *out = ctx->d_scratch[slot];
+    return POY_OK;
+}
+static poy_status pinned(poy_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (ctx->pinned_cap[slot] < bytes) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_pinned[slot]) { cudaFreeHost(ctx->h_pinned[slot]); ctx->h_pinned[slot] = nullptr; ctx->pinned_cap[slot] = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        CK(cudaMallocHost(&ctx->h_pinned[slot], want));
+        ctx->pinned_cap[slot] = want;
+    }
+    *out = ctx->h_pinned[slot];
+    return POY_OK;
+}
+enum { SL_JOBS = 0, SL_JOBS2 = 1, SL_BOUND = 2, SL_STATE = 3, SL_EBROW = 4, SL_DIR = 5, SL_MISC = 6, SL_WORK = 7 };
+
+// ---- Cost_matrix.Two_D table construction (src/cost_matrix.ml) --------------------------------
+namespace {
+const int A_SZ = 5, NCOMB = 31, GAPC = 16;
+const int CM_MAX_INT = 0x3fffffff;  // (Int32.max_int) lsr 1, src/cost_matrix.ml:38
+
+inline int &at(int32_t *t, int a, int b) { return t[(a << 5) + b]; }
+inline int at(const int32_t *t, int a, int b) { return t[(a << 5) + b]; }
+
+// members of a bitset, highest bit first (BitSet.Int.list_of_packed_max, src/bitSet.ml:343-353)
+int members(int v, int *out) {
+    int n = 0;
+    for (int b = A_SZ - 1; b >= 0; --b) if (v & (1 << b)) out[n++] = 1 << b;
+    return n;
+}
+
+// fill_best_cost_and_median_for_all_combinations (src/cost_matrix.ml:862-897) with
+// test_combinations (:479-506) and cleanup (:700-716).
+void fill_all_combinations(poy_cm_host *m) {
+    const bool affine = m->cost_model_type == 1;
+    for (int i = 1; i <= NCOMB; ++i) {
+        int li[A_SZ], ni = members(i, li);
+        for (int j = 1; j <= NCOMB; ++j) {
+            int lj[A_SZ], nj = members(j, lj);
+            int best = 0, c = CM_MAX_INT, w = 0;
+            for (int x = 0; x < ni; ++x)
+                for (int y = 0; y < nj; ++y) {
+                    const int a = li[x], b = lj[y];
+                    for (int e = 0; e < A_SZ; ++e) {
+                        const int v = 1 << e;
+                        const int goa = (affine && v == GAPC && (a & GAPC) && (b & GAPC)) ? m->gap_open : 0;
+                        const int tc = at(m->cost, a, v) + at(m->cost, v, b) + goa;
+                        if (tc < c) { c = tc; best = v; }
+                        else if (tc == c) best |= v;
+                    }
+                    if (at(m->cost, a, b) > w) w = at(m->cost, a, b);
+                }
+            if (ni == 1 && nj == 1) m->median[(i << 5) + j] = (uint8_t)(i | j);
+            else {
+                at(m->cost, i, j) = c;
+                int med = best;
+                if (affine && med != GAPC && (med & GAPC)) med = GAPC;
+                m->median[(i << 5) + j] = (uint8_t)med;
+            }
+            at(m->worst, i, j) = w;
+        }
+    }
+}
+
+// fill_best_cost_and_median_for_all_combinations_bitwise (src/cost_matrix.ml:721-804)
+void fill_bitwise(poy_cm_host *m, bool create_original) {
+    int32_t old[1024];
+    memcpy(old, m->cost, sizeof old);
+    struct Acc { int best, med, worst; };
+    auto step = [&](Acc acc, int i, int j) {
+        const int cost1 = at(old, i, i) + at(old, i, j), cost2 = at(old, i, j) + at(old, j, j);
+        int cij, mij;
+        if (cost1 == cost2) { cij = create_original ? cost1 - at(old, i, i) : cost1; mij = i | j; }
+        else if (cost1 > cost2) { cij = create_original ? cost2 - at(old, j, j) : cost2; mij = j; }
+        else { cij = create_original ? cost1 - at(old, i, i) : cost1; mij = i; }
+        if (cij < acc.best) { acc.best = cij; acc.med = mij; }
+        else if (cij == acc.best) acc.med |= mij;
+        if (cij > acc.worst) acc.worst = cij;
+        return acc;
+    };
+    for (int i = 1; i <= NCOMB; ++i) {
+        int li[A_SZ], ni = members(i, li);
+        for (int j = 1; j <= NCOMB; ++j) {
+            int lj[A_SZ], nj = members(j, lj);
+            int median, best, worst;
+            if (ni == 1 && nj == 1) {
+                if (i == j) {
+                    int cii = at(old, i, i);
+                    if (!create_original) cii *= 2;
+                    median = i; best = worst = cii;
+                } else {
+                    const int cost1 = at(old, i, j) + at(old, j, j), cost2 = at(old, i, i) + at(old, i, j);
+                    int cij;
+                    if (cost1 == cost2) { cij = cost1; median = i | j; }
+                    else if (cost1 > cost2) { cij = cost2; median = i; }
+                    else { cij = cost1; median = j; }
+                    if (create_original) cij = at(old, i, j);
+                    best = worst = cij;
+                }
+            } else {
+                Acc acc = { CM_MAX_INT, 0, 0 };
+                for (int x = 0; x < nj; ++x) for (int y = 0; y < ni; ++y) acc = step(acc, lj[x], li[y]);
+                for (int x = 0; x < ni; ++x) for (int y = 0; y < nj; ++y) acc = step(acc, li[x], lj[y]);
+                median = acc.med; best = acc.best; worst = acc.worst;
+            }
+            m->median[(i << 5) + j] = (uint8_t)median;
+            at(m->cost, i, j) = best;
+            at(m->worst, i, j) = worst;
+        }
+    }
+}
+
+void fill_prepend_tail(poy_cm_host *m) {  // fill_default_prepend_tail, src/cost_matrix.ml:994-1001
+    for (int i = 1; i <= NCOMB; ++i) { m->tail[i] = at(m->cost, i, GAPC); m->prepend[i] = at(m->cost, GAPC, i); }
+}
+
+// fill_cost_matrix (src/cost_matrix.ml:1140-1189), use_comb = true, level = 0
+void fill_cost_matrix(const int32_t single[25], bool create_original, poy_cm_host *m) {
+    memset(m, 0, sizeof *m);
+    bool pos = true, sym = true, ident = true;
+    for (int a = 0; a < A_SZ; ++a)
+        for (int b = 0; b < A_SZ; ++b) {
+            at(m->cost, 1 << a, 1 << b) = single[a * A_SZ + b];
+            if (single[a * A_SZ + b] < 0) pos = false;
+            if (single[a * A_SZ + b] != single[b * A_SZ + a]) sym = false;
+            if (a == b && single[a * A_SZ + b] != 0) ident = false;
+        }
+    if (pos && sym && ident) fill_all_combinations(m);
+    else fill_bitwise(m, create_original);
+    fill_prepend_tail(m);
+}
+}  // namespace
+
+extern "C" poy_status poy_cm_fill(const int32_t single[25], int32_t gap_open, poy_cm_host *full, poy_cm_host *original) {
+    if (!single || !full || !original) return POY_ERR_ARG;
+    for (int x = 0; x < 25; ++x) if (single[x] < 0) return POY_ERR_COST_RANGE;
+    fill_cost_matrix(single, false, full);
+    fill_cost_matrix(single, true, original);
+    if (gap_open >= 0) {  // set_cost_model (Affine go), src/cost_matrix.ml:1003-1016 via src/data.ml:5937-5964
+        poy_cm_host *ms[2] = { full, original };
+        for (poy_cm_host *m : ms) {
+            m->cost_model_type = 1;
+            m->gap_open = gap_open;
+            fill_bitwise(m, false);
+        }
+    }
+    return POY_OK;
+}
+
+extern "C" int32_t poy_cm_min_non0(const poy_cm_host *cm) {
+    int m = 0x3fffffff;  // INT_MAX/2
+    for (int x = 0; x < 1024; ++x) if (cm->cost[x] > 0 && cm->cost[x] < m) m = cm->cost[x];
+    return m;
+}
+
+extern "C" int32_t poy_cm_get_closest(const poy_cm_host *cm, int32_t a, int32_t b) {
+    if (a <= 0 || b <= 0 || a > NCOMB || b > NCOMB) return -1;
+    if (a == GAPC || b == GAPC) { /* keep b */ }
+    else if ((a & GAPC) && (b & GAPC)) b = GAPC;
+    else b &= ~GAPC;
+    int best = a, cur = CM_MAX_INT;
+    for (int e = 0; e < A_SZ; ++e) {  // states_of_code: ascending bit order
+        const int x = 1 << e;
+        if (!(b & x)) continue;
+        const int nc = at(cm->cost, a, x);
+        if (nc < cur) { best = x; cur = nc; }
+    }
+    return best;
+}
+
+extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm **out) {
+    if (!ctx || !h || !out) return POY_ERR_ARG;
+    *out = nullptr;
+    int max_entry = 0;
+    for (int x = 0; x < 1024; ++x) {
+        if (h->cost[x] < 0) return fail(ctx, POY_ERR_COST_RANGE, "negative cost entry");
+        max_entry = std::max(max_entry, h->cost[x]);
+    }
+    for (int x = 0; x < 32; ++x) {
+        if (h->prepend[x] < 0 || h->tail[x] < 0) return fail(ctx, POY_ERR_COST_RANGE, "negative prepend/tail cost");
+        max_entry = std::max(max_entry, std::max(h->prepend[x], h->tail[x]));
+    }
+    if (h->gap_open < 0 || max_entry >= POY_INF || h->gap_open >= POY_INF)
+        return fail(ctx, POY_ERR_COST_RANGE, "cost entry or gap opening >= HIGH_NUM");
+    poy_cm *cm = new poy_cm;
+    cm->h = *h;
+    cm->min_non0 = poy_cm_min_non0(h);
+    cm->max_entry = max_entry;
+    DevCM *img = new DevCM;
+    memset(img, 0, sizeof *img);
+    for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b) img->cost16[a * 16 + b] = h->cost[(a << 5) + b];
+    memcpy(img->cost32, h->cost, sizeof img->cost32);
+    memcpy(img->worst32, h->worst, sizeof img->worst32);
+    memcpy(img->median32, h->median, sizeof img->median32);
+    memcpy(img->prepend, h->prepend, sizeof img->prepend);
+    memcpy(img->tail, h->tail, sizeof img->tail);
+    for (int a = 0; a < 32; ++a) img->gapext[a] = h->cost[(a << 5) + GAPC];
+    img->gap_open = h->gap_open;
+    img->model = h->cost_model_type;
+    img->min_non0 = cm->min_non0;
+    img->max_entry = max_entry;
+    cudaError_t e = cudaMalloc(&cm->d, sizeof(DevCM));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cm->d, img, sizeof(DevCM), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    delete img;
+    if (e != cudaSuccess) { delete cm; return cuda_fail(ctx, e, "poy_cm_upload"); }
+    *out = cm;
+    return POY_OK;
+}
+extern "C" void poy_cm_free(poy_ctx *ctx, poy_cm *cm) {
+    if (!cm) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(cm->d);
+    delete cm;
+}
+
+// ---- pool ----------------------------------------------------------------------------------------
+static poy_status pool_alloc(poy_ctx *ctx, poy_pool *p) {
+    const size_t nb = (size_t)std::max<int64_t>(p->nbytes, 1);
+    CK(cudaMalloc(&p->d_rowp, nb * sizeof(int4)));
+    CK(cudaMalloc(&p->d_colp, nb * sizeof(int4)));
+    CK(cudaMalloc(&p->d_h0, nb * sizeof(int)));
+    CK(cudaMalloc(&p->d_g0, nb * sizeof(int)));
+    CK(cudaMalloc(&p->d_gapfree, (size_t)std::max(p->nseq, 1)));
+    return POY_OK;
+}
+
+extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
+    if (!p) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (p->owns_data) { cudaFree(p->d_data); cudaFree(p->d_off); }
+    cudaFree(p->d_rowp); cudaFree(p->d_colp); cudaFree(p->d_h0); cudaFree(p->d_g0); cudaFree(p->d_gapfree);
+    free(p->h_off);
+    delete p;
+}
+
+static poy_status pool_new(poy_ctx *ctx, const int64_t *h_off, int32_t nseq, poy_pool **out) {
+    if (nseq < 0 || !h_off || h_off[0] != 0) return fail(ctx, POY_ERR_ARG, "pool offsets must start at 0");
+    for (int s = 0; s < nseq; ++s)
+        if (h_off[s + 1] <= h_off[s]) return fail(ctx, POY_ERR_ARG, "every pool sequence needs at least its leading gap");
+    poy_pool *p = new poy_pool;
+    memset(p, 0, sizeof *p);
+    p->nseq = nseq;
+    p->nbytes = h_off[nseq];
+    p->h_off = (int64_t *)malloc(sizeof(int64_t) * (nseq + 1));
+    memcpy(p->h_off, h_off, sizeof(int64_t) * (nseq + 1));
+    *out = p;
+    return POY_OK;
+}
+
+extern "C" poy_status poy_pool_upload(poy_ctx *ctx, const uint8_t *data, const int64_t *offsets, int32_t nseq, poy_pool **out) {
+    if (!ctx || !data || !offsets || !out) return POY_ERR_ARG;
+    *out = nullptr;
+    poy_pool *p;
+    poy_status s = pool_new(ctx, offsets, nseq, &p);
+    if (s != POY_OK) return s;
+    p->owns_data = true;
+    cudaError_t e = cudaMalloc(&p->d_data, (size_t)std::max<int64_t>(p->nbytes, 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_off, sizeof(int64_t) * (nseq + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_data, data, (size_t)p->nbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_off, offsets, sizeof(int64_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { poy_pool_free(ctx, p); return cuda_fail(ctx, e, "poy_pool_upload"); }
+    s = pool_alloc(ctx, p);
+    if (s != POY_OK) { poy_pool_free(ctx, p); return s; }
+    *out = p;
+    return POY_OK;
+}
+
+extern "C" poy_status poy_pool_from_device(poy_ctx *ctx, const uint8_t *d_data, const int64_t *d_offsets,
+                                           const int64_t *h_offsets, int32_t nseq, poy_pool **out) {
+    if (!ctx || !d_data || !d_offsets || !h_offsets || !out) return POY_ERR_ARG;
+    *out = nullptr;
+    poy_pool *p;
+    poy_status s = pool_new(ctx, h_offsets, nseq, &p);
+    if (s != POY_OK) return s;
+    p->owns_data = false;
+    p->d_data = const_cast<uint8_t *>(d_data);
+    p->d_off = const_cast<int64_t *>(d_offsets);
+    s = pool_alloc(ctx, p);
+    if (s != POY_OK) { poy_pool_free(ctx, p); return s; }
+    *out = p;
+    return POY_OK;
+}
+
+static poy_status ensure_params(poy_ctx *ctx, const poy_cm *cm, const poy_pool *cpool) {
+    poy_pool *pool = const_cast<poy_pool *>(cpool);
+    if (pool->params_for == cm) return POY_OK;
+    CK(launch_params(ctx, cm, pool));
+    pool->params_for = cm;
+    return POY_OK;
+}
+
+static int64_t max_len(const poy_pool *pool) {
+    int64_t m = 0;
+    for (int s = 0; s < pool->nseq; ++s) m = std::max(m, pool->h_off[s + 1] - pool->h_off[s]);
+    return m;
+}
+
+// The reference is only defined while path costs stay below HIGH_NUM (src/algn.c:37).
+static poy_status domain_check(poy_ctx *ctx, const poy_cm *cm, int64_t len_sum) {
+    const int64_t per_step = (int64_t)cm->max_entry + 2 * (int64_t)cm->h.gap_open;
+    if (per_step * len_sum + cm->h.gap_open >= POY_INF)
+        return fail(ctx, POY_ERR_COST_RANGE, "sequence lengths x costs can reach HIGH_NUM; the reference is undefined there");
+    return POY_OK;
+}
+
+// ---- batch cost-only affine --------------------------------------------------------------------------
+extern "C" poy_status poy_batch_cost_affine_dev(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                                const int32_t *d_a, const int32_t *d_b, int32_t *d_cost) {
+    if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!d_a || !d_b || !d_cost))) return POY_ERR_ARG;
+    if (cm->h.cost_model_type != 1) return fail(ctx, POY_ERR_MODEL, "cost_affine needs an affine cost model");
+    if (n == 0) return POY_OK;
+    const int64_t ml = max_len(pool);
+    poy_status s = domain_check(ctx, cm, 2 * ml);
+    if (s != POY_OK) return s;
+    s = ensure_params(ctx, cm, pool);
+    if (s != POY_OK) return s;
+    void *jobs_free, *jobs_gen, *misc, *bound;
+    if ((s = scratch(ctx, SL_JOBS, sizeof(CostJob) * (size_t)n, &jobs_free)) != POY_OK) return s;
+    if ((s = scratch(ctx, SL_JOBS2, sizeof(CostJob) * (size_t)n, &jobs_gen)) != POY_OK) return s;
+    if ((s = scratch(ctx, SL_MISC, 64, &misc)) != POY_OK) return s;
+    const int blocks = ctx->sm_count * 4;
+    const size_t bound_stride = (size_t)ml + 2;
+    if ((s = scratch(ctx, SL_BOUND, sizeof(int4) * 2 * bound_stride * (size_t)blocks * 4, &bound)) != POY_OK) return s;
+    int *counts = (int *)misc;  // [0],[1] = work counters; [2],[3] = job counts
+    CK(cudaMemsetAsync(counts, 0, 16, ctx->stream));
+    CK(launch_build_cost_jobs(ctx, pool, n, d_a, d_b, (CostJob *)jobs_free, (CostJob *)jobs_gen, counts + 2));
+    // the job counts stay on the device: both kernels read them there
+    CK(launch_cost_affine_split(ctx, cm, pool, (CostJob *)jobs_free, (CostJob *)jobs_gen, counts + 2, counts, (int4 *)bound,
+                                bound_stride, blocks, d_cost));
+    return POY_OK;
+}
+
+extern "C" poy_status poy_batch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                            const int32_t *a, const int32_t *b, int32_t *cost) {
+    if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!a || !b || !cost))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    for (int p = 0; p < n; ++p)
+        if (a[p] < 0 || a[p] >= pool->nseq || b[p] < 0 || b[p] >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+    void *dbuf;
+    poy_status s = scratch(ctx, SL_STATE, sizeof(int32_t) * 3 * (size_t)n, &dbuf);
+    if (s != POY_OK) return s;
+    int32_t *d_a = (int32_t *)dbuf, *d_b = d_a + n, *d_cost = d_b + n;
+    CK(cudaMemcpyAsync(d_a, a, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_b, b, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    s = poy_batch_cost_affine_dev(ctx, cm, pool, n, d_a, d_b, d_cost);
+    if (s != POY_OK) return s;
+    CK(cudaMemcpyAsync(cost, d_cost, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+
+// ---- batch banded affine with traceback ------------------------------------------------------------------
+namespace {
+struct HostPair {
+    int lasti, lastj, T, k, dclass, stride;
+    int64_t off_i, off_j, eb_off, dir_bytes;
+    int iterations;
+    int64_t cells;
+    bool done;
+};
+
+// number of band cells of one fill (rows 1..lasti, columns max(i-k,0)..min(i+delta+k,lastj))
+int64_t band_cells(int lasti, int lastj, int k) {
+    if (lasti <= 0) return 0;
+    const int64_t delta = lastj - lasti;
+    int64_t hi = 0, lo = 0;
+    const int64_t n1 = std::max<int64_t>(0, std::min<int64_t>(lasti, (int64_t)lastj - 1 - delta - k));  // rows with i+delta+k <= lastj-1
+    hi += n1 * (delta + k) + n1 * (n1 + 1) / 2;
+    hi += (lasti - n1) * (int64_t)lastj;
+    if (lasti > k) { const int64_t m = lasti - k; lo = m * (m + 1) / 2; }
+    return hi - lo + lasti;
+}
+}  // namespace
+
+extern "C" poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                                 const int32_t *d_si, const int32_t *d_sj, const uint8_t *d_swaped,
+                                                 const int32_t *h_si, const int32_t *h_sj, const int64_t *d_out_off,
+                                                 int32_t *d_cost, uint8_t *d_median, uint8_t *d_medianwg,
+                                                 uint8_t *d_resi, uint8_t *d_resj, int32_t *d_out_len, int32_t *d_stats);
+
+static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n, const int32_t *h_si,
+                             const int32_t *h_sj, const uint8_t *h_swaped, const int64_t *d_out_off, int32_t *d_cost,
+                             uint8_t *d_median, uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
+                             int32_t *d_out_len, int32_t *h_stats) {
+    if (cm->h.cost_model_type != 1) return fail(ctx, POY_ERR_MODEL, "align_affine needs an affine cost model");
+    if (n == 0) return POY_OK;
+    const bool want_trace = d_median || d_medianwg || d_resi || d_resj || d_out_len;
+    if (want_trace && !d_out_off) return fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
+    std::vector<HostPair> hp((size_t)n);
+    int64_t eb_total = 0, maxsum = 0;
+    for (int p = 0; p < n; ++p) {
+        const int a = h_si[p], b = h_sj[p];
+        if (a < 0 || a >= pool->nseq || b < 0 || b >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+        HostPair &h = hp[p];
+        h.off_i = pool->h_off[a]; h.off_j = pool->h_off[b];
+        h.lasti = (int)(pool->h_off[a + 1] - h.off_i) - 1;
+        h.lastj = (int)(pool->h_off[b + 1] - h.off_j) - 1;
+        if (h.lastj < h.lasti) return fail(ctx, POY_ERR_ORDER, "pass the shorter one as first");
+        h.T = (h.lastj - h.lasti + 1) * cm->min_non0;  // algn_fill_plane_3_aff, src/algn.c:2348-2349
+        h.eb_off = eb_total;
+        eb_total += h.lastj + 1;
+        h.iterations = 0; h.cells = 0; h.done = false;
+        maxsum = std::max<int64_t>(maxsum, (int64_t)h.lasti + h.lastj + 2);
+    }
+    poy_status s = domain_check(ctx, cm, maxsum);
+    if (s != POY_OK) return s;
+    if ((s = ensure_params(ctx, cm, pool)) != POY_OK) return s;
+
+    void *v_state, *v_eb, *v_jobs, *v_misc, *v_pin, *v_pin2;
+    if ((s = scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
+    if ((s = scratch(ctx, SL_EBROW, sizeof(int) * (size_t)eb_total, &v_eb)) != POY_OK) return s;
+    if ((s = scratch(ctx, SL_JOBS, sizeof(BandJob) * (size_t)n, &v_jobs)) != POY_OK) return s;
+    if ((s = scratch(ctx, SL_MISC, 64, &v_misc)) != POY_OK) return s;
+    if ((s = pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (size_t)n, &v_pin)) != POY_OK) return s;
+    if ((s = pinned(ctx, 1, (size_t)n + sizeof(int32_t) * (size_t)n, &v_pin2)) != POY_OK) return s;
+    PairState *d_state = (PairState *)v_state;
+    uint8_t *d_done = (uint8_t *)(d_state + n);
+    int *d_eb = (int *)v_eb;
+    BandJob *d_jobs = (BandJob *)v_jobs;
+    int *d_counter = (int *)v_misc;
+    uint8_t *h_done = (uint8_t *)v_pin2;
+
+    {   // initial per-pair state: EH[0][0] = go, EB row 0 = INF (initialize_matrices_affine, src/algn.c:1875-1898)
+        PairState *hs = (PairState *)v_pin;
+        for (int p = 0; p < n; ++p) { hs[p].T = hp[p].T; hs[p].eh00 = cm->h.gap_open; hs[p].cost = 0; hs[p].gapnum = 0; hs[p].iterations = 0; hs[p].done = 0; hs[p].cells = 0; }
+        CK(cudaMemcpyAsync(d_state, hs, sizeof(PairState) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(d_done, 0, (size_t)n, ctx->stream));
+    }
+    CK(launch_fill_int(ctx, d_eb, eb_total, POY_INF));
+    CK(cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
+
+    std::vector<int> active((size_t)n);
+    for (int p = 0; p < n; ++p) active[p] = p;
+    std::vector<int> order;
+    const int gen_blocks = ctx->sm_count * 2;
+
+    while (!active.empty()) {
+        // band geometry of this round (algn_newkk_increaseT_aff / algn_newkk_test_aff, src/algn.c:2311-2336, 2195-2196)
+        for (int p : active) {
+            HostPair &h = hp[p];
+            const int delta = h.lastj - h.lasti;
+            const int pp = (h.T - delta) / 2;
+            h.k = pp >= h.lasti ? h.lasti - 1 : pp;
+            if (h.lasti == 0) h.k = 0;
+            const int64_t B = (int64_t)delta + 2 * (int64_t)h.k + 1;
+            h.dclass = h.lasti == 0 ? 2 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : 0;
+            h.stride = h.dclass ? 16 * h.dclass : (int)(((B + 1) / 2 + 15) & ~15ll);
+            h.dir_bytes = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2) * h.stride;
+            h.iterations++;
+            h.cells += band_cells(h.lasti, h.lastj, h.k);
+        }
+        // order: by kernel class, then by size (largest first) for load balance
+        order = active;
+        std::sort(order.begin(), order.end(), [&](int x, int y) {
+            if (hp[x].dclass != hp[y].dclass) return hp[x].dclass > hp[y].dclass;
+            if (hp[x].dir_bytes != hp[y].dir_bytes) return hp[x].dir_bytes > hp[y].dir_bytes;
+            return x < y;
+        });
+        size_t pos = 0;
+        while (pos < order.size()) {
+            // one wave: as many pairs as fit in the direction arena
+            int64_t used = 0;
+            size_t end = pos;
+            while (end < order.size()) {
+                const int64_t need = (hp[order[end]].dir_bytes + 255) & ~255ll;
+                if (end > pos && used + need > (int64_t)ctx->arena_limit) break;
+                used += need;
+                ++end;
+            }
+            void *v_dir;
+            if ((s = scratch(ctx, SL_DIR, (size_t)used, &v_dir)) != POY_OK) return s;
+            uint8_t *d_dir = (uint8_t *)v_dir;
+            BandJob *hj = (BandJob *)v_pin;
+            const int nj = (int)(end - pos);
+            int64_t doff = 0;
+            int64_t gen_width = 0;
+            for (int q = 0; q < nj; ++q) {
+                const int p = order[pos + q];
+                const HostPair &h = hp[p];
+                BandJob &j = hj[q];
+                j.off_i = h.off_i; j.off_j = h.off_j; j.lasti = h.lasti; j.lastj = h.lastj; j.k = h.k; j.pair = p;
+                j.swaped = h_swaped ? (h_swaped[p] ? 1 : 0) : 0;
+                j.stride = h.stride; j.dir_off = doff; j.eb_off = h.eb_off;
+                doff += (h.dir_bytes + 255) & ~255ll;
+                if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
+            }
+            CK(cudaMemcpyAsync(d_jobs, hj, sizeof(BandJob) * (size_t)nj, cudaMemcpyHostToDevice, ctx->stream));
+            // launch per class (jobs of one class are contiguous)
+            int q0 = 0;
+            while (q0 < nj) {
+                const int cls = hp[order[pos + q0]].dclass;
+                int q1 = q0;
+                while (q1 < nj && hp[order[pos + q1]].dclass == cls) ++q1;
+                if (cls != 0) {
+                    CK(launch_band_fill(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter, d_state, d_eb, d_dir));
+                } else {
+                    void *v_work;
+                    const size_t wstride = 6 * (size_t)((gen_width + 31) & ~31ll);
+                    const int blocks = std::min(gen_blocks, q1 - q0);
+                    if ((s = scratch(ctx, SL_WORK, sizeof(int) * wstride * (size_t)blocks, &v_work)) != POY_OK) return s;
+                    CK(launch_band_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_eb, d_dir, (int *)v_work, wstride, blocks));
+                }
+                q0 = q1;
+            }
+            // stop rule on the device, then traceback of the pairs that stopped (others return immediately)
+            CK(launch_band_finish(ctx, d_jobs, nj, d_state, d_done, pool->d_g0, cm->h.gap_open));
+            if (want_trace) {
+                CK(launch_traceback(ctx, cm, pool, d_jobs, nj, d_done, d_dir, d_out_off, d_median, d_medianwg, d_resi,
+                                    d_resj, d_out_len));
+            }
+            CK(cudaStreamSynchronize(ctx->stream));  // the pinned job staging and the arena are reused by the next wave
+            pos = end;
+        }
+        CK(cudaMemcpyAsync(h_done, d_done, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::vector<int> next;
+        next.reserve(active.size());
+        for (int p : active) {
+            if (h_done[p]) hp[p].done = true;
+            else { hp[p].T *= 2; next.push_back(p); }
+        }
+        active.swap(next);
+    }
+    if (d_cost) {
+        CK(launch_gather_cost(ctx, d_state, n, d_cost));
+    }
+    if (h_stats)
+        for (int p = 0; p < n; ++p) {
+            h_stats[4 * p + 0] = hp[p].iterations; h_stats[4 * p + 1] = hp[p].T; h_stats[4 * p + 2] = hp[p].k;
+            h_stats[4 * p + 3] = (int32_t)std::min<int64_t>(hp[p].cells / 1024, 0x7fffffff);
+        }
+    return POY_OK;
+}
+
+extern "C" poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                                 const int32_t *d_si, const int32_t *d_sj, const uint8_t *d_swaped,
+                                                 const int32_t *h_si, const int32_t *h_sj, const int64_t *d_out_off,
+                                                 int32_t *d_cost, uint8_t *d_median, uint8_t *d_medianwg,
+                                                 uint8_t *d_resi, uint8_t *d_resj, int32_t *d_out_len, int32_t *d_stats) {
+    (void)d_si; (void)d_sj;
+    if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!h_si || !h_sj))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    // the band schedule is driven from the host, so the swaped flags are needed there as well
+    std::vector<uint8_t> sw;
+    if (d_swaped) {
+        sw.resize((size_t)n);
+        CK(cudaMemcpyAsync(sw.data(), d_swaped, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<int32_t> stats;
+    if (d_stats) stats.resize(4 * (size_t)n);
+    poy_status s = align_impl(ctx, cm, pool, n, h_si, h_sj, d_swaped ? sw.data() : nullptr, d_out_off, d_cost, d_median,
+                              d_medianwg, d_resi, d_resj, d_out_len, d_stats ? stats.data() : nullptr);
+    if (s != POY_OK) return s;
+    if (d_stats) {
+        CK(cudaMemcpyAsync(d_stats, stats.data(), sizeof(int32_t) * 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return POY_OK;
+}
+
+extern "C" poy_status poy_batch_align_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                             const int32_t *si, const int32_t *sj, const uint8_t *swaped,
+                                             const int64_t *out_off, int32_t *cost, uint8_t *median, uint8_t *medianwg,
+                                             uint8_t *resi, uint8_t *resj, int32_t *out_len, int32_t *stats) {
+    if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!si || !sj))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    const bool want_trace = median || medianwg || resi || resj || out_len;
+    if (want_trace && !out_off) return fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
+    // total output bytes = end of the last slot
+    int64_t total = 0;
+    if (want_trace)
+        for (int p = 0; p < n; ++p) {
+            if (si[p] < 0 || si[p] >= pool->nseq || sj[p] < 0 || sj[p] >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+            const int64_t cap = (pool->h_off[si[p] + 1] - pool->h_off[si[p]]) + (pool->h_off[sj[p] + 1] - pool->h_off[sj[p]]) + 2;
+            total = std::max(total, out_off[p] + cap);
+        }
+    const int nout = (median ? 1 : 0) + (medianwg ? 1 : 0) + (resi ? 1 : 0) + (resj ? 1 : 0);
+    const size_t al_total = ((size_t)total + 255) & ~(size_t)255;
+    void *v_out;
+    const size_t need = sizeof(int64_t) * (size_t)n + sizeof(int32_t) * 5 * (size_t)n + al_total * (size_t)nout + 1024;
+    poy_status s = scratch(ctx, SL_JOBS2, need, &v_out);
+    if (s != POY_OK) return s;
+    uint8_t *cur = (uint8_t *)v_out;
+    int64_t *d_out_off = (int64_t *)cur; cur += sizeof(int64_t) * (size_t)n;
+    int32_t *d_cost = (int32_t *)cur; cur += sizeof(int32_t) * (size_t)n;
+    int32_t *d_len = (int32_t *)cur; cur += sizeof(int32_t) * 4 * (size_t)n;
+    cur = (uint8_t *)(((uintptr_t)cur + 255) & ~(uintptr_t)255);
+    uint8_t *d_m = nullptr, *d_w = nullptr, *d_i = nullptr, *d_j = nullptr;
+    if (median) { d_m = cur; cur += al_total; }
+    if (medianwg) { d_w = cur; cur += al_total; }
+    if (resi) { d_i = cur; cur += al_total; }
+    if (resj) { d_j = cur; cur += al_total; }
+    if (want_trace) CK(cudaMemcpyAsync(d_out_off, out_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    s = align_impl(ctx, cm, pool, n, si, sj, swaped, want_trace ? d_out_off : nullptr, d_cost, d_m, d_w, d_i, d_j,
+                   want_trace ? d_len : nullptr, stats);
+    if (s != POY_OK) return s;
+    if (cost) CK(cudaMemcpyAsync(cost, d_cost, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_len) CK(cudaMemcpyAsync(out_len, d_len, sizeof(int32_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (median) CK(cudaMemcpyAsync(median, d_m, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (medianwg) CK(cudaMemcpyAsync(medianwg, d_w, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (resi) CK(cudaMemcpyAsync(resi, d_i, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (resj) CK(cudaMemcpyAsync(resj, d_j, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+
+// ---- micro-benchmark ---------------------------------------------------------------------------------------
+extern "C" poy_status poy_microbench_int(poy_ctx *ctx, int32_t kind, double *ops_per_second, double *sm_clock_mhz) {
+    if (!ctx || !ops_per_second) return POY_ERR_ARG;
+    void *v;
+    poy_status s = scratch(ctx, SL_MISC, 1 << 20, &v);
+    if (s != POY_OK) return s;
+    float ms = 0;
+    double ops = 0;
+    CK(launch_microbench(ctx, kind, 4096, (unsigned long long *)v, (int *)v + 1024, &ms, &ops));
+    *ops_per_second = ops / (ms * 1e-3);
+    if (sm_clock_mhz) {
+        unsigned long long cyc[2] = { 0, 1 };
+        CK(cudaMemcpy(cyc, v, sizeof cyc, cudaMemcpyDeviceToHost));
+        *sm_clock_mhz = cyc[1] ? (double)cyc[0] / (double)cyc[1] * 1e3 : 0.0;  // cycles per ns -> MHz
+    }
+    return POY_OK;
+}

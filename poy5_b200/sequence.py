@@ -1,0 +1,64 @@
+"""Host mirror of ``Sequence.Align`` (src/sequence.ml:596-1826), batch-shaped.
+
+Every function takes a Pool and arrays of pool indices: one call == the list of calls the
+reference makes one at a time from ``SeqCS``/``DynamicCS`` while mapping over loci and
+candidates.  All alignment work happens in libpoy5b200.so on the GPU."""
+import ctypes as C
+import numpy as np
+from .api import _ptr
+
+
+class Align:
+    @staticmethod
+    def cost_2(ctx, cm, pool, a, b):
+        """Sequence.Align.cost_2 under an Affine model = cost_2_affine =
+        "algn_CAML_cost_affine_3" (src/sequence.ml:630,928-936).  Either order; returns int32[n]."""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        n = len(a)
+        cost = np.zeros(n, np.int32)
+        ctx.check(ctx.L.poy_batch_cost_affine(ctx.h, cm.h, pool.h, n, _ptr(a), _ptr(b), _ptr(cost)))
+        return cost
+
+    @staticmethod
+    def align_affine_3(ctx, cm, pool, a, b, want=("median", "medianwg", "resi", "resj"), stats=False):
+        """Sequence.Align.align_affine_3 (src/sequence.ml:633-649): puts the shorter sequence first,
+        passes `swaped`, and un-swaps the two aligned rows on return.  Returns a dict with
+        cost[n] and, per requested output, a list of uint8 arrays (a's row is 'res_a', b's 'res_b')."""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        n = len(a)
+        la, lb = pool.lens[a], pool.lens[b]
+        swaped = (la > lb).astype(np.uint8)           # len1 <= len2 -> 0 (src/sequence.ml:636)
+        si = np.where(swaped == 1, b, a).astype(np.int32)
+        sj = np.where(swaped == 1, a, b).astype(np.int32)
+        caps = (la + lb + 2).astype(np.int64)
+        out_off = np.zeros(n, np.int64)
+        if n > 1:
+            np.cumsum(caps[:-1], out=out_off[1:])
+        total = int(caps.sum())
+        bufs = {k: (np.zeros(total, np.uint8) if k in want else None) for k in ("median", "medianwg", "resi", "resj")}
+        cost = np.zeros(n, np.int32)
+        out_len = np.zeros(4 * n, np.int32)
+        st = np.zeros(4 * n, np.int32) if stats else None
+        ctx.check(ctx.L.poy_batch_align_affine(ctx.h, cm.h, pool.h, n, _ptr(si), _ptr(sj), _ptr(swaped), _ptr(out_off),
+                                               _ptr(cost), _ptr(bufs["median"]), _ptr(bufs["medianwg"]),
+                                               _ptr(bufs["resi"]), _ptr(bufs["resj"]), _ptr(out_len), _ptr(st)))
+        out_len = out_len.reshape(n, 4)
+        res = {"cost": cost, "swaped": swaped, "out_len": out_len}
+        ends = out_off + caps
+
+        def cut(buf, col):
+            return [buf[ends[p] - out_len[p, col]:ends[p]] for p in range(n)]
+        if bufs["median"] is not None:
+            res["median"] = cut(bufs["median"], 0)
+        if bufs["medianwg"] is not None:
+            res["medianwg"] = cut(bufs["medianwg"], 1)
+        if bufs["resi"] is not None:
+            ri = cut(bufs["resi"], 2)
+        if bufs["resj"] is not None:
+            rj = cut(bufs["resj"], 3)
+        if bufs["resi"] is not None and bufs["resj"] is not None:
+            res["res_a"] = [rj[p] if swaped[p] else ri[p] for p in range(n)]
+            res["res_b"] = [ri[p] if swaped[p] else rj[p] for p in range(n)]
+        if stats:
+            res["stats"] = st.reshape(n, 4)
+        return res
