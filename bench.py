@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS / DO alignments per second of the batched affine alignment sweep
+(BASELINE.json configs[1]: 100k pairs, lengths 500/2k/10k bp, Ukkonen band off and on).
+
+One "step" = one pass of the hot path over the whole sweep: for every length, the cost-only
+entry point on all pairs ("band off", batch twin of algn_CAML_cost_affine_3) and the banded
+align + traceback + median entry point on all pairs ("band on", batch twin of
+algn_CAML_align_affine_3), followed by the min-reduction of the candidate costs (NCCL
+all-reduce when N > 1).  `value` counts full-matrix-equivalent cells (len_i-1)*(len_j-1) of every
+alignment performed per second with inputs resident in HBM; `e2e` is the same
+sweep through the host-buffer C ABI (pinned host inputs uploaded and all results read back
+inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun ... bench.py --gpus N ...      (one rank per GPU, weak scaling: each rank owns
+                                             its own --pairs pairs per length)
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+METRIC = "GCUPS (full-matrix-equivalent cell updates/s) of batched affine DO alignment, band off + band on"
+LENGTHS = (500, 2000, 10000)
+REGIME = (1, 1, 3)          # R1: substitution 1, indel 1, gap opening 3
+SEED = 0x504F5935
+OPS_PER_CELL = {"gapfree": 9, "general": 16}   # scalar int32 add/min per cost-only cell
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=100000, help="pairs per length per GPU")
+    ap.add_argument("--lengths", default=",".join(str(x) for x in LENGTHS))
+    ap.add_argument("--chunk-bases", type=int, default=600_000_000, help="max pool bytes per batch call")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+def chunks_for(npairs, length, chunk_bases):
+    per = max(1, chunk_bases // (2 * (length + 8)))
+    out, p = [], 0
+    while p < npairs:
+        n = min(per, npairs - p)
+        out.append((p, n))
+        p += n
+    return out
+
+
+def cpu_reference(lengths, threads, budget_core_s=24.0, seed=SEED):
+    """Times the reference's own CPU implementation (oracle/_ref, unmodified src/algn.c) -- or the
+    oracle port if the compiled reference is absent -- on a bounded sample of the same workload."""
+    from poy5_b200 import synth
+    from oracle import cost_matrix_oracle as cmo
+    full, _ = cmo.dna_matrices(*REGIME)
+    kind, lib, cm = None, None, None
+    try:
+        from oracle import refbind
+        if refbind.available(True):
+            lib = refbind.RefLib(True)
+            cm = lib.cm(full)
+            kind = "reference"
+    except Exception:
+        lib = None
+    if lib is None:
+        from oracle.port import Port
+        lib = Port()
+        cm = lib.cm(full)
+        kind = "port"
+    # per-length sample sized from the probe rates: ~0.17 GCUPS/core cost-only
+    share = budget_core_s / (2 * len(lengths))
+    cells_tot, secs_tot, aln_tot, sample = 0, 0.0, 0, []
+    for L in lengths:
+        n = int(max(threads, min(20000, share * 0.17e9 / (L * L))))
+        n = (n + threads - 1) // threads * threads
+        data, off = synth.pair_pool(seed + L, 0, n, L)
+        lens = np.diff(off).astype(np.int32)
+        la, lb = lens[0::2], lens[1::2]
+        oa, ob = off[0:-1:2], off[1::2]
+        swap = la > lb
+        oi = np.where(swap, ob, oa); oj = np.where(swap, oa, ob)
+        li = np.where(swap, lb, la).astype(np.int32); lj = np.where(swap, la, lb).astype(np.int32)
+        cells = int(((la - 1).astype(np.int64) * (lb - 1)).sum())
+        for mode in (0, 1):
+            t, _ = lib.batch_affine(cm, mode, data, oi, li, oj, lj, swap.astype(np.uint8), threads)
+            cells_tot += cells; secs_tot += t; aln_tot += n
+        sample.append("%d pairs @%d" % (n, L))
+    return dict(value=cells_tot / secs_tot / 1e9, unit="GCUPS", cores=threads, kind=kind,
+                sample="band off + band on, " + ", ".join(sample) + " (same generator/seed as the GPU workload)",
+                alignments_per_s=aln_tot / secs_tot, seconds=secs_tot)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    lengths = tuple(int(x) for x in args.lengths.split(","))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = []
+        for w in range(args.warmup + args.steps):
+            r = cpu_reference(lengths, threads, budget_core_s=max(4.0, 1.5 * threads), seed=SEED + 7919 * w)
+            if w >= args.warmup:
+                steps.append(r)
+        val = float(np.mean([r["value"] for r in steps])) if steps else 0.0
+        r = steps[-1]
+        line = dict(metric=METRIC, value=val, unit="GCUPS", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=1e3 * float(np.mean([x["seconds"] for x in steps])), higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="int32", data="synthetic", impl="reference",
+                    config=dict(workload="batched pairwise affine alignment sweep, lengths %s, band off + band on; each step a bounded CPU sample" % (list(lengths),),
+                                regime="subst %d indel %d gap_open %d" % REGIME),
+                    cpu_baseline=dict(value=val, unit="GCUPS", cores=r["cores"], kind=r["kind"], sample=r["sample"]),
+                    alignments_per_s=r["alignments_per_s"],
+                    e2e=dict(value=val, unit="GCUPS", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import poy5_b200 as pb
+    from poy5_b200 import synth, sequence
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.api import _ptr
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(dev)          # a real (non-legacy) stream shared by torch and the library
+    torch.cuda.set_stream(stream)
+    ctx = pb.Context(local_rank, stream.cuda_stream)
+    t2d = Two_D.of_transformations_and_gaps(REGIME[0], REGIME[1], REGIME[2])
+    cm = pb.CostModel(ctx, t2d.full)
+
+    peak_ops, peak_clock = ctx.microbench(0)   # IADD3-class issue rate, measured live
+    dpx_ops, _ = ctx.microbench(2)
+
+    # ---- build the workload: host (pinned) + device-resident copies --------------------------------
+    work = []   # one entry per (length, chunk)
+    total_cells = 0
+    total_aln = 0
+    h2d = d2h = 0
+    for L in lengths:
+        for (p0, n) in chunks_for(args.pairs, L, args.chunk_bases):
+            cap = synth.pair_pool_capacity(n, L)
+            pinned = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            data, off = synth.pair_pool(SEED + L, rank * args.pairs + p0, n, L, out=pinned.numpy(), nthreads=min(threads, 16))
+            lens = np.diff(off)
+            ia = np.arange(0, 2 * n, 2, dtype=np.int32); ib = ia + 1
+            la, lb = lens[ia], lens[ib]
+            swaped = (la > lb).astype(np.uint8)
+            si = np.where(swaped == 1, ib, ia).astype(np.int32); sj = np.where(swaped == 1, ia, ib).astype(np.int32)
+            caps = (la + lb + 2).astype(np.int64)
+            out_off = np.zeros(n, np.int64); np.cumsum(caps[:-1], out=out_off[1:])
+            out_total = int(caps.sum())
+            cells = int(((la - 1) * (lb - 1)).sum())
+            w = dict(L=L, n=n, data=data, off=off, ia=ia, ib=ib, si=si, sj=sj, swaped=swaped, out_off=out_off,
+                     out_total=out_total, cells=cells, pinned=pinned)
+            # device-resident inputs/outputs for the `value` measurement
+            w["d_data"] = torch.from_numpy(data).to(dev)
+            w["d_off"] = torch.from_numpy(off).to(dev)
+            w["d_ia"] = torch.from_numpy(ia).to(dev); w["d_ib"] = torch.from_numpy(ib).to(dev)
+            w["d_sw"] = torch.from_numpy(swaped).to(dev)
+            w["d_out_off"] = torch.from_numpy(out_off).to(dev)
+            w["d_cost0"] = torch.empty(n, dtype=torch.int32, device=dev)
+            w["d_cost1"] = torch.empty(n, dtype=torch.int32, device=dev)
+            w["d_len"] = torch.empty(4 * n, dtype=torch.int32, device=dev)
+            work.append(w)
+            total_cells += 2 * cells
+            total_aln += 2 * n
+            h2d += data.nbytes + off.nbytes + 2 * (ia.nbytes + ib.nbytes) + swaped.nbytes + out_off.nbytes
+            d2h += 2 * 4 * n + 16 * n + 4 * out_total
+    max_out = max(w["out_total"] for w in work)
+    d_outs = [torch.empty(max_out + 256, dtype=torch.uint8, device=dev) for _ in range(4)]
+    h_outs = [torch.empty(max_out + 256, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+    best = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    seg_events = {}
+
+    def reduce_costs(costs):
+        # candidate min-reduction: (cost << 32 | index) packed int64, min over the batch and over ranks
+        packed = (costs.to(torch.int64) << 32) | torch.arange(costs.numel(), device=dev, dtype=torch.int64)
+        m = packed.min().reshape(1)
+        if world > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MIN)
+        return m
+
+    def step_resident(record=False):
+        for wi, w in enumerate(work):
+            if record:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            pool = sequence.DevicePool(ctx, w["d_data"].data_ptr(), w["d_off"].data_ptr(), w["off"])
+            sequence.cost_2_dev(ctx, cm, pool, w["n"], w["d_ia"].data_ptr(), w["d_ib"].data_ptr(), w["d_cost0"].data_ptr())
+            if record:
+                e1.record(stream)
+            sequence.align_affine_3_dev(ctx, cm, pool, w["si"], w["sj"], w["d_sw"].data_ptr(), w["d_out_off"].data_ptr(),
+                                        w["d_cost1"].data_ptr(), d_outs[0].data_ptr(), d_outs[1].data_ptr(),
+                                        d_outs[2].data_ptr(), d_outs[3].data_ptr(), w["d_len"].data_ptr())
+            best.copy_(torch.minimum(reduce_costs(w["d_cost0"]), reduce_costs(w["d_cost1"])))
+            if record:
+                e2.record(stream)
+                seg_events[wi] = (e0, e1, e2)
+            pool.close()
+
+    def step_e2e():
+        res = 0
+        for w in work:
+            pool = pb.Pool(ctx, data=w["data"], offsets=w["off"])
+            cost0 = sequence.Align.cost_2(ctx, cm, pool, w["ia"], w["ib"])
+            n = w["n"]
+            cost1 = np.empty(n, np.int32); out_len = np.empty(4 * n, np.int32)
+            ctx.check(ctx.L.poy_batch_align_affine(ctx.h, cm.h, pool.h, n, _ptr(w["si"]), _ptr(w["sj"]), _ptr(w["swaped"]),
+                                                   _ptr(w["out_off"]), _ptr(cost1),
+                                                   ctypes.c_void_p(h_outs[0].data_ptr()), ctypes.c_void_p(h_outs[1].data_ptr()),
+                                                   ctypes.c_void_p(h_outs[2].data_ptr()), ctypes.c_void_p(h_outs[3].data_ptr()),
+                                                   _ptr(out_len), None))
+            res = min(int(cost0.min()), int(cost1.min()))
+            pool.close()
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident (value) measurement ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launches
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for k in range(args.steps):
+        step_resident(record=(k == args.steps - 1))
+    ev1.record(stream)
+    barrier()
+    launches = ctx.launches - launches0
+    ms = ev0.elapsed_time(ev1) / max(1, args.steps)
+    clocks = sampler.stop() if sampler else {}
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+
+    # per-segment breakdown (last timed step)
+    breakdown = []
+    kernel_ms = {}
+    for wi, w in enumerate(work):
+        if wi in seg_events:
+            e0, e1, e2 = seg_events[wi]
+            t_off, t_on = e0.elapsed_time(e1), e1.elapsed_time(e2)
+            breakdown.append(dict(L=w["L"], pairs=w["n"], band_off_ms=round(t_off, 3), band_on_ms=round(t_on, 3),
+                                  band_off_gcups=round(w["cells"] / t_off / 1e6, 2), band_on_gcups=round(w["cells"] / t_on / 1e6, 2),
+                                  band_off_aln_per_s=round(w["n"] / t_off * 1e3, 1), band_on_aln_per_s=round(w["n"] / t_on * 1e3, 1)))
+            kernel_ms.setdefault(w["L"], [0.0, 0])
+            kernel_ms[w["L"]][0] += t_off; kernel_ms[w["L"]][1] += w["cells"]
+
+    # ---- e2e measurement ------------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        te = (time.perf_counter() - t0) / max(1, args.steps)
+        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+        e2e = dict(value=world * total_cells / te / 1e9, unit="GCUPS", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   ms_per_step=1e3 * te, alignments_per_s=world * total_aln / te)
+
+    if rank == 0:
+        # dominant kernel: the gap-free cost-only wavefront (k_cost_affine<16,true>) on the longest length
+        Ltop = max(kernel_ms) if kernel_ms else lengths[-1]
+        k_ms, k_cells = kernel_ms.get(Ltop, (ms, total_cells))
+        achieved = k_cells * OPS_PER_CELL["gapfree"] / (k_ms * 1e-3) / 1e12
+        roofline = dict(bound="int32", kernel="k_cost_affine<16,true>", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
+                        frac=achieved / (peak_ops / 1e12), traffic=None,
+                        note="INT32 issue roofline: algorithmic scalar add/min per cell (%d, gap-free cost-only cell) x cells / "
+                             "launch time, vs the IADD3-class issue rate measured live by poy_microbench_int "
+                             "(DPX VIADDMNMX measured %.2f Tops/s). Launch time from CUDA events around the cost-only "
+                             "call on the L=%d segment (about 10%% of its pairs carry gap bits and run the 4-state kernel)."
+                             % (OPS_PER_CELL["gapfree"], dpx_ops / 1e12, Ltop),
+                        hbm_bytes_per_launch=None, sm_clock_mhz_microbench=peak_clock)
+        cpu = None
+        if not args.no_cpu:
+            try:
+                cpu = cpu_reference(lengths, threads)
+                cpu = dict(value=cpu["value"], unit=cpu["unit"], cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"],
+                           alignments_per_s=cpu["alignments_per_s"])
+            except Exception as e:  # the oracle always exists; report rather than hide
+                cpu = dict(value=None, unit="GCUPS", cores=threads, kind="unavailable", sample=str(e))
+        line = dict(metric=METRIC, value=world * total_cells / (ms * 1e-3) / 1e9, unit="GCUPS", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="int32", data="synthetic",
+                    config=dict(workload="configs[1]: batched pairwise affine alignment sweep, %d pairs per length per GPU, lengths %s bp, "
+                                         "Ukkonen band off (cost-only) and on (align+traceback+median), 1 GPU per rank" % (args.pairs, list(lengths)),
+                                regime="subst %d indel %d gap_open %d" % REGIME, l2="inputs larger than L2 (%.1f GB of sequences per step)" % (sum(w["data"].nbytes for w in work) / 1e9),
+                                pairs_per_length=args.pairs, lengths=list(lengths), parallelism="pairs sharded over %d GPU(s), NCCL min-reduce of candidate costs" % world),
+                    alignments_per_s=world * total_aln / (ms * 1e-3), breakdown=breakdown, clocks=clocks, e2e=e2e,
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

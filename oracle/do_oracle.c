@@ -465,3 +465,54 @@ int do_align_affine(const do_cm *c, do_scratch *sc, const u8 *si, int leni, cons
     lens[0] = rfinish(&med); lens[1] = rfinish(&medwg); lens[2] = rfinish(&ri); lens[3] = rfinish(&rj);
     return res;
 }
+
+/* ---- multi-threaded batch runner (CPU baseline when oracle/_ref is unavailable) --------- */
+#include <pthread.h>
+#include <time.h>
+typedef struct {
+    const do_cm *cm; int mode, n; const u8 *seqs; const long long *off_i, *off_j; const int *len_i, *len_j;
+    const u8 *swaped; int *cost; volatile int *next;
+} do_batch_job;
+
+static void *do_batch_worker(void *arg) {
+    do_batch_job *j = (do_batch_job *)arg;
+    do_scratch *sc = do_scratch_new();
+    int maxl = 0, p;
+    u8 *b0, *b1, *b2, *b3;
+    for (p = 0; p < j->n; p++) { if (j->len_i[p] > maxl) maxl = j->len_i[p]; if (j->len_j[p] > maxl) maxl = j->len_j[p]; }
+    b0 = malloc(2 * maxl + 4); b1 = malloc(2 * maxl + 4); b2 = malloc(2 * maxl + 4); b3 = malloc(2 * maxl + 4);
+    for (;;) {
+        int lens[4];
+        p = __sync_fetch_and_add(j->next, 1);
+        if (p >= j->n) break;
+        if (j->mode == 0)
+            j->cost[p] = do_cost_affine(j->cm, j->seqs + j->off_i[p], j->len_i[p], j->seqs + j->off_j[p], j->len_j[p]);
+        else
+            j->cost[p] = do_align_affine(j->cm, sc, j->seqs + j->off_i[p], j->len_i[p], j->seqs + j->off_j[p], j->len_j[p],
+                                         j->swaped ? j->swaped[p] : 0, b0, b1, b2, b3, lens, NULL);
+    }
+    free(b0); free(b1); free(b2); free(b3);
+    do_scratch_free(sc);
+    return NULL;
+}
+
+/* mode 0 = cost only, 1 = banded align + traceback.  Returns wall seconds. */
+double do_batch_affine(const do_cm *cm, int mode, int n, const u8 *seqs, const long long *off_i, const int *len_i,
+                       const long long *off_j, const int *len_j, const u8 *swaped, int *cost, int nthreads) {
+    pthread_t th[256];
+    do_batch_job jobs[256];
+    volatile int next = 0;
+    struct timespec t0, t1;
+    int t;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (t = 0; t < nthreads; t++) {
+        do_batch_job jb = { cm, mode, n, seqs, off_i, off_j, len_i, len_j, swaped, cost, &next };
+        jobs[t] = jb;
+        pthread_create(&th[t], NULL, do_batch_worker, &jobs[t]);
+    }
+    for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

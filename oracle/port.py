@@ -15,7 +15,7 @@ INT_MIN = -2**31
 def build(force=False):
     src = os.path.join(_HERE, "do_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-o", _SO, src])
+        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-o", _SO, src, "-lpthread"])
     return _SO
 
 
@@ -37,6 +37,9 @@ class Port:
         L.do_scratch_free.argtypes = [C.c_void_p]
         L.do_align_affine.argtypes = [C.c_void_p, C.c_void_p, _u8p, C.c_int, _u8p, C.c_int, C.c_int,
                                       _u8p, _u8p, _u8p, _u8p, _i32p, C.POINTER(AlignStats)]
+        L.do_batch_affine.restype = C.c_double
+        L.do_batch_affine.argtypes = [C.c_void_p, C.c_int, C.c_int, _u8p, C.POINTER(C.c_longlong), _i32p,
+                                      C.POINTER(C.c_longlong), _i32p, _u8p, _i32p, C.c_int]
         self.scratch = L.do_scratch_new()
 
     def cm(self, m):
@@ -65,3 +68,17 @@ class Port:
             raise RuntimeError("pass the shorter one as first")
         res = (r,) + tuple(o[:n].copy() for o, n in zip(outs, lens))
         return res + (st,) if with_stats else res
+
+    def batch_affine(self, cm, mode, seqs, off_i, len_i, off_j, len_j, swaped=None, nthreads=1):
+        """mode 0 = cost only, 1 = align+traceback.  -> (seconds, int32 costs)."""
+        seqs = np.ascontiguousarray(seqs, np.uint8)
+        off_i = np.ascontiguousarray(off_i, np.int64); off_j = np.ascontiguousarray(off_j, np.int64)
+        len_i = np.ascontiguousarray(len_i, np.int32); len_j = np.ascontiguousarray(len_j, np.int32)
+        n = len(len_i)
+        cost = np.zeros(n, np.int32)
+        sw = None if swaped is None else np.ascontiguousarray(swaped, np.uint8)
+        i64p = C.POINTER(C.c_longlong)
+        t = self.lib.do_batch_affine(cm, mode, n, _p8(seqs), off_i.ctypes.data_as(i64p), len_i.ctypes.data_as(_i32p),
+                                     off_j.ctypes.data_as(i64p), len_j.ctypes.data_as(_i32p),
+                                     None if sw is None else _p8(sw), cost.ctypes.data_as(_i32p), int(nthreads))
+        return t, cost

@@ -62,3 +62,42 @@ class Align:
         if stats:
             res["stats"] = st.reshape(n, 4)
         return res
+
+
+class DevicePool:
+    """A pool whose bytes already live in HBM (poy_pool_from_device): `d_data`/`d_off` are raw device
+    pointers (ints), `offsets` the host copy of the offsets."""
+
+    def __init__(self, ctx, d_data, d_off, offsets):
+        self.ctx = ctx
+        self.offsets = np.ascontiguousarray(offsets, np.int64)
+        self.nseq = len(self.offsets) - 1
+        self.lens = np.diff(self.offsets)
+        h = C.c_void_p()
+        ctx.check(ctx.L.poy_pool_from_device(ctx.h, C.c_void_p(d_data), C.c_void_p(d_off), _ptr(self.offsets), self.nseq,
+                                             C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.poy_pool_free(self.ctx.h, self.h)
+            self.h = None
+
+
+def cost_2_dev(ctx, cm, pool, n, d_a, d_b, d_cost):
+    """poy_batch_cost_affine_dev: index and result arrays are device pointers (ints); asynchronous."""
+    ctx.check(ctx.L.poy_batch_cost_affine_dev(ctx.h, cm.h, pool.h, int(n), C.c_void_p(d_a), C.c_void_p(d_b),
+                                              C.c_void_p(d_cost)))
+
+
+def align_affine_3_dev(ctx, cm, pool, h_si, h_sj, d_swaped, d_out_off, d_cost, d_median, d_medianwg, d_resi, d_resj,
+                       d_out_len):
+    """poy_batch_align_affine_dev: outputs stay in HBM.  h_si/h_sj (host int32, shorter first) drive the
+    band schedule; every d_* is a raw device pointer or 0."""
+    h_si = np.ascontiguousarray(h_si, np.int32); h_sj = np.ascontiguousarray(h_sj, np.int32)
+
+    def vp(x):
+        return C.c_void_p(x) if x else None
+    ctx.check(ctx.L.poy_batch_align_affine_dev(ctx.h, cm.h, pool.h, len(h_si), None, None, vp(d_swaped), _ptr(h_si),
+                                               _ptr(h_sj), vp(d_out_off), vp(d_cost), vp(d_median), vp(d_medianwg),
+                                               vp(d_resi), vp(d_resj), vp(d_out_len), None))

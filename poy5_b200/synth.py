@@ -73,3 +73,42 @@ def pair_batch(seed, n, length, subst=0.10, indel=0.01, frac_decorated=0.0, jitt
 def cells(pool_lens, a, b):
     """full-matrix cells (len_i-1)*(len_j-1) per pair."""
     return (pool_lens[a] - 1).astype(np.int64) * (pool_lens[b] - 1).astype(np.int64)
+
+
+# ---- fast C generator (poy5_b200/csrc/synth.c -> libpoysynth.so) -------------------------------
+_SYNTH = None
+
+
+def _synth_lib():
+    global _SYNTH
+    if _SYNTH is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpoysynth.so")
+        if not os.path.exists(path):
+            raise ImportError("libpoysynth.so is not built; run __graft_entry__.build()")
+        L = C.CDLL(path)
+        L.synth_pairs_capacity.restype = C.c_int64
+        L.synth_pairs_capacity.argtypes = [C.c_int64, C.c_int, C.c_double]
+        L.synth_pairs.restype = C.c_int64
+        L.synth_pairs.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        _SYNTH = L
+    return _SYNTH
+
+
+def pair_pool(seed, first_pair, n, length, jitter=0.0, subst=0.10, indel=0.01, decorated=0.10, out=None, nthreads=8):
+    """n pairs (pair p = sequences 2p, 2p+1) as (data uint8[total], offsets int64[2n+1]).
+    `out` may be a preallocated uint8 array of at least pair_pool_capacity() bytes (e.g. pinned)."""
+    L = _synth_lib()
+    cap = L.synth_pairs_capacity(n, length, jitter)
+    data = out if out is not None else np.empty(cap, np.uint8)
+    assert data.nbytes >= cap
+    off = np.empty(2 * n + 1, np.int64)
+    tot = L.synth_pairs(seed, first_pair, n, length, jitter, subst, indel, decorated, data.ctypes.data, off.ctypes.data,
+                        nthreads)
+    return data[:tot], off
+
+
+def pair_pool_capacity(n, length, jitter=0.0):
+    return _synth_lib().synth_pairs_capacity(n, length, jitter)

@@ -1,0 +1,45 @@
+"""Shared test inputs: seeded pair sets that cover the reference's edge cases."""
+import numpy as np
+from poy5_b200 import synth
+
+REGIMES = dict(synth.REGIMES, R4=(1, 1, 1), R5=(3, 2, 4))
+
+
+def edge_pairs(seed, n=300, maxlen=40):
+    """tiny / ragged / empty / decorated pairs (lengths 0..maxlen bases)."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for p in range(n):
+        L = int(rng.integers(0, maxlen))
+        anc = synth.random_seq(rng, L)
+        a = synth.evolve(rng, anc, 0.15, 0.06)
+        b = synth.evolve(rng, anc, 0.15, 0.06)
+        if p % 3 == 0:
+            a, b = synth.decorate(rng, a, 0.1, 0.1), synth.decorate(rng, b, 0.1, 0.1)
+        if p % 7 == 0:
+            b = synth.random_seq(rng, int(rng.integers(0, maxlen + 10)))
+        if p % 11 == 0:
+            a = np.zeros(0, np.uint8)
+        if p % 13 == 0:
+            a = np.full(int(rng.integers(1, 6)), 16, np.uint8)          # a run of pure gap codes
+        seqs += [synth.with_gap(a), synth.with_gap(b)]
+    idx = np.arange(n, dtype=np.int32)
+    return seqs, 2 * idx, 2 * idx + 1
+
+
+def witness_pairs():
+    """F5 / F6 witnesses of SURVEY.md 8c."""
+    return {
+        "R3": ([16, 4, 4, 4, 4, 2, 1, 2, 1], [16, 4, 4, 1, 4, 4, 2, 1, 2]),
+        "R2": ([16, 8, 8, 8, 4, 2, 8, 2, 2, 8, 4, 4, 4, 8, 1, 4, 4, 4, 4, 2],
+               [16, 1, 2, 1, 4, 4, 1, 4, 4, 2, 1, 2, 1, 8, 1, 8, 2, 2, 8, 4, 4, 4]),
+    }
+
+
+def oracle_align(P, pc, a, b):
+    """Sequence.Align.align_affine_3 semantics on top of the oracle: shorter first + swaped,
+    rows un-swapped on return.  -> (cost, median, medianwg, res_a, res_b)"""
+    sw = int(len(a) > len(b))
+    si, sj = (b, a) if sw else (a, b)
+    c, m, w, ri, rj = P.align_affine(pc, si, sj, sw)
+    return (c, m, w, rj, ri) if sw else (c, m, w, ri, rj)

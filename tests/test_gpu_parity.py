@@ -1,0 +1,142 @@
+"""Parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs,
+plus size-independent properties at the BASELINE sizes."""
+import numpy as np
+import pytest
+from oracle import cost_matrix_oracle as cmo
+from tests.helpers import REGIMES, edge_pairs, oracle_align
+from poy5_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def setup(ctx, regime):
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    s_, g_, go = regime
+    return pb.CostModel(ctx, Two_D.of_transformations_and_gaps(s_, g_, go).full), cmo.dna_matrices(s_, g_, go)[0]
+
+
+def check_batch(ctx, port, regime, seqs, ia, ib, align=True):
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, regime)
+    pc = port.cm(full)
+    pool = pb.Pool(ctx, seqs)
+    cost = Align.cost_2(ctx, cm, pool, ia, ib)
+    for p in range(len(ia)):
+        assert cost[p] == port.cost_affine(pc, seqs[ia[p]], seqs[ib[p]]), ("cost", p)
+    if align:
+        r = Align.align_affine_3(ctx, cm, pool, ia, ib)
+        for p in range(len(ia)):
+            oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+            assert oc == r["cost"][p], ("align cost", p)
+            assert np.array_equal(om, r["median"][p]) and np.array_equal(ow, r["medianwg"][p]), ("median", p)
+            assert np.array_equal(ra, r["res_a"][p]) and np.array_equal(rb, r["res_b"][p]), ("rows", p)
+    cm.close(); pool.close()
+
+
+@pytest.mark.parametrize("rname", list(REGIMES))
+def test_edge_cases(ctx, port, rname):
+    """empty, ragged, tiny (exact-emulation path), pure-gap runs, ambiguity and gap-bit codes"""
+    seqs, ia, ib = edge_pairs(31 + len(rname), n=500, maxlen=44)
+    check_batch(ctx, port, REGIMES[rname], seqs, ia, ib)
+
+
+@pytest.mark.parametrize("L,n,dec", [(150, 150, 0.3), (600, 60, 0.4), (1300, 24, 0.5), (2500, 8, 0.2)])
+@pytest.mark.parametrize("rname", ["R1", "R2", "R3"])
+def test_related_pairs(ctx, port, rname, L, n, dec):
+    seqs, ia, ib = synth.pair_batch(1000 + L, n, L, frac_decorated=dec, jitter=0.25)
+    check_batch(ctx, port, REGIMES[rname], seqs, ia, ib)
+
+
+def test_unrelated_pairs_wide_bands(ctx, port):
+    rng = np.random.default_rng(3)
+    seqs = []
+    for p in range(8):
+        seqs += [synth.with_gap(synth.random_seq(rng, 200 + 60 * p)), synth.with_gap(synth.random_seq(rng, 900))]
+    idx = np.arange(8, dtype=np.int32)
+    check_batch(ctx, port, REGIMES["R1"], seqs, 2 * idx, 2 * idx + 1)
+    check_batch(ctx, port, REGIMES["R2"], seqs, 2 * idx + 1, 2 * idx)   # longer first: swaped path
+
+
+def test_wrong_order_is_reported(ctx):
+    import ctypes
+    import poy5_b200 as pb
+    from poy5_b200.api import _ptr
+    cm, _ = setup(ctx, REGIMES["R1"])
+    pool = pb.Pool(ctx, [synth.with_gap([1, 2, 4]), synth.with_gap([1, 2])])
+    si = np.array([0], np.int32); sj = np.array([1], np.int32); cost = np.zeros(1, np.int32)
+    st = ctx.L.poy_batch_align_affine(ctx.h, cm.h, pool.h, 1, _ptr(si), _ptr(sj), None, None, _ptr(cost),
+                                      None, None, None, None, None, None)
+    assert st == -4 and b"shorter" in ctx.L.poy_last_error(ctx.h)   # "pass the shorter one as first"
+    cm.close(); pool.close()
+
+
+def test_linear_model_rejected(ctx):
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.sequence import Align
+    cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 1, None).full)
+    pool = pb.Pool(ctx, [synth.with_gap([1, 2, 4]), synth.with_gap([1, 2])])
+    with pytest.raises(pb.PoyError) as e:
+        Align.cost_2(ctx, cm, pool, [0], [1])
+    assert e.value.status == -6
+    cm.close(); pool.close()
+
+
+# ---- BASELINE sizes: size-independent properties + sampled oracle checks ------------------------------
+def _strip(row):
+    return row[row != 16]
+
+
+@pytest.mark.parametrize("L,n,sample", [(500, 20000, 40), (2000, 4000, 12), (10000, 400, 3)])
+def test_full_size_properties(ctx, port, L, n, sample):
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES["R1"])
+    pc = port.cm(full)
+    data, off = synth.pair_pool(0x504F5935 + L, 0, n, L)
+    pool = pb.Pool(ctx, data=data, offsets=off)
+    ia = np.arange(0, 2 * n, 2, dtype=np.int32); ib = ia + 1
+    c_ab = Align.cost_2(ctx, cm, pool, ia, ib)
+    c_ba = Align.cost_2(ctx, cm, pool, ib, ia)
+    assert np.array_equal(c_ab, c_ba)                       # the stub accepts either order
+    sub = np.arange(0, n, max(1, n // 2000))
+    r = Align.align_affine_3(ctx, cm, pool, ia[sub], ib[sub])
+    for q, p in enumerate(sub):
+        a, b = pool.seq(ia[p]), pool.seq(ib[p])
+        ra, rb = r["res_a"][q], r["res_b"][q]
+        assert len(ra) == len(rb) == len(r["medianwg"][q])
+        # implied alignment reproduces the inputs once the inserted pure gaps are removed
+        assert np.array_equal(np.concatenate([[16], _strip(ra[1:])]), np.concatenate([[16], _strip(a[1:])]))
+        assert np.array_equal(np.concatenate([[16], _strip(rb[1:])]), np.concatenate([[16], _strip(b[1:])]))
+        assert not np.any((ra[1:] == 16) & (rb[1:] == 16))  # no all-gap column
+        assert np.array_equal(r["median"][q], np.concatenate([[16], _strip(r["medianwg"][q][1:])]))
+        assert r["cost"][q] >= 0
+    # sampled pairs against the oracle at full length
+    rng = np.random.default_rng(L)
+    for q in rng.choice(len(sub), size=sample, replace=False):
+        p = sub[q]
+        a, b = pool.seq(ia[p]), pool.seq(ib[p])
+        assert c_ab[p] == port.cost_affine(pc, a, b)
+        oc, om, ow, ra, rb = oracle_align(port, pc, a, b)
+        assert oc == r["cost"][q] and np.array_equal(om, r["median"][q]) and np.array_equal(ow, r["medianwg"][q])
+        assert np.array_equal(ra, r["res_a"][q]) and np.array_equal(rb, r["res_b"][q])
+    cm.close(); pool.close()
+
+
+def test_arena_waves_do_not_change_results(ctx, port):
+    """a tiny direction arena forces many waves; results must be identical"""
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES["R1"])
+    seqs, ia, ib = synth.pair_batch(5, 300, 400, frac_decorated=0.3, jitter=0.2)
+    pool = pb.Pool(ctx, seqs)
+    r1 = Align.align_affine_3(ctx, cm, pool, ia, ib)
+    ctx.set_arena_limit(2 << 20)
+    r2 = Align.align_affine_3(ctx, cm, pool, ia, ib)
+    ctx.set_arena_limit(8 << 30)
+    assert np.array_equal(r1["cost"], r2["cost"])
+    for p in range(len(ia)):
+        assert np.array_equal(r1["median"][p], r2["median"][p]) and np.array_equal(r1["res_a"][p], r2["res_a"][p])
+    cm.close(); pool.close()
