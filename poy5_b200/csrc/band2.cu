@@ -1,0 +1,382 @@
+// Register-resident Ukkonen-band fill, second generation: k_band2<D, NW, GF>.
+//
+// Same algorithm and bit-exact semantics as band_affine.cu (which keeps the documentation of the
+// band geometry, the direction byte and the reference citations: algn_newkk_test_aff /
+// algn_newkk_fill_a_row_aff / ASSIGN_MINIMUM / algn_fill_gapnum, src/algn.c:2186-2306, 2113-2180,
+// 1936-1981, 126-176).  What changes is how the work is mapped to the machine:
+//
+//  * one CTA of NW warps per pair; thread t owns the D diagonals [t*D, (t+1)*D) and keeps the
+//    latest cell of each in registers, so a CTA covers bands up to NW*32*D diagonals
+//    (D=16, NW=8: 4096).  Strip edges cross lanes by one __shfl per sub-step and cross warps through
+//    12 bytes of shared memory + one __syncthreads per sub-step;
+//  * the tie logic is branch free: every tie mask of the reference equals "candidate == minimum"
+//    (a strict improvement resets the mask, an equal candidate joins it), so a cell is a handful of
+//    VIMNMX/VIADDMNMX, ISETP and SEL instead of nested compare chains;
+//  * per-row / per-column gap parameters ride in sliding register windows (an anti-diagonal step
+//    moves every thread one row down and one column right), so a cell does no global loads;
+//  * the two unsigned-short gap counters travel packed in one register and are updated with the
+//    DPX 16x2 max (__vimax3_u16x2); exact while len_i + len_j < 65535 (longer pairs take the
+//    generic kernel);
+//  * the 16x16 cost table is replicated once per shared-memory bank (32 KB) so the per-cell lookup
+//    is conflict free whatever symbols the 32 lanes hold;
+//  * the anti-diagonals a < delta+k+2, where some cell of the band still lies outside the matrix,
+//    run a predicated prologue; afterwards every cell with d < B either is valid or lies beyond the
+//    last row/column, where garbage can no longer reach a valid cell (the right-border rule cuts the
+//    only path), so the steady-state loop carries no validity predicates at all;
+//  * GF = both sequences free of gap-bit symbols: the EB state and everything that depends on gap
+//    bits disappear (EB >= INF can neither win nor tie a minimum there).
+#include <stdlib.h>
+#include <type_traits>
+#include "common.cuh"
+
+namespace {
+
+template <int N, class F>
+__device__ __forceinline__ void sfor(F &&f) {
+    if constexpr (N > 0) {
+        sfor<N - 1>(f);
+        f(std::integral_constant<int, N - 1>{});
+    }
+}
+
+// window entries.  meta: bits 0-15 shared-memory byte offset of the cost row / column,
+// bit 16 symbol has the gap bit, bit 17 previous symbol has it, bit 18 gap opening is free here.
+struct Ent { int ext, opn, meta; };
+#define M_HAS (1 << 16)
+#define M_PREV (1 << 17)
+#define M_GOZ (1 << 18)
+
+template <bool GF>
+__device__ __forceinline__ Ent row_entry(const int4 v) {
+    Ent e;
+    e.ext = v.x; e.opn = GF ? 0 : v.y;
+    e.meta = ((v.w & 15) << 11) | ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
+    return e;
+}
+template <bool GF>
+__device__ __forceinline__ Ent col_entry(const int4 v, int lane) {
+    Ent e;
+    e.ext = v.x; e.opn = GF ? 0 : v.y;
+    e.meta = (((v.w & 15) << 7) + (lane << 2)) | ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
+    return e;
+}
+
+// One band cell.  On entry CB/EV/EH/EB/G hold the diagonal predecessor (i-1,j-1), on exit the new
+// cell.  l* = (i,j-1), u* = (i-1,j).  EDGE adds the j == 0 handling of the prologue.
+template <bool GF, bool EDGE>
+__device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, unsigned &G, int lCB, int lEH, unsigned lG,
+                                         int uCB, int uEV, unsigned uG, const Ent r, const Ent c, const char *s_tab,
+                                         int GO, bool lb, bool rb, bool jpos, bool swaped) {
+    // extend horizontal / vertical: ties take the opening (END_* flag)
+    bool stopH, stopV;
+    int nEH, nEV;
+    if (GF) {   // no gap bits: ext = ge, opn = GO + ge, so the common ge is added after the minimum
+        const int tH = lCB + GO, tV = uCB + GO;
+        stopH = !(lEH < tH); nEH = min(lEH, tH) + c.ext;
+        stopV = !(uEV < tV); nEV = min(uEV, tV) + r.ext;
+    } else {
+        const int tH = lCB + c.opn, xH = lEH + c.ext;
+        stopH = !(xH < tH); nEH = min(xH, tH);
+        const int tV = uCB + r.opn, xV = uEV + r.ext;
+        stopV = !(xV < tV); nEV = min(xV, tV);
+    }
+    if (lb) { nEH = POY_INF; stopH = false; }
+    if (rb) { nEV = POY_INF; stopV = false; }
+    int nCB, nEB = POY_INF;
+    bool eqV, eqH, eqD = false, stopB = false;
+    {
+        const int diag = *(const int *)(s_tab + (r.meta & 0xFFFF) + (c.meta & 0xFFFF));
+        int m;
+        if (GF) {
+            m = __vimin3_s32(CB, EV, EH);
+            eqV = (EV == m); eqH = (EH == m);
+        } else {
+            const bool hg_i = (r.meta & M_HAS) != 0, hg_j = (c.meta & M_HAS) != 0;
+            // at the left border the reference's "previous column symbol" is the column symbol itself
+            const bool pg_j = lb ? hg_j : ((c.meta & M_PREV) != 0);
+            const bool both = hg_i && hg_j;
+            const bool clean = !(r.meta & M_PREV) && !pg_j;
+            const int dg = both ? 0 : POY_INF;
+            const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
+            const int xB = EB + dg, tB = CB + od;
+            stopB = !(xB < tB);
+            nEB = min(xB, tB);
+            const bool goz_i = (r.meta & M_GOZ) != 0, goz_j = (c.meta & M_GOZ) != 0;
+            const int v = EV + ((hg_i && !goz_j) ? GO : 0);
+            const int h = EH + ((hg_j && !goz_i) ? GO : 0);
+            const int dd = EB + ((goz_i && goz_j) ? 0 : GO);
+            m = min(__vimin3_s32(CB, v, h), dd);
+            eqV = (v == m); eqH = (h == m); eqD = (dd == m);
+        }
+        nCB = m + diag;
+    }
+    if (EDGE && !jpos) { nCB = POY_INF; nEB = POY_INF; eqV = eqH = eqD = false; stopB = false; }
+    // final minimum and its tie set
+    int fin = __vimin3_s32(nEH, nEV, nCB);
+    if (!GF) fin = min(fin, nEB);
+    const bool fH = (nEH == fin), fV = (nEV == fin), fA = (nCB == fin);
+    const bool fD = GF ? false : (nEB == fin);
+    const bool heqv = fH && fV;
+    // gap counters: component-wise max over the chosen predecessors (+1 on the side that gaps)
+    const unsigned cD = (fA || fD) ? G : 0u;
+    const unsigned cL = fH ? lG + 1u : 0u;
+    const unsigned cU = fV ? uG + 0x10000u : 0u;
+    G = __vimax3_u16x2(cD, cL, cU);
+    // traceback byte
+    unsigned todo, nxt;
+    if (!swaped) {
+        todo = fV ? 0u : fH ? 1u : fD ? 2u : 3u;
+        nxt = eqV ? 0u : eqH ? 4u : eqD ? 8u : 12u;
+    } else {
+        todo = fH ? 1u : fV ? 0u : fD ? 2u : 3u;
+        nxt = eqH ? 4u : eqV ? 0u : eqD ? 8u : 12u;
+    }
+    unsigned b = todo | nxt;
+    if (stopV || heqv) b |= 16u;
+    if (stopH || heqv) b |= 32u;
+    if (stopB) b |= 64u;
+    CB = nCB; EV = nEV; EH = nEH; EB = nEB;
+    return b;
+}
+
+template <int H>
+__device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed) {
+    if (H == 1) *p = (uint8_t)packed;
+    else if (H == 2) *(uint16_t *)p = (uint16_t)packed;
+    else if (H == 4) *(uint32_t *)p = (uint32_t)packed;
+    else *(unsigned long long *)p = packed;
+}
+
+}  // namespace
+
+// NW warps cooperate on one pair.  NW == 1: a CTA holds WPB independent warps (each with its own
+// pair) that only share the replicated cost table.
+template <int D, int NW, bool GF, int WPB>
+__global__ void __launch_bounds__(WPB * 32)
+k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
+        const int *__restrict__ h0v, const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state,
+        int *ebrow, uint8_t *dir) {
+    constexpr int H = D / 2;
+    __shared__ int s_tab_i[256 * 32];  // cost16 replicated per bank: entry e of lane l at [e*32 + l]
+    __shared__ int s_job;
+    __shared__ int s_xe[NW][4];        // slot-0 state of lane 0 of every warp (read by the warp to its left)
+    __shared__ int s_xo[NW][4];        // slot-(D-1) state of lane 31 of every warp (read by the warp to its right)
+    static_assert(NW == 1 || WPB == NW, "cooperating warps fill the whole CTA");
+    const int lane = threadIdx.x & 31, warp = (NW == 1) ? 0 : (threadIdx.x >> 5);
+    const int tid = (NW == 1) ? lane : (int)threadIdx.x;   // thread index within the group that owns the pair
+    for (int x = threadIdx.x; x < 256 * 32; x += WPB * 32) s_tab_i[x] = cm->cost16[x >> 5];
+    __syncthreads();
+    const char *s_tab = (const char *)s_tab_i;
+    const int GO = cm->gap_open;
+
+    for (;;) {
+        int job;
+        if (NW == 1) {
+            job = 0;
+            if (lane == 0) job = atomicAdd(counter, 1);
+            job = __shfl_sync(0xffffffffu, job, 0);
+        } else {
+            __syncthreads();
+            if (tid == 0) s_job = atomicAdd(counter, 1);
+            __syncthreads();
+            job = s_job;
+        }
+        if (job >= njobs) break;
+        const BandJob J = jobs[job];
+        const int lasti = J.lasti, lastj = J.lastj, k = J.k;
+        const bool swaped = J.swaped != 0;
+        if (lasti == 0) continue;
+        const int delta = lastj - lasti, B = delta + 2 * k + 1;
+        const int4 *rp = rowp + J.off_i;
+        const int4 *cp = colp + J.off_j;
+        const int *h0 = h0v + J.off_j;
+        int *eb = ebrow + J.eb_off;
+        PairState *st = state + J.pair;
+        uint8_t *dbase = dir + J.dir_off;
+        const int stride = J.stride;
+        const int d0 = tid * D;
+        const int eh00 = st->eh00;
+        const int rbslot = (B - 1) - d0;  // slot holding the right border, if 0 <= rbslot < D
+
+        int CB[D], EV[D], EH[D], EB[D];
+        unsigned G[D];
+        sfor<D>([&](auto uc) {
+            constexpr int u = decltype(uc)::value;
+            const int d = d0 + u, j0 = d - k;
+            if (d < B && j0 >= 0 && j0 <= lastj) {  // row 0 (src/algn.c:2222-2247)
+                CB[u] = h0[j0];
+                EH[u] = j0 == 0 ? eh00 : h0[j0];
+                EV[u] = POY_INF;
+                EB[u] = GF ? POY_INF : eb[j0];
+                G[u] = (unsigned)j0 & 0xFFFFu;
+            } else {
+                CB[u] = EV[u] = EH[u] = EB[u] = POY_INF; G[u] = 0u;
+            }
+        });
+
+        // sliding windows: R[h] = row i0-h, C[h] = column j0+h
+        int a = k & 1;
+        int i0 = (a - d0 + k) >> 1, j0 = a - i0;
+        Ent R[H], C[H + 1];
+        auto load_row = [&](int i) { i = i < 0 ? 0 : (i > lasti ? lasti : i); return row_entry<GF>(rp[i]); };
+        auto load_col = [&](int j) { j = j < 0 ? 0 : (j > lastj ? lastj : j); return col_entry<GF>(cp[j], lane); };
+        sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; R[h] = load_row(i0 - h); });
+        sfor<H + 1>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = load_col(j0 + h); });
+
+        if (NW > 1) {
+            if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
+            if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
+            __syncthreads();
+        } else {
+            __syncwarp();
+        }
+
+        const int a_end = lasti + lastj;
+        int a_main = delta + k + 2;                     // first anti-diagonal whose band cells all have i >= 1, j >= 1
+        if ((a_main ^ a) & 1) ++a_main;
+        const int istar = lasti & ~1;                   // last even row: source of the stale EB row
+
+        // one loop iteration = anti-diagonals a (even diagonals) and a+1 (odd diagonals)
+        auto iteration = [&](auto edge_c) {
+            constexpr bool EDGE = decltype(edge_c)::value;
+            // ---- even diagonals ----
+            {
+                int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
+                int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
+                unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
+                if (NW > 1 && lane == 0 && warp > 0) { sCB = s_xo[warp - 1][0]; sEH = s_xo[warp - 1][1]; sG = (unsigned)s_xo[warp - 1][2]; }
+                unsigned long long packed = 0;
+                sfor<H>([&](auto hc) {
+                    constexpr int h = decltype(hc)::value;
+                    constexpr int u = 2 * h;
+                    const int i = i0 - h, j = j0 + h, d = d0 + u;
+                    bool valid = true;
+                    if (EDGE) valid = (d < B) && (i >= 1) && (i <= lasti) && (j >= 0) && (j <= lastj);
+                    if (valid) {
+                        int lCB, lEH; unsigned lG;
+                        if constexpr (u == 0) { lCB = sCB; lEH = sEH; lG = sG; }
+                        else { lCB = CB[u > 0 ? u - 1 : 0]; lEH = EH[u > 0 ? u - 1 : 0]; lG = G[u > 0 ? u - 1 : 0]; }
+                        bool lb = false;
+                        if constexpr (u == 0) lb = (tid == 0);
+                        if (EDGE) lb = lb || (j == 0);
+                        const unsigned b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
+                                                          R[h], C[h], s_tab, GO, lb, u == rbslot, j > 0, swaped);
+                        packed |= (unsigned long long)b << (8 * h);
+                        if (!GF) {
+                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
+                        }
+                    }
+                });
+                store_dir<H>(dbase + (size_t)a * stride + tid * H, packed);
+                if (NW > 1) {
+                    if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
+                    __syncthreads();
+                }
+            }
+            // ---- odd diagonals ----
+            {
+                int sCB = __shfl_down_sync(0xffffffffu, CB[0], 1);
+                int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
+                unsigned sG = __shfl_down_sync(0xffffffffu, G[0], 1);
+                if (NW > 1 && lane == 31 && warp < NW - 1) { sCB = s_xe[warp + 1][0]; sEV = s_xe[warp + 1][1]; sG = (unsigned)s_xe[warp + 1][2]; }
+                unsigned long long packed = 0;
+                sfor<H>([&](auto hc) {
+                    constexpr int h = decltype(hc)::value;
+                    constexpr int u = 2 * h + 1;
+                    const int i = i0 - h, j = j0 + h + 1, d = d0 + u;
+                    bool valid = true;
+                    if (EDGE) valid = (d < B) && (i >= 1) && (i <= lasti) && (j >= 0) && (j <= lastj);
+                    if (valid) {
+                        int uCB, uEV; unsigned uG;
+                        if constexpr (u == D - 1) { uCB = sCB; uEV = sEV; uG = sG; }
+                        else { constexpr int uu = u < D - 1 ? u + 1 : u; uCB = CB[uu]; uEV = EV[uu]; uG = G[uu]; }
+                        bool lb = false;
+                        if (EDGE) lb = (j == 0);
+                        const unsigned b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
+                                                          R[h], C[h + 1], s_tab, GO, lb, u == rbslot, j > 0, swaped);
+                        packed |= (unsigned long long)b << (8 * h);
+                        if (!GF) {
+                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
+                        }
+                    }
+                });
+                store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, packed);
+                if (NW > 1) {
+                    if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
+                    __syncthreads();
+                }
+            }
+            // ---- slide the windows one row down / one column right ----
+            sfor<H - 1>([&](auto hc) { constexpr int h = H - 1 - decltype(hc)::value; R[h] = R[h - 1]; });
+            sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = C[h + 1]; });
+            ++i0; ++j0;
+            R[0] = load_row(i0);
+            C[H] = load_col(j0 + H);
+        };
+
+        for (; a <= a_end && a < a_main; a += 2) iteration(std::true_type{});
+        for (; a <= a_end; a += 2) iteration(std::false_type{});
+
+        // result: the cell (lasti, lastj) is the latest cell of diagonal delta + k
+        const int dstar = delta + k;
+        if (tid == dstar / D) {
+            sfor<D>([&](auto uc) {
+                constexpr int u = decltype(uc)::value;
+                if (u == dstar % D) {
+                    int fin = __vimin3_s32(EH[u], EV[u], CB[u]);
+                    if (!GF) fin = min(fin, EB[u]);
+                    st->cost = fin;
+                    st->gapnum = max((int)(G[u] & 0xFFFFu), (int)(G[u] >> 16));
+                }
+            });
+        }
+        if (tid == 0 && min(k, lasti) >= 2) st->eh00 = POY_INF;  // an even row wrote EH[.][0] = INF into row buffer 0
+    }
+}
+
+template <int D, int NW>
+static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                              bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+    cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
+    if (e != cudaSuccess) return e;
+    constexpr int WPB = NW == 1 ? 8 : NW;
+    const int groups_per_block = WPB / NW;
+    int blocks = (njobs + groups_per_block - 1) / groups_per_block;
+    const int cap = ctx->sm_count * 6;   // more CTAs than can be resident just queue behind the persistent ones
+    if (blocks > cap) blocks = cap;
+    if (gapfree)
+        k_band2<D, NW, true, WPB><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
+                                                                         d_counter, d_state, d_ebrow, d_dir);
+    else
+        k_band2<D, NW, false, WPB><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
+                                                                          d_counter, d_state, d_ebrow, d_dir);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+// class = number of diagonals one CTA covers: 64, 128, 256, 512, 1024, 2048, 4096
+int band2_class_for(long long B) {
+    const int classes[7] = { 64, 128, 256, 512, 1024, 2048, 4096 };
+    for (int c = 0; c < 7; ++c) if (B <= classes[c]) return classes[c];
+    return 0;
+}
+int band2_stride_for(int cls) { return cls / 2; }  // bytes per anti-diagonal = diagonals / 2
+
+cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
+                         bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+    if (njobs <= 0) return cudaSuccess;
+    static int wide_d = 0;   // diagonals per thread for the classes above 256 (POY_BAND_D=8|16, tuning knob)
+    if (!wide_d) { const char *e = getenv("POY_BAND_D"); wide_d = (e && atoi(e) == 16) ? 16 : 8; }
+#define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, d_counter, d_state, d_ebrow, d_dir)
+    switch (cls) {
+        case 64: L1(2, 1);
+        case 128: L1(4, 1);
+        case 256: L1(8, 1);
+        case 512: if (wide_d == 16) L1(16, 1); else L1(8, 2);
+        case 1024: if (wide_d == 16) L1(16, 2); else L1(8, 4);
+        case 2048: if (wide_d == 16) L1(16, 4); else L1(8, 8);
+        case 4096: if (wide_d == 16) L1(16, 8); else L1(8, 16);
+    }
+#undef L1
+    return cudaErrorInvalidValue;
+}

@@ -48,6 +48,7 @@ struct poy_pool {
     int *d_g0;             // cost-only entry point: EH[0][j] - GO = sum of prepend (src/algn.c:1847)
     uint8_t *d_gapfree;    // per sequence: 1 if no base at index >= 1 carries the gap bit
     int64_t *h_off;        // host copy of the offsets
+    uint8_t *h_gapfree;    // host copy of d_gapfree (valid once the parameters have been computed)
     int32_t nseq;
     int64_t nbytes;
     bool owns_data;
@@ -107,6 +108,10 @@ cudaError_t launch_cost_affine_split(poy_ctx *ctx, const poy_cm *cm, const poy_p
                                      size_t bound_stride, int blocks, int *d_cost);
 cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                              int dclass, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
+cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
+                         bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
+int band2_class_for(long long B);
+int band2_stride_for(int cls);
 cudaError_t launch_band_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                                 PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_work, size_t work_stride,
                                 int blocks);

@@ -324,6 +324,7 @@ extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
     if (p->owns_data) { cudaFree(p->d_data); cudaFree(p->d_off); }
     cudaFree(p->d_rowp); cudaFree(p->d_colp); cudaFree(p->d_h0); cudaFree(p->d_g0); cudaFree(p->d_gapfree);
     free(p->h_off);
+    free(p->h_gapfree);
     delete p;
 }
 
@@ -335,6 +336,7 @@ static poy_status pool_new(poy_ctx *ctx, const int64_t *h_off, int32_t nseq, poy
     memset(p, 0, sizeof *p);
     p->nseq = nseq;
     p->nbytes = h_off[nseq];
+    p->h_gapfree = (uint8_t *)calloc((size_t)nseq + 1, 1);
     p->h_off = (int64_t *)malloc(sizeof(int64_t) * (nseq + 1));
     memcpy(p->h_off, h_off, sizeof(int64_t) * (nseq + 1));
     *out = p;
@@ -379,6 +381,8 @@ static poy_status ensure_params(poy_ctx *ctx, const poy_cm *cm, const poy_pool *
     poy_pool *pool = const_cast<poy_pool *>(cpool);
     if (pool->params_for == cm) return POY_OK;
     CK(launch_params(ctx, cm, pool));
+    CK(cudaMemcpyAsync(pool->h_gapfree, pool->d_gapfree, (size_t)pool->nseq, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     pool->params_for = cm;
     return POY_OK;
 }
@@ -446,7 +450,7 @@ extern "C" poy_status poy_batch_cost_affine(poy_ctx *ctx, const poy_cm *cm, cons
 // ---- batch banded affine with traceback ------------------------------------------------------------------
 namespace {
 struct HostPair {
-    int lasti, lastj, T, k, dclass, stride;
+    int lasti, lastj, T, k, dclass, stride, gapfree;
     int64_t off_i, off_j, eb_off, dir_bytes;
     int iterations;
     int64_t cells;
@@ -499,6 +503,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     poy_status s = domain_check(ctx, cm, maxsum);
     if (s != POY_OK) return s;
     if ((s = ensure_params(ctx, cm, pool)) != POY_OK) return s;
+    for (int p = 0; p < n; ++p) hp[p].gapfree = pool->h_gapfree[h_si[p]] && pool->h_gapfree[h_sj[p]];
 
     void *v_state, *v_eb, *v_jobs, *v_misc, *v_pin, *v_pin2;
     if ((s = scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
@@ -537,8 +542,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             h.k = pp >= h.lasti ? h.lasti - 1 : pp;
             if (h.lasti == 0) h.k = 0;
             const int64_t B = (int64_t)delta + 2 * (int64_t)h.k + 1;
-            h.dclass = h.lasti == 0 ? 2 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : 0;
-            h.stride = h.dclass ? 16 * h.dclass : (int)(((B + 1) / 2 + 15) & ~15ll);
+            // the packed 16x2 gap counters of k_band2 are exact while len_i + len_j < 65535
+            h.dclass = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2 >= 65535) ? 0 : band2_class_for(B);
+            h.stride = h.dclass ? band2_stride_for(h.dclass) : (int)(((B + 1) / 2 + 15) & ~15ll);
             h.dir_bytes = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2) * h.stride;
             h.iterations++;
             h.cells += band_cells(h.lasti, h.lastj, h.k);
@@ -547,6 +553,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         order = active;
         std::sort(order.begin(), order.end(), [&](int x, int y) {
             if (hp[x].dclass != hp[y].dclass) return hp[x].dclass > hp[y].dclass;
+            if (hp[x].gapfree != hp[y].gapfree) return hp[x].gapfree > hp[y].gapfree;
             if (hp[x].dir_bytes != hp[y].dir_bytes) return hp[x].dir_bytes > hp[y].dir_bytes;
             return x < y;
         });
@@ -579,14 +586,14 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
             }
             CK(cudaMemcpyAsync(d_jobs, hj, sizeof(BandJob) * (size_t)nj, cudaMemcpyHostToDevice, ctx->stream));
-            // launch per class (jobs of one class are contiguous)
-            int q0 = 0;
+            // launch per (class, gap-free) group (contiguous after the sort); each launch gets its own work counter
+            int q0 = 0, nlaunch = 0;
             while (q0 < nj) {
-                const int cls = hp[order[pos + q0]].dclass;
+                const int cls = hp[order[pos + q0]].dclass, gf = hp[order[pos + q0]].gapfree;
                 int q1 = q0;
-                while (q1 < nj && hp[order[pos + q1]].dclass == cls) ++q1;
+                while (q1 < nj && hp[order[pos + q1]].dclass == cls && hp[order[pos + q1]].gapfree == gf) ++q1;
                 if (cls != 0) {
-                    CK(launch_band_fill(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter, d_state, d_eb, d_dir));
+                    CK(launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, d_counter + (nlaunch++ & 7), d_state, d_eb, d_dir));
                 } else {
                     void *v_work;
                     const size_t wstride = 6 * (size_t)((gen_width + 31) & ~31ll);
