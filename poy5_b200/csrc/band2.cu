@@ -50,14 +50,16 @@ template <bool GF>
 __device__ __forceinline__ Ent row_entry(const int4 v) {
     Ent e;
     e.ext = v.x; e.opn = GF ? 0 : v.y;
-    e.meta = ((v.w & 15) << 11) | ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
+    e.meta = ((v.w & 15) << 11);
+    if (!GF) e.meta |= ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
     return e;
 }
 template <bool GF>
 __device__ __forceinline__ Ent col_entry(const int4 v, int lane) {
     Ent e;
     e.ext = v.x; e.opn = GF ? 0 : v.y;
-    e.meta = (((v.w & 15) << 7) + (lane << 2)) | ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
+    e.meta = (((v.w & 15) << 7) + (lane << 2));
+    if (!GF) e.meta |= ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
     return e;
 }
 
@@ -85,7 +87,8 @@ __device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, uns
     int nCB, nEB = POY_INF;
     bool eqV, eqH, eqD = false, stopB = false;
     {
-        const int diag = *(const int *)(s_tab + (r.meta & 0xFFFF) + (c.meta & 0xFFFF));
+        const int diag = GF ? *(const int *)(s_tab + r.meta + c.meta)
+                            : *(const int *)(s_tab + (r.meta & 0xFFFF) + (c.meta & 0xFFFF));
         int m;
         if (GF) {
             m = __vimin3_s32(CB, EV, EH);
@@ -123,14 +126,12 @@ __device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, uns
     const unsigned cU = fV ? uG + 0x10000u : 0u;
     G = __vimax3_u16x2(cD, cL, cU);
     // traceback byte
-    unsigned todo, nxt;
-    if (!swaped) {
-        todo = fV ? 0u : fH ? 1u : fD ? 2u : 3u;
-        nxt = eqV ? 0u : eqH ? 4u : eqD ? 8u : 12u;
-    } else {
-        todo = fH ? 1u : fV ? 0u : fD ? 2u : 3u;
-        nxt = eqH ? 4u : eqV ? 0u : eqD ? 8u : 12u;
-    }
+    // priorities V > H > D > A, or H > V > D > A when the caller swapped the operands (choose_dir):
+    // the two orders differ only when V and H tie
+    unsigned todo = fV ? 0u : fH ? 1u : fD ? 2u : 3u;
+    unsigned nxt = eqV ? 0u : eqH ? 4u : eqD ? 8u : 12u;
+    if (swaped && heqv) todo = 1u;
+    if (swaped && eqV && eqH) nxt = 4u;
     unsigned b = todo | nxt;
     if (stopV || heqv) b |= 16u;
     if (stopH || heqv) b |= 32u;
@@ -235,6 +236,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         int a_main = delta + k + 2;                     // first anti-diagonal whose band cells all have i >= 1, j >= 1
         if ((a_main ^ a) & 1) ++a_main;
         const int istar = lasti & ~1;                   // last even row: source of the stale EB row
+        const bool warp_in_band = (NW == 1) || (warp * 32 * D < B);   // warps wholly right of the band just keep the barriers company
 
         // one loop iteration = anti-diagonals a (even diagonals) and a+1 (odd diagonals)
         auto iteration = [&](auto edge_c) {
@@ -246,6 +248,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
                 if (NW > 1 && lane == 0 && warp > 0) { sCB = s_xo[warp - 1][0]; sEH = s_xo[warp - 1][1]; sG = (unsigned)s_xo[warp - 1][2]; }
                 unsigned long long packed = 0;
+                if (warp_in_band)
                 sfor<H>([&](auto hc) {
                     constexpr int h = decltype(hc)::value;
                     constexpr int u = 2 * h;
@@ -267,7 +270,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         }
                     }
                 });
-                store_dir<H>(dbase + (size_t)a * stride + tid * H, packed);
+                if (warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, packed);
                 if (NW > 1) {
                     if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
                     __syncthreads();
@@ -280,6 +283,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 unsigned sG = __shfl_down_sync(0xffffffffu, G[0], 1);
                 if (NW > 1 && lane == 31 && warp < NW - 1) { sCB = s_xe[warp + 1][0]; sEV = s_xe[warp + 1][1]; sG = (unsigned)s_xe[warp + 1][2]; }
                 unsigned long long packed = 0;
+                if (warp_in_band)
                 sfor<H>([&](auto hc) {
                     constexpr int h = decltype(hc)::value;
                     constexpr int u = 2 * h + 1;
@@ -300,7 +304,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         }
                     }
                 });
-                store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, packed);
+                if (warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, packed);
                 if (NW > 1) {
                     if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
                     __syncthreads();
@@ -310,8 +314,10 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             sfor<H - 1>([&](auto hc) { constexpr int h = H - 1 - decltype(hc)::value; R[h] = R[h - 1]; });
             sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = C[h + 1]; });
             ++i0; ++j0;
-            R[0] = load_row(i0);
-            C[H] = load_col(j0 + H);
+            if (warp_in_band) {
+                R[0] = load_row(i0);
+                C[H] = load_col(j0 + H);
+            }
         };
 
         for (; a <= a_end && a < a_main; a += 2) iteration(std::true_type{});
@@ -360,22 +366,25 @@ int band2_class_for(long long B) {
     for (int c = 0; c < 7; ++c) if (B <= classes[c]) return classes[c];
     return 0;
 }
-int band2_stride_for(int cls) { return cls / 2; }  // bytes per anti-diagonal = diagonals / 2
+// bytes per anti-diagonal: one per two diagonals; above 256 diagonals only the warps that reach into the
+// band store (128 bytes each)
+int band2_stride_for(int cls, long long B) {
+    if (cls <= 256) return cls / 2;
+    return (int)((B + 255) / 256) * 128;
+}
 
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
                          bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
     if (njobs <= 0) return cudaSuccess;
-    static int wide_d = 0;   // diagonals per thread for the classes above 256 (POY_BAND_D=8|16, tuning knob)
-    if (!wide_d) { const char *e = getenv("POY_BAND_D"); wide_d = (e && atoi(e) == 16) ? 16 : 8; }
 #define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, d_counter, d_state, d_ebrow, d_dir)
     switch (cls) {
         case 64: L1(2, 1);
         case 128: L1(4, 1);
         case 256: L1(8, 1);
-        case 512: if (wide_d == 16) L1(16, 1); else L1(8, 2);
-        case 1024: if (wide_d == 16) L1(16, 2); else L1(8, 4);
-        case 2048: if (wide_d == 16) L1(16, 4); else L1(8, 8);
-        case 4096: if (wide_d == 16) L1(16, 8); else L1(8, 16);
+        case 512: L1(8, 2);    // 8 diagonals per thread measured faster than 16 (registers -> occupancy)
+        case 1024: L1(8, 4);
+        case 2048: L1(8, 8);
+        case 4096: L1(8, 16);
     }
 #undef L1
     return cudaErrorInvalidValue;

@@ -323,24 +323,30 @@ k_band_generic(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, cons
 }
 
 // ---- traceback: backtrace_aff (src/algn.c:1715-1819) -------------------------------------------
-// One thread per pair.  Results are written right to left into the caller's
-// capacity-(leni+lenj+2) slots, i.e. exactly like seq_prepend fills a struct seq.
+// One WARP per pair.  The walk itself is a serial pointer chase (lane 0), so what matters is the
+// latency of each step: the warp stages a 64 x 32-byte tile of direction bytes around the current
+// cell in shared memory with one coalesced load (64 anti-diagonals x 64 diagonals), lane 0 walks
+// until it leaves the tile, and the tile is re-centred.  Results are written right to left into the
+// caller's capacity-(leni+lenj+2) slots, i.e. exactly like seq_prepend fills a struct seq.
+#define TB_ROWS 64
+#define TB_COLS 32
 __global__ void __launch_bounds__(128)
 k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, const BandJob *__restrict__ jobs, int njobs,
-            const uint8_t *__restrict__ done, const uint8_t *__restrict__ dir, const int64_t *__restrict__ out_off, uint8_t *median, uint8_t *medianwg,
-            uint8_t *resi, uint8_t *resj, int *out_len) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+            const uint8_t *__restrict__ done, const uint8_t *__restrict__ dir, const int64_t *__restrict__ out_off,
+            uint8_t *median, uint8_t *medianwg, uint8_t *resi, uint8_t *resj, int *out_len) {
+    __shared__ __align__(16) uint8_t s_tile[4][TB_ROWS * TB_COLS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = blockIdx.x * 4 + w;
     if (t >= njobs) return;
     const BandJob J = jobs[t];
     if (done && !done[J.pair]) return;  // this pair's band is not final yet
     const uint8_t *si = data + J.off_i, *sj = data + J.off_j;
-    const int k = J.k, swaped = J.swaped;
-    (void)swaped;
+    const int k = J.k;
     const int B = (J.lastj - J.lasti) + 2 * k + 1;
     const uint8_t *db = dir + J.dir_off;
     const int stride = J.stride;
     const int cap = J.lasti + J.lastj + 4;  // len_i + len_j + 2
-    const int64_t base = out_off[J.pair];
+    const int64_t base = out_off ? out_off[J.pair] : 0;
     uint8_t *pm = median ? median + base + cap : nullptr;
     uint8_t *pw = medianwg ? medianwg + base + cap : nullptr;
     uint8_t *pi = resi ? resi + base + cap : nullptr;
@@ -351,54 +357,83 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
 #define PUT_M(v) do { first_m = (v); PUT(pm, nm, v); } while (0)
 #define INDEL(sym) do { if (!((sym) & POY_GAP)) { PUT_M((sym) | POY_GAP); PUT(pw, nw, (sym) | POY_GAP); } else PUT(pw, nw, POY_GAP); } while (0)
     int i = J.lasti, j = J.lastj;
-    int ic = si[i], jc = sj[j];
     int mode = 4;  // 0 vertical, 1 horizontal, 2 diagonal, 3 align, 4 todo
-    while (i != 0 && j != 0) {
-        int d = j - i + k;
-        d = d < 0 ? 0 : (d >= B ? B - 1 : d);
-        const unsigned b = db[(size_t)(i + j) * stride + (d >> 1)];
-        if (mode == 4) mode = b & 3;
-        if (mode == 0) {
-            if (b & 16) mode = 4;
+    uint8_t *tile = s_tile[w];
+    for (;;) {
+        i = __shfl_sync(0xffffffffu, i, 0);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (i == 0 || j == 0) break;
+        // tile: anti-diagonals a_hi-63 .. a_hi, direction-byte columns c0 .. c0+31
+        const int a_hi = i + j;
+        int dcur = j - i + k;
+        dcur = dcur < 0 ? 0 : (dcur >= B ? B - 1 : dcur);
+        int c0 = ((dcur >> 1) - 12) & ~15;
+        if (c0 > stride - TB_COLS) c0 = stride - TB_COLS;
+        if (c0 < 0) c0 = 0;
+        for (int q = lane; q < TB_ROWS * 2; q += 32) {
+            const int r = q >> 1, half = q & 1;
+            const int a = a_hi - r;
+            if (a >= 0 && c0 + half * 16 + 16 <= stride)
+                *(uint4 *)(tile + r * TB_COLS + half * 16) = *(const uint4 *)(db + (size_t)a * stride + c0 + half * 16);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int ic = si[i], jc = sj[j];
+            while (i != 0 && j != 0) {
+                const int r = a_hi - (i + j);
+                int d = j - i + k;
+                d = d < 0 ? 0 : (d >= B ? B - 1 : d);
+                const int cb = (d >> 1) - c0;
+                if (r >= TB_ROWS || cb < 0 || cb >= TB_COLS) break;  // left the tile
+                const unsigned b = tile[r * TB_COLS + cb];
+                if (mode == 4) mode = b & 3;
+                if (mode == 0) {
+                    if (b & 16) mode = 4;
+                    INDEL(ic);
+                    PUT(pi, ni, ic); PUT(pj, nj, POY_GAP);
+                    --i; ic = si[i];
+                } else if (mode == 1) {
+                    if (b & 32) mode = 4;
+                    INDEL(jc);
+                    PUT(pi, ni, POY_GAP); PUT(pj, nj, jc);
+                    --j; jc = sj[j];
+                } else if (mode == 2) {
+                    if (b & 64) mode = 4;
+                    PUT(pi, ni, ic); PUT(pj, nj, jc); PUT(pw, nw, POY_GAP);
+                    --i; --j; ic = si[i]; jc = sj[j];
+                } else {
+                    mode = (b >> 2) & 3;
+                    const int prep = cm->median32[((ic & POY_NOGAP) << 5) + (jc & POY_NOGAP)];
+                    PUT_M(prep); PUT(pw, nw, prep);
+                    PUT(pi, ni, ic); PUT(pj, nj, jc);
+                    --i; --j; ic = si[i]; jc = sj[j];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        int ic = si[i], jc = sj[j];
+        while (i != 0) {
             INDEL(ic);
             PUT(pi, ni, ic); PUT(pj, nj, POY_GAP);
             --i; ic = si[i];
-        } else if (mode == 1) {
-            if (b & 32) mode = 4;
+        }
+        while (j != 0) {
             INDEL(jc);
             PUT(pi, ni, POY_GAP); PUT(pj, nj, jc);
             --j; jc = sj[j];
-        } else if (mode == 2) {
-            if (b & 64) mode = 4;
-            PUT(pi, ni, ic); PUT(pj, nj, jc); PUT(pw, nw, POY_GAP);
-            --i; --j; ic = si[i]; jc = sj[j];
-        } else {
-            mode = (b >> 2) & 3;
-            const int prep = cm->median32[((ic & POY_NOGAP) << 5) + (jc & POY_NOGAP)];
-            PUT_M(prep); PUT(pw, nw, prep);
-            PUT(pi, ni, ic); PUT(pj, nj, jc);
-            --i; --j; ic = si[i]; jc = sj[j];
+        }
+        PUT(pi, ni, POY_GAP); PUT(pj, nj, POY_GAP); PUT(pw, nw, POY_GAP);
+        if (first_m != POY_GAP) PUT_M(POY_GAP);
+        if (out_len) {
+            out_len[4 * J.pair + 0] = nm; out_len[4 * J.pair + 1] = nw;
+            out_len[4 * J.pair + 2] = ni; out_len[4 * J.pair + 3] = nj;
         }
     }
-    while (i != 0) {
-        INDEL(ic);
-        PUT(pi, ni, ic); PUT(pj, nj, POY_GAP);
-        --i; ic = si[i];
-    }
-    while (j != 0) {
-        INDEL(jc);
-        PUT(pi, ni, POY_GAP); PUT(pj, nj, jc);
-        --j; jc = sj[j];
-    }
-    PUT(pi, ni, POY_GAP); PUT(pj, nj, POY_GAP); PUT(pw, nw, POY_GAP);
-    if (first_m != POY_GAP) PUT_M(POY_GAP);
 #undef PUT
 #undef PUT_M
 #undef INDEL
-    if (out_len) {
-        out_len[4 * J.pair + 0] = nm; out_len[4 * J.pair + 1] = nw;
-        out_len[4 * J.pair + 2] = ni; out_len[4 * J.pair + 3] = nj;
-    }
 }
 
 cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
@@ -437,7 +472,7 @@ cudaError_t launch_traceback(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                              const uint8_t *d_done, const uint8_t *d_dir, const int64_t *d_out_off, uint8_t *d_median,
                              uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj, int *d_out_len) {
     if (njobs <= 0) return cudaSuccess;
-    k_traceback<<<(njobs + 127) / 128, 128, 0, ctx->stream>>>(cm->d, pool->d_data, d_jobs, njobs, d_done, d_dir, d_out_off, d_median,
+    k_traceback<<<(njobs + 3) / 4, 128, 0, ctx->stream>>>(cm->d, pool->d_data, d_jobs, njobs, d_done, d_dir, d_out_off, d_median,
                                                               d_medianwg, d_resi, d_resj, d_out_len);
     ctx->launches++;
     return cudaGetLastError();

@@ -44,6 +44,7 @@ struct poy_pool {
     int64_t *d_off;        // nseq+1 offsets
     int4 *d_rowp;          // per-base parameters, row role
     int4 *d_colp;          // per-base parameters, column role
+    unsigned *d_rowpk;     // row role, packed for the gap-free cost kernel: ge << 16 | table row offset
     int *d_h0;             // banded entry point: CB[0][j] = sum of in-loop hext (src/algn.c:2244)
     int *d_g0;             // cost-only entry point: EH[0][j] - GO = sum of prepend (src/algn.c:1847)
     uint8_t *d_gapfree;    // per sequence: 1 if no base at index >= 1 carries the gap bit
@@ -106,12 +107,14 @@ cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, co
 cudaError_t launch_cost_affine_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs_free,
                                      const CostJob *d_jobs_gen, const int *d_counts, int *d_counters, int4 *d_bound,
                                      size_t bound_stride, int blocks, int *d_cost);
+cudaError_t launch_cost_gf(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs,
+                           const int *d_count, int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost);
 cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                              int dclass, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
                          bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 int band2_class_for(long long B);
-int band2_stride_for(int cls);
+int band2_stride_for(int cls, long long B);
 cudaError_t launch_band_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                                 PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_work, size_t work_stride,
                                 int blocks);

@@ -261,9 +261,8 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
 cudaError_t launch_cost_affine_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs_free,
                                      const CostJob *d_jobs_gen, const int *d_counts, int *d_counters, int4 *d_bound,
                                      size_t bound_stride, int blocks, int *d_cost) {
-    k_cost_affine<16, true><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_g0, d_jobs_free,
-                                                              d_counts, d_counters, d_bound, bound_stride, d_cost);
-    ctx->launches++;
+    cudaError_t e = launch_cost_gf(ctx, cm, pool, d_jobs_free, d_counts, d_counters, d_bound, bound_stride, blocks, d_cost);
+    if (e != cudaSuccess) return e;
     k_cost_affine<8, false><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_g0, d_jobs_gen,
                                                               d_counts + 1, d_counters + 1, d_bound, bound_stride, d_cost);
     ctx->launches++;

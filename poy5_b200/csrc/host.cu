@@ -54,7 +54,15 @@ extern "C" poy_status poy_ctx_create(int device, void *stream, poy_ctx **out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return POY_ERR_CUDA; }
         ctx->owns_stream = true;
     }
-    ctx->arena_limit = 8ull << 30;
+    {   // direction arena: up to 40% of the free HBM, at most 64 GiB
+        size_t fr = 0, tot = 0;
+        ctx->arena_limit = 8ull << 30;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+            uint64_t lim = (uint64_t)(fr * 0.4);
+            if (lim > (64ull << 30)) lim = 64ull << 30;
+            if (lim > ctx->arena_limit) ctx->arena_limit = lim;
+        }
+    }
     *out = ctx;
     return POY_OK;
 }
@@ -312,6 +320,7 @@ static poy_status pool_alloc(poy_ctx *ctx, poy_pool *p) {
     const size_t nb = (size_t)std::max<int64_t>(p->nbytes, 1);
     CK(cudaMalloc(&p->d_rowp, nb * sizeof(int4)));
     CK(cudaMalloc(&p->d_colp, nb * sizeof(int4)));
+    CK(cudaMalloc(&p->d_rowpk, nb * sizeof(unsigned)));
     CK(cudaMalloc(&p->d_h0, nb * sizeof(int)));
     CK(cudaMalloc(&p->d_g0, nb * sizeof(int)));
     CK(cudaMalloc(&p->d_gapfree, (size_t)std::max(p->nseq, 1)));
@@ -322,7 +331,7 @@ extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
     if (!p) return;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     if (p->owns_data) { cudaFree(p->d_data); cudaFree(p->d_off); }
-    cudaFree(p->d_rowp); cudaFree(p->d_colp); cudaFree(p->d_h0); cudaFree(p->d_g0); cudaFree(p->d_gapfree);
+    cudaFree(p->d_rowp); cudaFree(p->d_colp); cudaFree(p->d_rowpk); cudaFree(p->d_h0); cudaFree(p->d_g0); cudaFree(p->d_gapfree);
     free(p->h_off);
     free(p->h_gapfree);
     delete p;
@@ -544,7 +553,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             const int64_t B = (int64_t)delta + 2 * (int64_t)h.k + 1;
             // the packed 16x2 gap counters of k_band2 are exact while len_i + len_j < 65535
             h.dclass = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2 >= 65535) ? 0 : band2_class_for(B);
-            h.stride = h.dclass ? band2_stride_for(h.dclass) : (int)(((B + 1) / 2 + 15) & ~15ll);
+            h.stride = h.dclass ? band2_stride_for(h.dclass, B) : (int)(((B + 1) / 2 + 31) & ~31ll);
             h.dir_bytes = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2) * h.stride;
             h.iterations++;
             h.cells += band_cells(h.lasti, h.lastj, h.k);

@@ -16,7 +16,8 @@ __global__ void k_build_cost_jobs(const int64_t *__restrict__ off, const uint8_t
     if (la <= lb) { j.off_i = oa; j.lasti = la - 1; j.off_j = ob; j.lastj = lb - 1; }
     else { j.off_i = ob; j.lasti = lb - 1; j.off_j = oa; j.lastj = la - 1; }
     j.out = p;
-    j.gapfree = gapfree[sa] && gapfree[sb];
+    // tiny pairs take the exact flat-layout emulation inside the general kernel (cost_affine.cu, TINY_L)
+    j.gapfree = gapfree[sa] && gapfree[sb] && (j.lastj + 1 > 8);
     if (j.gapfree) jfree[atomicAdd(counts, 1)] = j;
     else jgen[atomicAdd(counts + 1, 1)] = j;
 }

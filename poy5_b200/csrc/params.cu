@@ -18,7 +18,7 @@ __device__ __forceinline__ int gap_opening_at(int idx, int prev, int cur, int go
 
 __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data,
                                                 const int64_t *__restrict__ off, int nseq, int4 *__restrict__ rowp,
-                                                int4 *__restrict__ colp, int *__restrict__ h0, int *__restrict__ g0,
+                                                unsigned *__restrict__ rowpk, int4 *__restrict__ colp, int *__restrict__ h0, int *__restrict__ g0,
                                                 uint8_t *__restrict__ gapfree) {
     __shared__ int s_prepend[32], s_gapext[32];
     if (threadIdx.x < 32) {
@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
                 }
                 rowp[base + x] = r;
                 colp[base + x] = c;
+                // gap-free cost kernel: ge_i in the high half, byte offset of the cost row (17 columns x 32
+                // bank replicas x 4 B) in the low half
+                rowpk[base + x] = ((unsigned)min(max(s_gapext[code], 0), 0xFFFF) << 16) | (unsigned)((code & POY_NOGAP) * 17 * 128);
             }
             // inclusive warp scans of hl and ge_c
             int sh = hl, sg = ge_c;
@@ -83,7 +86,7 @@ cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool) {
     if (pool->nseq == 0) return cudaSuccess;
     int blocks = (pool->nseq + 3) / 4;
     if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-    k_params<<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_data, pool->d_off, pool->nseq, pool->d_rowp, pool->d_colp,
+    k_params<<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_data, pool->d_off, pool->nseq, pool->d_rowp, pool->d_rowpk, pool->d_colp,
                                                pool->d_h0, pool->d_g0, pool->d_gapfree);
     ctx->launches++;
     return cudaGetLastError();
