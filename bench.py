@@ -337,11 +337,11 @@ def main():
                    ms_per_step=1e3 * te, alignments_per_s=world * total_aln / te)
 
     if rank == 0:
-        # dominant kernel: the gap-free cost-only wavefront (k_cost_affine<16,true>) on the longest length
+        # dominant kernel: the gap-free cost-only wavefront (k_cost_gf<16>) on the longest length
         Ltop = max(kernel_ms) if kernel_ms else lengths[-1]
         k_ms, k_cells = kernel_ms.get(Ltop, (ms, total_cells))
         achieved = k_cells * OPS_PER_CELL["gapfree"] / (k_ms * 1e-3) / 1e12
-        roofline = dict(bound="int32", kernel="k_cost_affine<16,true>", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
+        roofline = dict(bound="int32", kernel="k_cost_gf<16>", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
                         frac=achieved / (peak_ops / 1e12), traffic=None,
                         note="INT32 issue roofline: algorithmic scalar add/min per cell (%d, gap-free cost-only cell) x cells / "
                              "launch time, vs the IADD3-class issue rate measured live by poy_microbench_int "

@@ -241,6 +241,14 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         // one loop iteration = anti-diagonals a (even diagonals) and a+1 (odd diagonals)
         auto iteration = [&](auto edge_c) {
             constexpr bool EDGE = decltype(edge_c)::value;
+            // next window entries: issued now, consumed after both sub-steps (hides the L1/L2 latency)
+            int4 nrow = make_int4(0, 0, 0, 0), ncol = make_int4(0, 0, 0, 0);
+            if (warp_in_band) {
+                int ri = i0 + 1, cj = j0 + 1 + H;
+                ri = ri < 0 ? 0 : (ri > lasti ? lasti : ri);
+                cj = cj < 0 ? 0 : (cj > lastj ? lastj : cj);
+                nrow = rp[ri]; ncol = cp[cj];
+            }
             // ---- even diagonals ----
             {
                 int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
@@ -314,10 +322,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             sfor<H - 1>([&](auto hc) { constexpr int h = H - 1 - decltype(hc)::value; R[h] = R[h - 1]; });
             sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = C[h + 1]; });
             ++i0; ++j0;
-            if (warp_in_band) {
-                R[0] = load_row(i0);
-                C[H] = load_col(j0 + H);
-            }
+            R[0] = row_entry<GF>(nrow);
+            C[H] = col_entry<GF>(ncol, lane);
         };
 
         for (; a <= a_end && a < a_main; a += 2) iteration(std::true_type{});

@@ -92,7 +92,9 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
               int4 *bound, size_t bound_stride, int *__restrict__ cost_out) {
     constexpr int W = 32 * C;
     __shared__ int s_cost16[256];
+    __shared__ int s_rep[256 * 32];  // cost16 replicated once per bank: entry e of lane l at [e*32 + l]
     for (int x = threadIdx.x; x < 256; x += blockDim.x) s_cost16[x] = cm->cost16[x];
+    for (int x = threadIdx.x; x < 256 * 32; x += blockDim.x) s_rep[x] = cm->cost16[x >> 5];
     __syncthreads();
     const int GO = cm->gap_open;
     const int njobs = *njobs_ptr;
@@ -198,7 +200,7 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
                             cbL = cb; ehL = eh;
                         }
                     } else {
-                        const int *rowbase = s_cost16 + (r.w & 15) * 16;
+                        const int *rowbase = s_rep + (r.w & 15) * 512 + lane;
                         const int vext = r.x, opnV = r.y, go_i = r.z;
                         const int mask_i = (r.w & PF_HASGAP) ? -1 : 0;
                         int xCB = dCB, xEV = dEV, xEH = dEH, xEB = dEB;
@@ -213,7 +215,7 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
                             const int dg = both ? 0 : POY_INF;
                             const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
                             const int eb = __viaddmin_s32(xEB, dg, xCB + od);
-                            const int diag = rowbase[fl & 15];
+                            const int diag = rowbase[(fl & 15) << 5];
                             const int gv = go_j & mask_i;
                             const int gh = (fl & PF_HASGAP) ? go_i : 0;
                             const int xgo = go_j < go_i ? go_i : go_j;
