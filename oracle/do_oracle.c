@@ -516,3 +516,254 @@ double do_batch_affine(const do_cm *cm, int mode, int n, const u8 *seqs, const l
     clock_gettime(CLOCK_MONOTONIC, &t1);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ======================================================================== */
+/* 3. linear-gap alignment: algn_CAML_simple_2 -> algn_nw -> algn_fill_plane_2 */
+/*    (src/algn.c:3134, 2954-2975, 1134-1177), full plane algn_fill_plane    */
+/*    (:927-973, 675-690, 458-533, 654-667), Ukkonen band algn_newkk_*       */
+/*    (:1008-1130, 747-923, 543-647, 693-730, 978-1005), backtrace_2d        */
+/*    (:3277-3327, 79-124)                                                    */
+/* ======================================================================== */
+enum { L_ALIGN = 1, L_INSERT = 2, L_DELETE = 4 }; /* src/matrices.h:22-27 */
+
+typedef struct { int *mm; u16 *dm; size_t mcap, dcap; int lenX, lenY; } do_lin_scratch;
+do_lin_scratch *do_lin_scratch_new(void) { return (do_lin_scratch *)calloc(1, sizeof(do_lin_scratch)); }
+void do_lin_scratch_free(do_lin_scratch *s) { if (s) { free(s->mm); free(s->dm); free(s); } }
+static void lin_fit(do_lin_scratch *s, int lenX, int lenY) {
+    size_t n = (size_t)(lenX + 1) * (lenY + 1);
+    if (s->mcap < n) { s->mm = (int *)realloc(s->mm, n * sizeof(int)); memset(s->mm + s->mcap, 0, (n - s->mcap) * sizeof(int)); s->mcap = n; }
+    if (s->dcap < n) { s->dm = (u16 *)realloc(s->dm, n * sizeof(u16)); memset(s->dm + s->dcap, 0, (n - s->dcap) * sizeof(u16)); s->dcap = n; }
+    s->lenX = lenX; s->lenY = lenY;
+}
+
+/* interior cell (algn_fill_row :458-533): every minimal candidate is recorded */
+static void lin_cell(int *mm, const int *pm, u16 *dm, int j, int c_del, int gapc, int algc) {
+    int t1 = pm[j] + c_del, t2 = mm[j - 1] + gapc, t3 = pm[j - 1] + algc;
+    int m = t1 < t2 ? t1 : t2;
+    if (t3 < m) m = t3;
+    mm[j] = m;
+    dm[j] = (u16)((t1 == m ? L_DELETE : 0) | (t2 == m ? L_INSERT : 0) | (t3 == m ? L_ALIGN : 0));
+}
+/* right-border cell: no DELETE candidate (algn_fill_ukk_right_cell :543-581) */
+static void lin_right(int *mm, const int *pm, u16 *dm, int j, int gapc, int algc) {
+    int t2 = mm[j - 1] + gapc, t3 = pm[j - 1] + algc;
+    int m = t2 < t3 ? t2 : t3;
+    mm[j] = m;
+    dm[j] = (u16)((t2 == m ? L_INSERT : 0) | (t3 == m ? L_ALIGN : 0));
+}
+/* left-border cell: no INSERT candidate (algn_fill_ukk_left_cell :614-647) */
+static void lin_left(int *mm, const int *pm, u16 *dm, int j, int c_del, int algc) {
+    int t1 = pm[j] + c_del, t3 = pm[j - 1] + algc;
+    int m = t1 < t3 ? t1 : t3;
+    mm[j] = m;
+    dm[j] = (u16)((t1 == m ? L_DELETE : 0) | (t3 == m ? L_ALIGN : 0));
+}
+/* last column additionally offers tail_cost (algn_fill_last_column :654-667) */
+static void lin_last(int *mm, const int *pm, u16 *dm, int l, int tlc) {
+    if (l > 0) {
+        int cst = tlc + pm[l];
+        if (cst < mm[l]) { mm[l] = cst; dm[l] = L_DELETE; }
+        else if (cst == mm[l]) dm[l] |= L_DELETE;
+    }
+}
+
+static int lin_full_plane(const do_cm *c, do_lin_scratch *sc, const u8 *s1, int lenX, const u8 *s2, int lenY) {
+    int *mm = sc->mm, *nm = sc->mm, *tmp, i, j;
+    u16 *dm = sc->dm;
+    mm[0] = 0; dm[0] = L_ALIGN;
+    for (j = 1; j < lenY; j++) { mm[j] = mm[j - 1] + c->prepend[s2[j]]; dm[j] = L_INSERT; }
+    mm += lenY;
+    for (i = 1, dm += lenY; i < lenX; i++, dm += lenY) {
+        int a = s1[i], c_del = c->cost[(a << 5) + GAPBIT], tlc = c->tail[a];
+        mm[0] = c_del + nm[0]; dm[0] = L_DELETE;                 /* algn_fill_full_row :679-680 */
+        for (j = 1; j <= lenY - 1; j++) lin_cell(mm, nm, dm, j, c_del, c->cost[(GAPBIT << 5) + s2[j]], c->cost[(a << 5) + s2[j]]);
+        lin_last(mm, nm, dm, lenY - 1, tlc);
+        tmp = mm; mm = nm; nm = tmp;
+    }
+    return nm[lenY - 1];
+}
+
+/* gap count of the ALIGN > INSERT > DELETE traceback (backtrace_2d_gaps :978-1005) */
+static int lin_trace_gaps(const do_lin_scratch *sc, int lenX, int lenY) {
+    int nd = 0, ni = 0;
+    long pos = (long)lenY * (lenX - 1) + lenY - 1;
+    while (pos >= 0) {
+        int d = sc->dm[pos];
+        if (d & L_ALIGN) pos -= lenY + 1;
+        else if (d & L_INSERT) { ni++; pos -= 1; }
+        else { nd++; pos -= lenY; }
+    }
+    return nd > ni ? nd : ni;
+}
+
+static int lin_band_fill(const do_cm *c, do_lin_scratch *sc, const u8 *s1, int lenX, const u8 *s2, int lenY, int p,
+                         int *cost, long long *cells) {
+    int k = p >= lenX ? lenX - 1 : p, delta = lenY - lenX, i, j;
+    int first = delta + 1 + p;
+    int *a = sc->mm, *b = sc->mm + lenY;
+    u16 *dm = sc->dm;
+    if (first > lenY) first = lenY;
+    a[0] = 0; dm[0] = L_ALIGN;                                   /* algn_fill_first_row :693-717 */
+    for (j = 1; j < first; j++) { a[j] = a[j - 1] + c->prepend[s2[j]]; dm[j] = L_INSERT; }
+    for (i = 1; i < lenX; i++) {
+        int sym = s1[i], c_del = c->cost[(sym << 5) + GAPBIT], tlc = c->tail[sym];
+        int left = (i - k) > 0, startj = left ? i - k : 0;
+        int right = (i + delta + k) <= (lenY - 1), endj = right ? i + delta + k : lenY - 1;
+        int len = endj - startj + 1;
+        u16 *d = dm + (size_t)i * lenY;
+#define GAPC(j) (c->cost[(GAPBIT << 5) + s2[j]])
+#define ALGC(j) ((j) == 0 ? c->tail[sym] : c->cost[(sym << 5) + s2[j]])
+        if (left && right) {                                      /* algn_fill_extending_left_right :786-831 */
+            if (len == 1) { b[startj] = a[startj - 1] + ALGC(startj); d[startj] = L_ALIGN; }
+            else {
+                lin_left(b, a, d, startj, c_del, ALGC(startj));
+                for (j = startj + 1; j <= startj + len - 2; j++) lin_cell(b, a, d, j, c_del, GAPC(j), ALGC(j));
+                lin_right(b, a, d, startj + len - 1, GAPC(startj + len - 1), ALGC(startj + len - 1));
+            }
+        } else if (right) {                                       /* algn_fill_extending_right :746-784 */
+            b[0] = a[0] + ALGC(0); d[0] = L_DELETE;               /* first cell uses alg_row[0] = tail (A9) */
+            for (j = 1; j <= len - 2; j++) lin_cell(b, a, d, j, c_del, GAPC(j), ALGC(j));
+            lin_right(b, a, d, len - 1, GAPC(len - 1), ALGC(len - 1));
+        } else if (left) {                                        /* algn_fill_extending_left :833-886 */
+            lin_left(b, a, d, startj, c_del, ALGC(startj));
+            for (j = startj + 1; j <= startj + len - 1; j++) lin_cell(b, a, d, j, c_del, GAPC(j), ALGC(j));
+            lin_last(b, a, d, startj + len - 1, tlc);
+        } else {                                                  /* algn_fill_no_extending :888-923 */
+            b[0] = a[0] + ALGC(0); d[0] = L_DELETE;
+            for (j = 1; j <= lenY - 1; j++) lin_cell(b, a, d, j, c_del, GAPC(j), ALGC(j));
+            lin_last(b, a, d, lenY - 1, tlc);
+        }
+#undef GAPC
+#undef ALGC
+        *cells += len;
+        a = b;
+        if (i < lenX - 1) b = a + lenY;
+    }
+    *cost = a[lenY - 1];
+    return lin_trace_gaps(sc, lenX, lenY);
+}
+
+/* s1 must be the shorter sequence (the OCaml caller guarantees it, src/sequence.ml:917-925).
+ * Leaves the direction matrix in `sc` for do_backtrace_linear, like the reference leaves it in
+ * Matrix.default between c_cost_2 and extract_edited_2.  mode_out: 0 full plane, 1 Ukkonen. */
+int do_cost_linear(const do_cm *c, do_lin_scratch *sc, const u8 *s1, int lenX, const u8 *s2, int lenY, int deltawh,
+                   do_align_stats *st) {
+    int height, T, cost = 0;
+    do_align_stats local;
+    if (!st) st = &local;
+    st->iterations = 0; st->cells = 0; st->final_T = 0; st->final_k = -1;
+    if (lenX > lenY) return (-2147483647 - 1);
+    lin_fit(sc, lenX, lenY);
+    height = (lenX - lenY) + 50 + deltawh;                         /* algn_nw_limit :2963, algn_fill_plane_2 :1141-1144 */
+    if (height > lenX) height = lenX;
+    T = (lenY - lenX + 1) * c->min_non0;
+    if ((float)lenX >= 1.5f * (float)lenY) return lin_full_plane(c, sc, s1, lenX, s2, lenY);
+    if (!((2 * height) < lenX) && 8 >= (lenX - height)) return lin_full_plane(c, sc, s1, lenX, s2, lenY);
+    for (;;) {                                                      /* algn_newkk_increaseT :1117-1130 */
+        int p = (T - (lenY - lenX)) / 2, newp, gap_num;
+        gap_num = lin_band_fill(c, sc, s1, lenX, s2, lenY, p, &cost, &st->cells);
+        st->iterations++; st->final_T = T; st->final_k = p >= lenX ? lenX - 1 : p;
+        newp = (2 * T - (lenY - lenX)) / 2;
+        if ((gap_num + 1) < p || newp - lenY + 1 >= 0) return cost;
+        T *= 2;
+    }
+}
+
+/* backtrace_2d (:3277-3327): ALIGN first, then DELETE before INSERT, or INSERT before DELETE when
+ * the caller swapped the operands.  Outputs need capacity lenX+lenY; lens = {r1, r2}. */
+void do_backtrace_linear(const do_lin_scratch *sc, const u8 *s1, const u8 *s2, int swaped, u8 *r1, u8 *r2, int *lens) {
+    int lenX = sc->lenX, lenY = sc->lenY, cap = lenX + lenY, a1 = lenX, a2 = lenY;
+    long pos = (long)lenY * (lenX - 1) + lenY - 1;
+    rseq o1 = { r1, cap, cap }, o2 = { r2, cap, cap };
+    while (pos >= 0) {
+        int d = sc->dm[pos];
+        if (d & L_ALIGN) { rprep(&o1, s1[--a1]); rprep(&o2, s2[--a2]); pos -= lenY + 1; }
+        else {
+            int ins = swaped ? ((d & L_INSERT) != 0) : !(d & L_DELETE);
+            if (ins) { rprep(&o1, GAPBIT); rprep(&o2, s2[--a2]); pos -= 1; }
+            else { rprep(&o1, s1[--a1]); rprep(&o2, GAPBIT); pos -= lenY; }
+        }
+    }
+    lens[0] = rfinish(&o1); lens[1] = rfinish(&o2);
+}
+
+/* ======================================================================== */
+/* 4. O(L) column-wise helpers                                               */
+/* ======================================================================== */
+/* seq_get_median_2d_with_gaps / _no_gaps (src/seq.c:241-272) */
+int do_median_2(const do_cm *c, const u8 *a, const u8 *b, int len, int with_gaps, u8 *out) {
+    int i, n = 0;
+    u8 *tmp = (u8 *)malloc((size_t)len + 2);
+    if (!with_gaps) tmp[n++] = GAPBIT;
+    for (i = 0; i < len; i++) {
+        int m = c->median[(a[i] << 5) + b[i]];
+        if (with_gaps || m != GAPBIT) tmp[n++] = (u8)m;
+    }
+    memcpy(out, tmp, (size_t)n);
+    free(tmp);
+    return n;
+}
+/* algn_union (src/algn.c:3657-3666) */
+void do_union(const u8 *a, const u8 *b, int len, u8 *out) { int i; for (i = 0; i < len; i++) out[i] = a[i] | b[i]; }
+
+/* algn_calculate_from_2_aligned (src/algn.c:3003-3090), bitset alphabet branch: cost of an aligned
+ * pair under `table` (cost -> algn_verify_2, worst -> algn_worst_2) with the gap-opening automaton */
+static int from_2_aligned(const do_cm *c, const int *table, const u8 *s1, const u8 *s2, int len) {
+    int i, res = 0, go = c->gap_open, gap_row = 0;
+    i = ((s1[0] & GAPBIT) && (s2[0] & GAPBIT)) ? 1 : 0;
+    for (; i < len; i++) {
+        int a = s1[i], b = s2[i];
+        if (gap_row == 0) {
+            if ((a & GAPBIT) && !(b & GAPBIT)) { res += go; gap_row = 1; }
+            else if ((b & GAPBIT) && !(a & GAPBIT)) { res += go; gap_row = 2; }
+        } else if (gap_row == 1) {
+            if (!(a & GAPBIT)) {
+                if ((b & GAPBIT) && !(a & GAPBIT)) { res += go; gap_row = 2; }
+                else gap_row = 0;
+            }
+        } else {
+            if (!(b & GAPBIT)) {
+                if (a & GAPBIT) { res += go; gap_row = 1; }
+                else gap_row = 0;
+            }
+        }
+        res += table[(a << 5) + b];
+    }
+    return res;
+}
+int do_worst_2(const do_cm *c, const u8 *a, const u8 *b, int len) { return from_2_aligned(c, c->worst, a, b, len); }
+int do_verify_2(const do_cm *c, const u8 *a, const u8 *b, int len) { return from_2_aligned(c, c->cost, a, b, len); }
+
+/* algn_ancestor_2 (src/algn.c:3603-3626) with algn_correct_blocks_affine (:3561-3601) and
+ * algn_remove_gaps (:3539-3559); combinations = 1 */
+int do_ancestor_2(const do_cm *c, const u8 *s1, const u8 *s2, int len, u8 *out) {
+    int i, n = 0, gap = GAPBIT;
+    u8 *sm = (u8 *)malloc((size_t)len + 2);
+    for (i = 0; i < len; i++) {
+        int m = c->median[(s1[i] << 5) + s2[i]];
+        if (m == 0) { free(sm); return (-2147483647 - 1); }       /* failwith "median should not be 0" */
+        sm[i] = (u8)m;
+    }
+    if (c->cost_model_type != 1) {
+        /* non-affine: pure-gap medians are dropped while prepending, then the leading gap is restored */
+        out[n++] = (u8)gap;
+        for (i = 0; i < len; i++) if (sm[i] != gap) out[n++] = sm[i];
+    } else {
+        int extending = 0, inside = 0, prev_block = 0;
+        for (i = 0; i < len; i++) {
+            int ab = s1[i], bb = s2[i], sb = sm[i];
+            if (!inside && (!(ab & gap) || !(bb & gap))) inside = 0;
+            else if (inside && (!(ab & gap) || !(bb & gap))) inside = 0;
+            else if (((ab & gap) || (bb & gap)) && ((ab != gap) || (bb != gap))) inside = 1;
+            else inside = 0;
+            if (((gap & ab) || (gap & bb)) && !(sb & gap) && !extending) { prev_block = inside; extending = 1; }
+            else if ((gap & ab) && (gap & bb) && (sb & gap) && (sb != gap) && extending && inside && !prev_block) { sb = (~gap) & sb; prev_block = 0; }
+            else if ((gap & ab) && (gap & bb) && extending == 1) { prev_block = inside; extending = 0; }
+            sm[i] = (u8)sb;
+        }
+        out[n++] = (u8)gap;                                         /* algn_remove_gaps restores the leading gap */
+        for (i = 0; i < len; i++) if (sm[i] != gap) out[n++] = sm[i];
+    }
+    free(sm);
+    return n;
+}

@@ -40,6 +40,15 @@ class Port:
         L.do_batch_affine.restype = C.c_double
         L.do_batch_affine.argtypes = [C.c_void_p, C.c_int, C.c_int, _u8p, C.POINTER(C.c_longlong), _i32p,
                                       C.POINTER(C.c_longlong), _i32p, _u8p, _i32p, C.c_int]
+        L.do_lin_scratch_new.restype = C.c_void_p
+        L.do_cost_linear.argtypes = [C.c_void_p, C.c_void_p, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.POINTER(AlignStats)]
+        L.do_backtrace_linear.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, _u8p, _u8p, _i32p]
+        L.do_median_2.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, _u8p]
+        L.do_union.argtypes = [_u8p, _u8p, C.c_int, _u8p]
+        L.do_worst_2.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int]
+        L.do_verify_2.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int]
+        L.do_ancestor_2.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, _u8p]
+        self.lin = L.do_lin_scratch_new()
         self.scratch = L.do_scratch_new()
 
     def cm(self, m):
@@ -82,3 +91,52 @@ class Port:
                                      off_j.ctypes.data_as(i64p), len_j.ctypes.data_as(_i32p),
                                      None if sw is None else _p8(sw), cost.ctypes.data_as(_i32p), int(nthreads))
         return t, cost
+
+    # -- linear gap ---------------------------------------------------------------------------
+    def cost_linear(self, cm, s1, s2, deltawh, with_stats=False):
+        """algn_CAML_simple_2 semantics: s1 must be the shorter sequence."""
+        s1 = np.ascontiguousarray(s1, np.uint8); s2 = np.ascontiguousarray(s2, np.uint8)
+        st = AlignStats()
+        r = self.lib.do_cost_linear(cm, self.lin, _p8(s1), len(s1), _p8(s2), len(s2), int(deltawh), C.byref(st))
+        if r == INT_MIN:
+            raise RuntimeError("pass the shorter one as first")
+        return (r, st) if with_stats else r
+
+    def align_linear(self, cm, s1, s2, deltawh, swaped=0):
+        """algn_CAML_align_2d = simple_2 + backtrace_2d.  -> (cost, r1, r2)"""
+        s1 = np.ascontiguousarray(s1, np.uint8); s2 = np.ascontiguousarray(s2, np.uint8)
+        cost = self.cost_linear(cm, s1, s2, deltawh)
+        cap = len(s1) + len(s2)
+        o1 = np.zeros(cap, np.uint8); o2 = np.zeros(cap, np.uint8)
+        lens = (C.c_int * 2)()
+        self.lib.do_backtrace_linear(self.lin, _p8(s1), _p8(s2), int(swaped), _p8(o1), _p8(o2), lens)
+        return cost, o1[:lens[0]].copy(), o2[:lens[1]].copy()
+
+    # -- O(L) helpers -------------------------------------------------------------------------------
+    def median_2(self, cm, a, b, with_gaps):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        out = np.zeros(len(a) + 2, np.uint8)
+        n = self.lib.do_median_2(cm, _p8(a), _p8(b), len(a), int(with_gaps), _p8(out))
+        return out[:n].copy()
+
+    def union(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        out = np.zeros(len(a), np.uint8)
+        self.lib.do_union(_p8(a), _p8(b), len(a), _p8(out))
+        return out
+
+    def worst_2(self, cm, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return self.lib.do_worst_2(cm, _p8(a), _p8(b), len(a))
+
+    def verify_2(self, cm, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return self.lib.do_verify_2(cm, _p8(a), _p8(b), len(a))
+
+    def ancestor_2(self, cm, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        out = np.zeros(len(a) + 2, np.uint8)
+        n = self.lib.do_ancestor_2(cm, _p8(a), _p8(b), len(a), _p8(out))
+        if n == INT_MIN:
+            raise RuntimeError("median should not be 0")
+        return out[:n].copy()
