@@ -139,6 +139,22 @@ POY_API poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm, co
                                       uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
                                       int32_t *d_out_len, int32_t *d_stats);
 
+/* ---- batch twins of algn_CAML_simple_2 (src/algn.c:3134) and algn_CAML_align_2d (:3500) -----
+ * Linear-gap DO alignment (cost_model_type 0 or 2): algn_nw -> algn_fill_plane_2 chooses the full
+ * plane or the Ukkonen band from the lengths and deltawh[p] exactly like the reference
+ * (src/algn.c:1134-1177); deltawh is what the OCaml caller computes in Sequence.Align.cost_2
+ * (src/sequence.ml:868-925).  s1[p] must be the shorter sequence (POY_ERR_ORDER otherwise).
+ * align: r1 / r2 receive the two aligned rows of backtrace_2d (src/algn.c:3277-3327), pair p
+ * right-justified in the slot [out_off[p], out_off[p] + len1 + len2) (create_edited_2 allocates
+ * len1+len2, src/sequence.ml:1019-1033); out_len[2*p + {0,1}] = their lengths; swaped[p] selects
+ * the insertion/deletion preference.  stats as for the affine entry point. */
+POY_API poy_status poy_batch_cost_linear(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                         const int32_t *s1, const int32_t *s2, const int32_t *deltawh, int32_t *cost);
+POY_API poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                          const int32_t *s1, const int32_t *s2, const int32_t *deltawh,
+                                          const uint8_t *swaped, const int64_t *out_off, int32_t *cost, uint8_t *r1,
+                                          uint8_t *r2, int32_t *out_len, int32_t *stats);
+
 /* ---- INT32 / DPX issue-rate micro-benchmark (roofline denominator) ---------
  * Runs independent chains of one instruction class at full occupancy and
  * returns thread-level operations per second.  kind: 0 IADD3, 1 IMNMX (min),

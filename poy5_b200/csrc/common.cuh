@@ -115,6 +115,13 @@ cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, c
                          bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 int band2_class_for(long long B);
 int band2_stride_for(int cls, long long B);
+cudaError_t launch_band_lin(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
+                            int *d_counter, PairState *d_state, uint8_t *d_dir);
+cudaError_t launch_band_lin_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                                    PairState *d_state, uint8_t *d_dir, int *d_work, size_t work_stride, int blocks);
+cudaError_t launch_lin_finish(poy_ctx *ctx, const poy_pool *pool, const BandJob *d_jobs, int njobs, PairState *d_state, uint8_t *d_done);
+cudaError_t launch_traceback_lin(poy_ctx *ctx, const poy_pool *pool, const BandJob *d_jobs, int njobs, const uint8_t *d_done,
+                                 const uint8_t *d_dir, const int64_t *d_out_off, uint8_t *d_r1, uint8_t *d_r2, int *d_out_len);
 cudaError_t launch_band_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                                 PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_work, size_t work_stride,
                                 int blocks);

@@ -459,7 +459,7 @@ extern "C" poy_status poy_batch_cost_affine(poy_ctx *ctx, const poy_cm *cm, cons
 // ---- batch banded affine with traceback ------------------------------------------------------------------
 namespace {
 struct HostPair {
-    int lasti, lastj, T, k, dclass, stride, gapfree;
+    int lasti, lastj, T, k, dclass, stride, gapfree, fullplane;
     int64_t off_i, off_j, eb_off, dir_bytes;
     int iterations;
     int64_t cells;
@@ -485,11 +485,16 @@ extern "C" poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm,
                                                  int32_t *d_cost, uint8_t *d_median, uint8_t *d_medianwg,
                                                  uint8_t *d_resi, uint8_t *d_resj, int32_t *d_out_len, int32_t *d_stats);
 
+// `h_deltawh` != NULL selects the linear-gap path (algn_CAML_simple_2 / align_2d): d_resi / d_resj then receive the
+// two aligned rows (capacity len1+len2 each, src/sequence.ml:1019-1033), d_median / d_medianwg are unused and
+// d_out_len has 2 entries per pair.
 static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n, const int32_t *h_si,
                              const int32_t *h_sj, const uint8_t *h_swaped, const int64_t *d_out_off, int32_t *d_cost,
                              uint8_t *d_median, uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
-                             int32_t *d_out_len, int32_t *h_stats) {
-    if (cm->h.cost_model_type != 1) return fail(ctx, POY_ERR_MODEL, "align_affine needs an affine cost model");
+                             int32_t *d_out_len, int32_t *h_stats, const int32_t *h_deltawh = nullptr) {
+    const bool linear = h_deltawh != nullptr;
+    if (!linear && cm->h.cost_model_type != 1) return fail(ctx, POY_ERR_MODEL, "align_affine needs an affine cost model");
+    if (linear && cm->h.cost_model_type == 1) return fail(ctx, POY_ERR_MODEL, "the linear-gap entry points need a non-affine cost model");
     if (n == 0) return POY_OK;
     const bool want_trace = d_median || d_medianwg || d_resi || d_resj || d_out_len;
     if (want_trace && !d_out_off) return fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
@@ -506,13 +511,20 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         h.T = (h.lastj - h.lasti + 1) * cm->min_non0;  // algn_fill_plane_3_aff, src/algn.c:2348-2349
         h.eb_off = eb_total;
         eb_total += h.lastj + 1;
-        h.iterations = 0; h.cells = 0; h.done = false;
+        h.iterations = 0; h.cells = 0; h.done = false; h.fullplane = 0;
+        if (linear) {   // algn_nw_limit / algn_fill_plane_2: full plane or Ukkonen band (src/algn.c:2963, 1141-1176)
+            const int lenX = h.lasti + 1, lenY = h.lastj + 1;
+            int height = (lenX - lenY) + 50 + h_deltawh[p];
+            if (height > lenX) height = lenX;
+            if ((float)lenX >= 1.5f * (float)lenY) h.fullplane = 1;
+            else if (!((2 * height) < lenX) && 8 >= (lenX - height)) h.fullplane = 1;
+        }
         maxsum = std::max<int64_t>(maxsum, (int64_t)h.lasti + h.lastj + 2);
     }
     poy_status s = domain_check(ctx, cm, maxsum);
     if (s != POY_OK) return s;
     if ((s = ensure_params(ctx, cm, pool)) != POY_OK) return s;
-    for (int p = 0; p < n; ++p) hp[p].gapfree = pool->h_gapfree[h_si[p]] && pool->h_gapfree[h_sj[p]];
+    for (int p = 0; p < n; ++p) hp[p].gapfree = linear ? 1 : (pool->h_gapfree[h_si[p]] && pool->h_gapfree[h_sj[p]]);
 
     void *v_state, *v_eb, *v_jobs, *v_misc, *v_pin, *v_pin2;
     if ((s = scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
@@ -548,7 +560,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             HostPair &h = hp[p];
             const int delta = h.lastj - h.lasti;
             const int pp = (h.T - delta) / 2;
-            h.k = pp >= h.lasti ? h.lasti - 1 : pp;
+            if (!linear) h.k = pp >= h.lasti ? h.lasti - 1 : pp;           // src/algn.c:2195-2196 (lenX = last index)
+            else h.k = h.fullplane ? h.lasti : (pp >= h.lasti + 1 ? h.lasti : pp);  // :1070-1071 (lenX = length)
             if (h.lasti == 0) h.k = 0;
             const int64_t B = (int64_t)delta + 2 * (int64_t)h.k + 1;
             // the packed 16x2 gap counters of k_band2 are exact while len_i + len_j < 65535
@@ -556,7 +569,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             h.stride = h.dclass ? band2_stride_for(h.dclass, B) : (int)(((B + 1) / 2 + 31) & ~31ll);
             h.dir_bytes = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2) * h.stride;
             h.iterations++;
-            h.cells += band_cells(h.lasti, h.lastj, h.k);
+            h.cells += h.fullplane ? (int64_t)h.lasti * (h.lastj + 1) : band_cells(h.lasti, h.lastj, h.k);
         }
         // order: by kernel class, then by size (largest first) for load balance
         order = active;
@@ -589,7 +602,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 const HostPair &h = hp[p];
                 BandJob &j = hj[q];
                 j.off_i = h.off_i; j.off_j = h.off_j; j.lasti = h.lasti; j.lastj = h.lastj; j.k = h.k; j.pair = p;
-                j.swaped = h_swaped ? (h_swaped[p] ? 1 : 0) : 0;
+                j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0);
                 j.stride = h.stride; j.dir_off = doff; j.eb_off = h.eb_off;
                 doff += (h.dir_bytes + 255) & ~255ll;
                 if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
@@ -602,21 +615,25 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 int q1 = q0;
                 while (q1 < nj && hp[order[pos + q1]].dclass == cls && hp[order[pos + q1]].gapfree == gf) ++q1;
                 if (cls != 0) {
-                    CK(launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, d_counter + (nlaunch++ & 7), d_state, d_eb, d_dir));
+                    if (linear) CK(launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch++ & 7), d_state, d_dir));
+                    else CK(launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, d_counter + (nlaunch++ & 7), d_state, d_eb, d_dir));
                 } else {
                     void *v_work;
                     const size_t wstride = 6 * (size_t)((gen_width + 31) & ~31ll);
                     const int blocks = std::min(gen_blocks, q1 - q0);
                     if ((s = scratch(ctx, SL_WORK, sizeof(int) * wstride * (size_t)blocks, &v_work)) != POY_OK) return s;
-                    CK(launch_band_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_eb, d_dir, (int *)v_work, wstride, blocks));
+                    if (linear) CK(launch_band_lin_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_dir, (int *)v_work, wstride, blocks));
+                    else CK(launch_band_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_eb, d_dir, (int *)v_work, wstride, blocks));
                 }
                 q0 = q1;
             }
             // stop rule on the device, then traceback of the pairs that stopped (others return immediately)
-            CK(launch_band_finish(ctx, d_jobs, nj, d_state, d_done, pool->d_g0, cm->h.gap_open));
+            if (linear) CK(launch_lin_finish(ctx, pool, d_jobs, nj, d_state, d_done));
+            else CK(launch_band_finish(ctx, d_jobs, nj, d_state, d_done, pool->d_g0, cm->h.gap_open));
             if (want_trace) {
-                CK(launch_traceback(ctx, cm, pool, d_jobs, nj, d_done, d_dir, d_out_off, d_median, d_medianwg, d_resi,
-                                    d_resj, d_out_len));
+                if (linear) CK(launch_traceback_lin(ctx, pool, d_jobs, nj, d_done, d_dir, d_out_off, d_resi, d_resj, d_out_len));
+                else CK(launch_traceback(ctx, cm, pool, d_jobs, nj, d_done, d_dir, d_out_off, d_median, d_medianwg, d_resi,
+                                         d_resj, d_out_len));
             }
             CK(cudaStreamSynchronize(ctx->stream));  // the pinned job staging and the arena are reused by the next wave
             pos = end;
@@ -713,6 +730,53 @@ extern "C" poy_status poy_batch_align_affine(poy_ctx *ctx, const poy_cm *cm, con
     if (resj) CK(cudaMemcpyAsync(resj, d_j, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return POY_OK;
+}
+
+// ---- batch twins of algn_CAML_simple_2 / algn_CAML_align_2d (linear gap) ---------------------------------------
+extern "C" poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                             const int32_t *s1, const int32_t *s2, const int32_t *deltawh,
+                                             const uint8_t *swaped, const int64_t *out_off, int32_t *cost, uint8_t *r1,
+                                             uint8_t *r2, int32_t *out_len, int32_t *stats) {
+    if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!s1 || !s2 || !deltawh))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    const bool want_trace = r1 || r2 || out_len;
+    if (want_trace && !out_off) return fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
+    int64_t total = 0;
+    for (int p = 0; p < n; ++p) {
+        if (s1[p] < 0 || s1[p] >= pool->nseq || s2[p] < 0 || s2[p] >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+        if (want_trace) {
+            const int64_t cap = (pool->h_off[s1[p] + 1] - pool->h_off[s1[p]]) + (pool->h_off[s2[p] + 1] - pool->h_off[s2[p]]);
+            total = std::max(total, out_off[p] + cap);
+        }
+    }
+    const size_t al_total = ((size_t)total + 255) & ~(size_t)255;
+    void *v_out;
+    const size_t need = sizeof(int64_t) * (size_t)n + sizeof(int32_t) * 3 * (size_t)n + al_total * 2 + 1024;
+    poy_status s = scratch(ctx, SL_JOBS2, need, &v_out);
+    if (s != POY_OK) return s;
+    uint8_t *cur = (uint8_t *)v_out;
+    int64_t *d_out_off = (int64_t *)cur; cur += sizeof(int64_t) * (size_t)n;
+    int32_t *d_cost = (int32_t *)cur; cur += sizeof(int32_t) * (size_t)n;
+    int32_t *d_len = (int32_t *)cur; cur += sizeof(int32_t) * 2 * (size_t)n;
+    cur = (uint8_t *)(((uintptr_t)cur + 255) & ~(uintptr_t)255);
+    uint8_t *d_1 = nullptr, *d_2 = nullptr;
+    if (r1) { d_1 = cur; cur += al_total; }
+    if (r2) { d_2 = cur; cur += al_total; }
+    if (want_trace) CK(cudaMemcpyAsync(d_out_off, out_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    s = align_impl(ctx, cm, pool, n, s1, s2, swaped, want_trace ? d_out_off : nullptr, d_cost, nullptr, nullptr, d_1, d_2,
+                   want_trace ? d_len : nullptr, stats, deltawh);
+    if (s != POY_OK) return s;
+    if (cost) CK(cudaMemcpyAsync(cost, d_cost, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_len) CK(cudaMemcpyAsync(out_len, d_len, sizeof(int32_t) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (r1) CK(cudaMemcpyAsync(r1, d_1, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (r2) CK(cudaMemcpyAsync(r2, d_2, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+
+extern "C" poy_status poy_batch_cost_linear(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
+                                            const int32_t *s1, const int32_t *s2, const int32_t *deltawh, int32_t *cost) {
+    return poy_batch_align_linear(ctx, cm, pool, n, s1, s2, deltawh, nullptr, nullptr, cost, nullptr, nullptr, nullptr, nullptr);
 }
 
 // ---- micro-benchmark ---------------------------------------------------------------------------------------

@@ -8,16 +8,81 @@ import numpy as np
 from .api import _ptr
 
 
+def _gap_counts(pool):
+    """Sequence.count_gaps for every pool sequence: symbols that carry the gap bit, leading gap included
+    (seq_CAML_count, src/seq.c:644-669)."""
+    if getattr(pool, "_gapcnt", None) is None:
+        has = (pool.data & 16) != 0
+        cs = np.concatenate([[0], np.cumsum(has, dtype=np.int64)])
+        pool._gapcnt = (cs[pool.offsets[1:]] - cs[pool.offsets[:-1]]).astype(np.int64)
+    return pool._gapcnt
+
+
+def _linear_args(pool, a, b, deltaw):
+    """Shorter-first ordering and the deltaw of Sequence.Align.cost_2 (src/sequence.ml:868-925)."""
+    a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+    la, lb = pool.lens[a], pool.lens[b]
+    swaped = (la > lb)
+    s1 = np.where(swaped, b, a).astype(np.int32); s2 = np.where(swaped, a, b).astype(np.int32)
+    l1, l2 = pool.lens[s1], pool.lens[s2]
+    gc = _gap_counts(pool)
+    gaps = np.maximum(gc[a], gc[b])
+    dif = l1 - l2
+    lower = (l1.astype(np.float64) * 0.10).astype(np.int64)       # int_of_float (float s1len *. 0.10)
+    if deltaw is None:
+        dcalc = np.where(dif < lower, lower // 2, 2)
+    else:
+        dcalc = np.where(dif < lower, lower, int(deltaw))
+    return s1, s2, (gaps + dcalc).astype(np.int32), swaped.astype(np.uint8)
+
+
 class Align:
     @staticmethod
-    def cost_2(ctx, cm, pool, a, b):
-        """Sequence.Align.cost_2 under an Affine model = cost_2_affine =
-        "algn_CAML_cost_affine_3" (src/sequence.ml:630,928-936).  Either order; returns int32[n]."""
+    def cost_2(ctx, cm, pool, a, b, deltaw=None):
+        """Sequence.Align.cost_2 (src/sequence.ml:928-936).  Affine model: cost_2_affine =
+        "algn_CAML_cost_affine_3", either order.  Linear / no-alignment model: c_cost_2 =
+        "algn_CAML_simple_2" with the shorter sequence first and deltaw = gaps + deltaw_calc
+        (src/sequence.ml:868-925).  Returns int32[n]."""
+        if cm.host.cost_model_type != 1:
+            s1, s2, dwh, _ = _linear_args(pool, a, b, deltaw)
+            cost = np.zeros(len(s1), np.int32)
+            ctx.check(ctx.L.poy_batch_cost_linear(ctx.h, cm.h, pool.h, len(s1), _ptr(s1), _ptr(s2), _ptr(dwh), _ptr(cost)))
+            return cost
         a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
         n = len(a)
         cost = np.zeros(n, np.int32)
         ctx.check(ctx.L.poy_batch_cost_affine(ctx.h, cm.h, pool.h, n, _ptr(a), _ptr(b), _ptr(cost)))
         return cost
+
+    @staticmethod
+    def align_2(ctx, cm, pool, a, b, stats=False):
+        """Sequence.Align.align_2 (src/sequence.ml:1061-1082): affine -> align_affine_3; linear ->
+        cost_2 + create_edited_2 ("algn_CAML_backtrace_2d").  Returns dict(cost, res_a, res_b)."""
+        if cm.host.cost_model_type == 1:
+            r = Align.align_affine_3(ctx, cm, pool, a, b, want=("resi", "resj"), stats=stats)
+            return r
+        s1, s2, dwh, swaped = _linear_args(pool, a, b, None)
+        n = len(s1)
+        caps = (pool.lens[s1] + pool.lens[s2]).astype(np.int64)
+        out_off = np.zeros(n, np.int64)
+        if n > 1:
+            np.cumsum(caps[:-1], out=out_off[1:])
+        total = int(caps.sum())
+        r1 = np.zeros(total, np.uint8); r2 = np.zeros(total, np.uint8)
+        cost = np.zeros(n, np.int32); out_len = np.zeros(2 * n, np.int32)
+        st = np.zeros(4 * n, np.int32) if stats else None
+        ctx.check(ctx.L.poy_batch_align_linear(ctx.h, cm.h, pool.h, n, _ptr(s1), _ptr(s2), _ptr(dwh), _ptr(swaped), _ptr(out_off),
+                                               _ptr(cost), _ptr(r1), _ptr(r2), _ptr(out_len), _ptr(st)))
+        out_len = out_len.reshape(n, 2)
+        ends = out_off + caps
+        x1 = [r1[ends[p] - out_len[p, 0]:ends[p]] for p in range(n)]
+        x2 = [r2[ends[p] - out_len[p, 1]:ends[p]] for p in range(n)]
+        res = {"cost": cost, "swaped": swaped,
+               "res_a": [x2[p] if swaped[p] else x1[p] for p in range(n)],
+               "res_b": [x1[p] if swaped[p] else x2[p] for p in range(n)]}
+        if stats:
+            res["stats"] = st.reshape(n, 4)
+        return res
 
     @staticmethod
     def align_affine_3(ctx, cm, pool, a, b, want=("median", "medianwg", "resi", "resj"), stats=False):

@@ -72,16 +72,19 @@ def test_wrong_order_is_reported(ctx):
     cm.close(); pool.close()
 
 
-def test_linear_model_rejected(ctx):
+def test_model_mismatch_is_reported(ctx):
+    """the affine entry points refuse a linear cost model and vice versa (POY_ERR_MODEL)"""
     import poy5_b200 as pb
+    from poy5_b200.api import _ptr
     from poy5_b200.cost_matrix import Two_D
-    from poy5_b200.sequence import Align
-    cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 1, None).full)
-    pool = pb.Pool(ctx, [synth.with_gap([1, 2, 4]), synth.with_gap([1, 2])])
-    with pytest.raises(pb.PoyError) as e:
-        Align.cost_2(ctx, cm, pool, [0], [1])
-    assert e.value.status == -6
-    cm.close(); pool.close()
+    lin = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 1, None).full)
+    aff = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 1, 3).full)
+    pool = pb.Pool(ctx, [synth.with_gap([1, 2]), synth.with_gap([1, 2, 4])])
+    a = np.array([0], np.int32); b = np.array([1], np.int32); cost = np.zeros(1, np.int32); dw = np.array([3], np.int32)
+    assert ctx.L.poy_batch_cost_affine(ctx.h, lin.h, pool.h, 1, _ptr(a), _ptr(b), _ptr(cost)) == -6
+    assert ctx.L.poy_batch_cost_linear(ctx.h, aff.h, pool.h, 1, _ptr(a), _ptr(b), _ptr(dw), _ptr(cost)) == -6
+    assert ctx.L.poy_batch_cost_linear(ctx.h, lin.h, pool.h, 1, _ptr(b), _ptr(a), _ptr(dw), _ptr(cost)) == -4   # longer first
+    lin.close(); aff.close(); pool.close()
 
 
 # ---- BASELINE sizes: size-independent properties + sampled oracle checks ------------------------------
@@ -144,4 +147,64 @@ def test_arena_waves_do_not_change_results(ctx, port):
     assert np.array_equal(r1["cost"], r2["cost"])
     for p in range(len(ia)):
         assert np.array_equal(r1["median"][p], r2["median"][p]) and np.array_equal(r1["res_a"][p], r2["res_a"][p])
+    cm.close(); pool.close()
+
+
+# ---- linear-gap path (algn_CAML_simple_2 / backtrace_2d) -------------------------------------------------
+def _oracle_linear(port, pc, pool_seq_a, pool_seq_b, deltaw=None):
+    """Sequence.Align.cost_2 / align_2 semantics (linear) on top of the oracle."""
+    a, b = pool_seq_a, pool_seq_b
+    sw = int(len(a) > len(b))
+    s1, s2 = (b, a) if sw else (a, b)
+    gaps = max(int((a & 16 != 0).sum()), int((b & 16 != 0).sum()))
+    lower = int(len(s1) * 0.10)
+    dif = len(s1) - len(s2)
+    dcalc = (lower // 2 if dif < lower else 2) if deltaw is None else (lower if dif < lower else deltaw)
+    c, r1, r2 = port.align_linear(pc, s1, s2, gaps + dcalc, sw)
+    return (c, r2, r1) if sw else (c, r1, r2)
+
+
+@pytest.mark.parametrize("tcm", [(1, 1), (2, 1), (1, 2), (3, 2)])
+def test_linear_edge_and_related(ctx, port, tcm):
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.sequence import Align
+    t2d = Two_D.of_transformations_and_gaps(tcm[0], tcm[1], None)
+    full, orig = cmo.dna_matrices(tcm[0], tcm[1], None)
+    for host, om in ((t2d.full, full), (t2d.original, orig)):
+        cm = pb.CostModel(ctx, host)
+        pc = port.cm(om)
+        seqs, ia, ib = edge_pairs(77 + tcm[0], n=300, maxlen=120)
+        more, ja, jb = synth.pair_batch(9 + tcm[1], 60, 500, frac_decorated=0.4, jitter=0.3)
+        base = len(seqs); seqs = seqs + more
+        ia = np.concatenate([ia, ja + base]); ib = np.concatenate([ib, jb + base])
+        pool = pb.Pool(ctx, seqs)
+        for dw in (None, 7):
+            cost = Align.cost_2(ctx, cm, pool, ia, ib, deltaw=dw)
+            for p in range(len(ia)):
+                assert cost[p] == _oracle_linear(port, pc, seqs[ia[p]], seqs[ib[p]], dw)[0], ("linear cost", p, dw)
+        r = Align.align_2(ctx, cm, pool, ia, ib)
+        for p in range(len(ia)):
+            oc, ra, rb = _oracle_linear(port, pc, seqs[ia[p]], seqs[ib[p]])
+            assert oc == r["cost"][p], ("align_2 cost", p)
+            assert np.array_equal(ra, r["res_a"][p]) and np.array_equal(rb, r["res_b"][p]), ("align_2 rows", p)
+        cm.close(); pool.close()
+
+
+def test_linear_long_and_unrelated(ctx, port):
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.sequence import Align
+    cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 1, None).full)
+    pc = port.cm(cmo.dna_matrices(1, 1, None)[0])
+    seqs, ia, ib = synth.pair_batch(321, 10, 2500, frac_decorated=0.3, jitter=0.1)
+    rng = np.random.default_rng(8)
+    for p in range(4):
+        seqs += [synth.with_gap(synth.random_seq(rng, 300 + 50 * p)), synth.with_gap(synth.random_seq(rng, 1500))]
+        ia = np.append(ia, len(seqs) - 2); ib = np.append(ib, len(seqs) - 1)
+    pool = pb.Pool(ctx, seqs)
+    r = Align.align_2(ctx, cm, pool, ia, ib)
+    for p in range(len(ia)):
+        oc, ra, rb = _oracle_linear(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r["cost"][p] and np.array_equal(ra, r["res_a"][p]) and np.array_equal(rb, r["res_b"][p]), p
     cm.close(); pool.close()
