@@ -155,6 +155,25 @@ POY_API poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, const 
                                           const uint8_t *swaped, const int64_t *out_off, int32_t *cost, uint8_t *r1,
                                           uint8_t *r2, int32_t *out_len, int32_t *stats);
 
+/* ---- column-wise helpers over ALIGNED rows (O(L) per pair) ---------------------------------
+ * rows_a / rows_b are packed byte buffers; pair p uses rows_x[off[p] .. off[p] + len[p]).
+ *  poy_batch_median_2     seq_CAML_median_2_with_gaps / _no_gaps (src/seq.c:241-296): out slot of pair p
+ *                         starts at out_off[p] (capacity len[p] + 1), left-justified, out_len[p] bytes
+ *  poy_batch_union        algn_CAML_union (src/algn.c:3657-3678): out has the layout of the inputs
+ *  poy_batch_aligned_cost algn_CAML_verify_2 (use_worst = 0) / algn_CAML_worst_2 (use_worst = 1)
+ *                         (src/algn.c:3003-3130) = Sequence.Align.max_cost_2 / verify
+ *  poy_batch_ancestor_2   algn_CAML_ancestor_2 (src/algn.c:3603-3626,3742): capacity len[p] + 1 */
+POY_API poy_status poy_batch_median_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
+                                      const int64_t *off, const int32_t *len, int32_t with_gaps, const int64_t *out_off,
+                                      uint8_t *out, int32_t *out_len);
+POY_API poy_status poy_batch_union(poy_ctx *ctx, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b, const int64_t *off,
+                                   const int32_t *len, uint8_t *out);
+POY_API poy_status poy_batch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
+                                          const int64_t *off, const int32_t *len, int32_t use_worst, int32_t *cost);
+POY_API poy_status poy_batch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
+                                        const int64_t *off, const int32_t *len, const int64_t *out_off, uint8_t *out,
+                                        int32_t *out_len);
+
 /* ---- INT32 / DPX issue-rate micro-benchmark (roofline denominator) ---------
  * Runs independent chains of one instruction class at full occupancy and
  * returns thread-level operations per second.  kind: 0 IADD3, 1 IMNMX (min),

@@ -8,4 +8,4 @@ checked), but creating a :class:`Context` raises unless a CUDA device is present
 """
 from ._lib import PoyError, lib_path, load  # noqa: F401
 from .api import Context, CostModel, Pool  # noqa: F401
-from . import cost_matrix, sequence  # noqa: F401
+from . import cost_matrix, sequence, seqcs  # noqa: F401

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include "../../include/poy5_b200.h"
 
 #define POY_INF 1000000  // HIGH_NUM, src/algn.c:37 -- added to, never saturated
@@ -134,3 +135,11 @@ cudaError_t launch_gather_cost(poy_ctx *ctx, const PairState *d_state, int n, in
 cudaError_t launch_fill_int(poy_ctx *ctx, int *d, int64_t n, int v);
 cudaError_t launch_microbench(poy_ctx *ctx, int kind, int iters, unsigned long long *d_cycles, int *d_sink,
                               float *ms, double *ops);
+
+cudaError_t launch_median_2(poy_ctx *ctx, const poy_cm *cm, int n, const uint8_t *a, const uint8_t *b, const int64_t *off,
+                            const int *len, int with_gaps, const int64_t *out_off, uint8_t *out, int *out_len);
+cudaError_t launch_union(poy_ctx *ctx, int64_t total, const uint8_t *a, const uint8_t *b, uint8_t *out);
+cudaError_t launch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int n, const uint8_t *a, const uint8_t *b, const int64_t *off,
+                                const int *len, int use_worst, int *cost);
+cudaError_t launch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int n, const uint8_t *a, const uint8_t *b, const int64_t *off,
+                              const int *len, const int64_t *out_off, uint8_t *out, int *out_len);

@@ -779,6 +779,94 @@ extern "C" poy_status poy_batch_cost_linear(poy_ctx *ctx, const poy_cm *cm, cons
     return poy_batch_align_linear(ctx, cm, pool, n, s1, s2, deltawh, nullptr, nullptr, cost, nullptr, nullptr, nullptr, nullptr);
 }
 
+// ---- column-wise helpers over aligned rows ----------------------------------------------------------------------
+namespace {
+struct RowsOnDevice { uint8_t *a, *b, *out; int64_t *off, *out_off; int *len, *res; int64_t total, out_total; };
+
+// stages rows_a / rows_b (+ offsets, lengths and, if given, output offsets with `extra` bytes of slack per pair)
+poy_status stage_rows(poy_ctx *ctx, int n, const uint8_t *rows_a, const uint8_t *rows_b, const int64_t *off, const int32_t *len,
+                      const int64_t *out_off, int extra, RowsOnDevice *r) {
+    r->total = 0; r->out_total = 0;
+    for (int p = 0; p < n; ++p) {
+        if (off[p] < 0 || len[p] < 0) return fail(ctx, POY_ERR_ARG, "negative offset or length");
+        r->total = std::max(r->total, off[p] + len[p]);
+        if (out_off) r->out_total = std::max(r->out_total, out_off[p] + len[p] + extra);
+    }
+    const size_t A = ((size_t)r->total + 255) & ~(size_t)255, O = ((size_t)r->out_total + 255) & ~(size_t)255;
+    void *v;
+    poy_status s = scratch(ctx, SL_JOBS2, 2 * A + O + (size_t)n * (8 + 8 + 4 + 4) + 2048, &v);
+    if (s != POY_OK) return s;
+    uint8_t *cur = (uint8_t *)v;
+    r->a = cur; cur += A; r->b = cur; cur += A; r->out = cur; cur += O;
+    cur = (uint8_t *)(((uintptr_t)cur + 255) & ~(uintptr_t)255);
+    r->off = (int64_t *)cur; cur += 8 * (size_t)n; r->out_off = (int64_t *)cur; cur += 8 * (size_t)n;
+    r->len = (int *)cur; cur += 4 * (size_t)n; r->res = (int *)cur;
+    CK(cudaMemcpyAsync(r->a, rows_a, (size_t)r->total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(r->b, rows_b, (size_t)r->total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(r->off, off, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(r->len, len, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (out_off) CK(cudaMemcpyAsync(r->out_off, out_off, 8 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    return POY_OK;
+}
+}  // namespace
+
+extern "C" poy_status poy_batch_median_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
+                                         const int64_t *off, const int32_t *len, int32_t with_gaps, const int64_t *out_off,
+                                         uint8_t *out, int32_t *out_len) {
+    if (!ctx || !cm || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !out_off || !out || !out_len))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    RowsOnDevice r;
+    poy_status s = stage_rows(ctx, n, rows_a, rows_b, off, len, out_off, 1, &r);
+    if (s != POY_OK) return s;
+    CK(launch_median_2(ctx, cm, n, r.a, r.b, r.off, r.len, with_gaps, r.out_off, r.out, r.res));
+    CK(cudaMemcpyAsync(out, r.out, (size_t)r.out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_len, r.res, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+
+extern "C" poy_status poy_batch_union(poy_ctx *ctx, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b, const int64_t *off,
+                                      const int32_t *len, uint8_t *out) {
+    if (!ctx || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !out))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    RowsOnDevice r;
+    poy_status s = stage_rows(ctx, n, rows_a, rows_b, off, len, off, 0, &r);
+    if (s != POY_OK) return s;
+    CK(launch_union(ctx, r.total, r.a, r.b, r.out));
+    CK(cudaMemcpyAsync(out, r.out, (size_t)r.total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+
+extern "C" poy_status poy_batch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
+                                             const int64_t *off, const int32_t *len, int32_t use_worst, int32_t *cost) {
+    if (!ctx || !cm || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !cost))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    RowsOnDevice r;
+    poy_status s = stage_rows(ctx, n, rows_a, rows_b, off, len, nullptr, 0, &r);
+    if (s != POY_OK) return s;
+    CK(launch_aligned_cost(ctx, cm, n, r.a, r.b, r.off, r.len, use_worst, r.res));
+    CK(cudaMemcpyAsync(cost, r.res, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+
+extern "C" poy_status poy_batch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
+                                           const int64_t *off, const int32_t *len, const int64_t *out_off, uint8_t *out,
+                                           int32_t *out_len) {
+    if (!ctx || !cm || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !out_off || !out || !out_len))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    RowsOnDevice r;
+    poy_status s = stage_rows(ctx, n, rows_a, rows_b, off, len, out_off, 1, &r);
+    if (s != POY_OK) return s;
+    CK(launch_ancestor_2(ctx, cm, n, r.a, r.b, r.off, r.len, r.out_off, r.out, r.res));
+    CK(cudaMemcpyAsync(out, r.out, (size_t)r.out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_len, r.res, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < n; ++p) if (out_len[p] < 0) return fail(ctx, POY_ERR_ARG, "median should not be 0");
+    return POY_OK;
+}
+
 // ---- micro-benchmark ---------------------------------------------------------------------------------------
 extern "C" poy_status poy_microbench_int(poy_ctx *ctx, int32_t kind, double *ops_per_second, double *sm_clock_mhz) {
     if (!ctx || !ops_per_second) return POY_ERR_ARG;

@@ -1,0 +1,84 @@
+"""Host mirror of ``SeqCS.DOS`` (src/seqCS.ml), batch-shaped: the per-locus direct-optimization
+character.  One call == the ``Array_ops.map`` over loci / the Parmap map over candidates that the
+reference performs one alignment at a time (src/seqCS.ml:2232-2345, src/ptree.ml:1356-1408)."""
+import numpy as np
+from . import sequence
+from .sequence import Align
+
+
+class Heuristic:
+    """`h` of src/seqCS.ml:51-55: the pair (c2_full, c2_original) as device-resident cost models."""
+
+    def __init__(self, c2_full, c2_original):
+        self.c2_full = c2_full
+        self.c2_original = c2_original
+
+
+def _is_empty(pool):
+    """Sequence.is_empty (src/sequence.ml:241-251): every symbol equals the gap code."""
+    if getattr(pool, "_empty", None) is None:
+        nongap = (pool.data != 16)
+        cs = np.concatenate([[0], np.cumsum(nongap, dtype=np.int64)])
+        pool._empty = (cs[pool.offsets[1:]] - cs[pool.offsets[:-1]]) == 0
+    return pool._empty
+
+
+class DOS:
+    @staticmethod
+    def distance(ctx, h, pool, a, b, missing_distance=0):
+        """DOS.distance (src/seqCS.ml:701-774): cost-only alignment under c2_ORIGINAL; an empty sequence
+        on either side returns missing_distance.  deltaw = max(|len a - len b|, 8) as in the reference."""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        empty = _is_empty(pool)
+        skip = empty[a] | empty[b]
+        res = np.full(len(a), missing_distance, np.int64)
+        idx = np.flatnonzero(~skip)
+        if len(idx):
+            cm = h.c2_original
+            if cm.host.cost_model_type == 1:
+                res[idx] = Align.cost_2(ctx, cm, pool, a[idx], b[idx])
+            else:
+                # one deltaw per pair: run the linear entry point with the per-pair value
+                la, lb = pool.lens[a[idx]], pool.lens[b[idx]]
+                dw = np.maximum(np.abs(la - lb), 8)
+                out = np.zeros(len(idx), np.int64)
+                for v in np.unique(dw):
+                    m = dw == v
+                    out[m] = Align.cost_2(ctx, cm, pool, a[idx][m], b[idx][m], deltaw=int(v))
+                res[idx] = out
+        return res
+
+    @staticmethod
+    def median(ctx, h, pool, a, b):
+        """DOS.median (src/seqCS.ml:985-1084) for zero-diagonal (identity) matrices: an empty child yields
+        the other child with cost 0; otherwise align under c2_FULL (affine: align_affine_3; linear:
+        align_2 + ancestor_2 + median_2_with_gaps) and max_cost_2 of the aligned rows.
+        Returns dict(sequence, aligned_a, aligned_b, median_wg, cost2, cost2_max)."""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        n = len(a)
+        empty = _is_empty(pool)
+        ea, eb = empty[a], empty[b]
+        out = dict(sequence=[None] * n, aligned_a=[None] * n, aligned_b=[None] * n, median_wg=[None] * n,
+                   cost2=np.zeros(n, np.int64), cost2_max=np.zeros(n, np.int64))
+        for p in np.flatnonzero(ea | eb):
+            keep, lost = (b[p], a[p]) if ea[p] else (a[p], b[p])
+            out["sequence"][p] = pool.seq(keep).copy()
+            out["aligned_a"][p] = pool.seq(lost).copy(); out["aligned_b"][p] = pool.seq(lost).copy()
+            out["median_wg"][p] = pool.seq(keep).copy()
+        idx = np.flatnonzero(~(ea | eb))
+        if len(idx) == 0:
+            return out
+        cm = h.c2_full
+        if cm.host.cost_model_type == 1:
+            r = Align.align_affine_3(ctx, cm, pool, a[idx], b[idx])
+            med, mwg = r["median"], r["medianwg"]
+        else:
+            r = Align.align_2(ctx, cm, pool, a[idx], b[idx])
+            med = sequence.ancestor_2(ctx, cm, r["res_a"], r["res_b"])
+            mwg = sequence.median_2(ctx, cm, r["res_a"], r["res_b"], True)
+        mx = sequence.aligned_cost(ctx, cm, r["res_a"], r["res_b"], worst=True)
+        for q, p in enumerate(idx):
+            out["sequence"][p] = med[q]; out["median_wg"][p] = mwg[q]
+            out["aligned_a"][p] = r["res_a"][q]; out["aligned_b"][p] = r["res_b"][q]
+        out["cost2"][idx] = r["cost"]; out["cost2_max"][idx] = mx
+        return out

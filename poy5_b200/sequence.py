@@ -166,3 +166,53 @@ def align_affine_3_dev(ctx, cm, pool, h_si, h_sj, d_swaped, d_out_off, d_cost, d
     ctx.check(ctx.L.poy_batch_align_affine_dev(ctx.h, cm.h, pool.h, len(h_si), None, None, vp(d_swaped), _ptr(h_si),
                                                _ptr(h_sj), vp(d_out_off), vp(d_cost), vp(d_median), vp(d_medianwg),
                                                vp(d_resi), vp(d_resj), vp(d_out_len), None))
+
+
+# ---- column-wise helpers over aligned rows -------------------------------------------------------------------
+def _pack_rows(rows_a, rows_b):
+    lens = np.fromiter((len(r) for r in rows_a), np.int32, len(rows_a))
+    off = np.zeros(len(rows_a), np.int64)
+    if len(rows_a) > 1:
+        np.cumsum(lens[:-1], out=off[1:])
+    cat = lambda rows: (np.concatenate([np.asarray(r, np.uint8) for r in rows]) if len(rows) and lens.sum() else np.zeros(1, np.uint8))
+    return np.ascontiguousarray(cat(rows_a)), np.ascontiguousarray(cat(rows_b)), off, lens
+
+
+def median_2(ctx, cm, rows_a, rows_b, with_gaps):
+    """Sequence.median_2 / median_2_with_gaps (src/sequence.ml:473-492) over lists of aligned rows."""
+    a, b, off, lens = _pack_rows(rows_a, rows_b)
+    n = len(lens)
+    out_off = off + np.arange(n, dtype=np.int64)
+    out = np.zeros(int(lens.sum()) + n + 1, np.uint8)
+    out_len = np.zeros(n, np.int32)
+    ctx.check(ctx.L.poy_batch_median_2(ctx.h, cm.h, n, _ptr(a), _ptr(b), _ptr(off), _ptr(lens), int(with_gaps), _ptr(out_off),
+                                       _ptr(out), _ptr(out_len)))
+    return [out[out_off[p]:out_off[p] + out_len[p]] for p in range(n)]
+
+
+def union(ctx, rows_a, rows_b):
+    """Sequence.Align.union (src/sequence.ml:1150-1177 -> algn_CAML_union)."""
+    a, b, off, lens = _pack_rows(rows_a, rows_b)
+    out = np.zeros(max(1, int(lens.sum())), np.uint8)
+    ctx.check(ctx.L.poy_batch_union(ctx.h, len(lens), _ptr(a), _ptr(b), _ptr(off), _ptr(lens), _ptr(out)))
+    return [out[off[p]:off[p] + lens[p]] for p in range(len(lens))]
+
+
+def aligned_cost(ctx, cm, rows_a, rows_b, worst):
+    """algn_CAML_worst_2 (worst=True: Sequence.Align.max_cost_2 without its empty-sequence shortcut) or
+    algn_CAML_verify_2."""
+    a, b, off, lens = _pack_rows(rows_a, rows_b)
+    cost = np.zeros(len(lens), np.int32)
+    ctx.check(ctx.L.poy_batch_aligned_cost(ctx.h, cm.h, len(lens), _ptr(a), _ptr(b), _ptr(off), _ptr(lens), int(bool(worst)), _ptr(cost)))
+    return cost
+
+
+def ancestor_2(ctx, cm, rows_a, rows_b):
+    """Sequence.Align.ancestor_2 (algn_CAML_ancestor_2)."""
+    a, b, off, lens = _pack_rows(rows_a, rows_b)
+    n = len(lens)
+    out_off = off + np.arange(n, dtype=np.int64)
+    out = np.zeros(int(lens.sum()) + n + 1, np.uint8)
+    out_len = np.zeros(n, np.int32)
+    ctx.check(ctx.L.poy_batch_ancestor_2(ctx.h, cm.h, n, _ptr(a), _ptr(b), _ptr(off), _ptr(lens), _ptr(out_off), _ptr(out), _ptr(out_len)))
+    return [out[out_off[p]:out_off[p] + out_len[p]] for p in range(n)]

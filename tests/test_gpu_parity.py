@@ -208,3 +208,66 @@ def test_linear_long_and_unrelated(ctx, port):
         oc, ra, rb = _oracle_linear(port, pc, seqs[ia[p]], seqs[ib[p]])
         assert oc == r["cost"][p] and np.array_equal(ra, r["res_a"][p]) and np.array_equal(rb, r["res_b"][p]), p
     cm.close(); pool.close()
+
+
+# ---- column-wise helpers and the SeqCS.DOS mirror -------------------------------------------------------
+@pytest.mark.parametrize("go", [None, 3])
+def test_columnwise_helpers(ctx, port, go):
+    import poy5_b200 as pb
+    from poy5_b200 import sequence
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.sequence import Align
+    cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(2, 1, go).full)
+    pc = port.cm(cmo.dna_matrices(2, 1, go)[0])
+    seqs, ia, ib = edge_pairs(5, n=200, maxlen=70)
+    pool = pb.Pool(ctx, seqs)
+    r = Align.align_2(ctx, cm, pool, ia, ib)
+    ra, rb = r["res_a"], r["res_b"]
+    for wg in (False, True):
+        got = sequence.median_2(ctx, cm, ra, rb, wg)
+        for p in range(len(ia)):
+            assert np.array_equal(got[p], port.median_2(pc, ra[p], rb[p], wg)), ("median_2", wg, p)
+    u = sequence.union(ctx, ra, rb)
+    anc = sequence.ancestor_2(ctx, cm, ra, rb)
+    worst = sequence.aligned_cost(ctx, cm, ra, rb, True)
+    ver = sequence.aligned_cost(ctx, cm, ra, rb, False)
+    for p in range(len(ia)):
+        assert np.array_equal(u[p], port.union(ra[p], rb[p]))
+        assert np.array_equal(anc[p], port.ancestor_2(pc, ra[p], rb[p])), ("ancestor_2", p)
+        assert worst[p] == port.worst_2(pc, ra[p], rb[p]) and ver[p] == port.verify_2(pc, ra[p], rb[p])
+    cm.close(); pool.close()
+
+
+@pytest.mark.parametrize("go", [None, 3])
+def test_dos_median_and_distance(ctx, port, go):
+    """SeqCS.DOS.median / distance semantics incl. the empty-sequence rules (src/seqCS.ml:705-709,991-1039)"""
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.seqcs import DOS, Heuristic
+    t2d = Two_D.of_transformations_and_gaps(1, 2, go)
+    full, orig = cmo.dna_matrices(1, 2, go)
+    h = Heuristic(pb.CostModel(ctx, t2d.full), pb.CostModel(ctx, t2d.original))
+    pf, po = port.cm(full), port.cm(orig)
+    seqs, ia, ib = edge_pairs(23, n=150, maxlen=60)
+    pool = pb.Pool(ctx, seqs)
+    d = DOS.distance(ctx, h, pool, ia, ib, missing_distance=0)
+    m = DOS.median(ctx, h, pool, ia, ib)
+    for p in range(len(ia)):
+        a, b = seqs[ia[p]], seqs[ib[p]]
+        ea, eb = bool((a == 16).all()), bool((b == 16).all())
+        if ea or eb:
+            assert d[p] == 0
+            assert np.array_equal(m["sequence"][p], b if ea else a) and m["cost2"][p] == 0
+            continue
+        if go is None:
+            assert d[p] == _oracle_linear(port, po, a, b, max(abs(len(a) - len(b)), 8))[0]
+            oc, ra, rb = _oracle_linear(port, pf, a, b)
+            assert np.array_equal(m["sequence"][p], port.ancestor_2(pf, ra, rb))
+            assert np.array_equal(m["median_wg"][p], port.median_2(pf, ra, rb, True))
+        else:
+            assert d[p] == port.cost_affine(po, a, b)
+            oc, om, ow, ra, rb = oracle_align(port, pf, a, b)
+            assert np.array_equal(m["sequence"][p], om) and np.array_equal(m["median_wg"][p], ow)
+        assert m["cost2"][p] == oc and m["cost2_max"][p] == port.worst_2(pf, ra, rb)
+        assert np.array_equal(m["aligned_a"][p], ra) and np.array_equal(m["aligned_b"][p], rb)
+    pool.close()
