@@ -82,3 +82,26 @@ class DOS:
             out["aligned_a"][p] = r["res_a"][q]; out["aligned_b"][p] = r["res_b"][q]
         out["cost2"][idx] = r["cost"]; out["cost2_max"][idx] = mx
         return out
+
+
+def median_3_union(ctx, cm2, pool, parent, aligned_a, aligned_b):
+    """DOS.median_3_union (src/seqCS.ml:1151-1178): the live three-sequence path used for final-state
+    assignment.  For every node: union of its two aligned children
+    (Sequence.Align.union -> algn_CAML_union), ONE pairwise alignment parent x union under cm2
+    (Sequence.Align.align_2), median_2 of the two aligned rows (gap-free, leading gap restored) and
+    max_cost_2.  `parent` are pool indices, aligned_a / aligned_b lists of equal-length aligned rows.
+    Returns dict(sequence, cost, cost_max, aligned_parent, aligned_union)."""
+    from .api import Pool
+    parent = np.ascontiguousarray(parent, np.int32)
+    n = len(parent)
+    un = sequence.union(ctx, aligned_a, aligned_b)
+    # the unions become sequences of a scratch pool next to the parents
+    seqs = [pool.seq(int(p)) for p in parent] + [np.asarray(u, np.uint8) for u in un]
+    tmp = Pool(ctx, seqs)
+    ia = np.arange(n, dtype=np.int32); ib = ia + n
+    r = Align.align_2(ctx, cm2, tmp, ia, ib)
+    med = sequence.median_2(ctx, cm2, r["res_a"], r["res_b"], False)
+    mx = sequence.aligned_cost(ctx, cm2, r["res_a"], r["res_b"], worst=True)
+    tmp.close()
+    return dict(sequence=med, cost=np.asarray(r["cost"], np.int64), cost_max=mx.astype(np.int64),
+                aligned_parent=r["res_a"], aligned_union=r["res_b"])

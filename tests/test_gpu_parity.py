@@ -271,3 +271,40 @@ def test_dos_median_and_distance(ctx, port, go):
         assert m["cost2"][p] == oc and m["cost2_max"][p] == port.worst_2(pf, ra, rb)
         assert np.array_equal(m["aligned_a"][p], ra) and np.array_equal(m["aligned_b"][p], rb)
     pool.close()
+
+
+@pytest.mark.parametrize("go", [None, 3])
+def test_median_3_union(ctx, port, go):
+    """config #3's live path: parent x union(children) alignment + median_2"""
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.seqcs import DOS, Heuristic, median_3_union
+    t2d = Two_D.of_transformations_and_gaps(1, 1, go)
+    full, orig = cmo.dna_matrices(1, 1, go)
+    h = Heuristic(pb.CostModel(ctx, t2d.full), pb.CostModel(ctx, t2d.original))
+    pf = port.cm(full)
+    rng = np.random.default_rng(12)
+    seqs = []
+    nt = 60
+    for t in range(nt):
+        anc = synth.random_seq(rng, int(rng.integers(20, 220)))
+        par = synth.evolve(rng, anc, 0.08, 0.03)
+        c1 = synth.evolve(rng, anc, 0.1, 0.04); c2 = synth.evolve(rng, anc, 0.1, 0.04)
+        if t % 4 == 0:
+            par = synth.decorate(rng, par, 0.1, 0.1)
+        seqs += [synth.with_gap(par), synth.with_gap(c1), synth.with_gap(c2)]
+    pool = pb.Pool(ctx, seqs)
+    ip = np.arange(0, 3 * nt, 3, dtype=np.int32); i1 = ip + 1; i2 = ip + 2
+    node = DOS.median(ctx, h, pool, i1, i2)
+    got = median_3_union(ctx, h.c2_full, pool, ip, node["aligned_a"], node["aligned_b"])
+    for t in range(nt):
+        u = port.union(node["aligned_a"][t], node["aligned_b"][t])
+        p = seqs[ip[t]]
+        if go is None:
+            oc, ra, rb = _oracle_linear(port, pf, p, u)
+        else:
+            oc, _, _, ra, rb = oracle_align(port, pf, p, u)
+        assert got["cost"][t] == oc
+        assert np.array_equal(got["sequence"][t], port.median_2(pf, ra, rb, False))
+        assert got["cost_max"][t] == port.worst_2(pf, ra, rb)
+    pool.close()
