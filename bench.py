@@ -51,10 +51,12 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------
 def chunks_for(npairs, length, chunk_bases):
+    """equal-sized batches of at most chunk_bases sequence bytes"""
     per = max(1, chunk_bases // (2 * (length + 8)))
+    nchunks = (npairs + per - 1) // per
     out, p = [], 0
-    while p < npairs:
-        n = min(per, npairs - p)
+    for c in range(nchunks):
+        n = (npairs - p + (nchunks - c) - 1) // (nchunks - c)
         out.append((p, n))
         p += n
     return out
@@ -337,18 +339,27 @@ def main():
                    ms_per_step=1e3 * te, alignments_per_s=world * total_aln / te)
 
     if rank == 0:
-        # dominant kernel: the gap-free cost-only wavefront (k_cost_gf<16>) on the longest length
+        # dominant kernel: the cost-only wavefront (k_cost_affine) on the longest length
         Ltop = max(kernel_ms) if kernel_ms else lengths[-1]
         k_ms, k_cells = kernel_ms.get(Ltop, (ms, total_cells))
+        k_bytes = sum(int(w["data"].nbytes) + 4 * w["n"] for w in work if w["L"] == Ltop)
+        hbm_peak = 6550.7
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
         achieved = k_cells * OPS_PER_CELL["gapfree"] / (k_ms * 1e-3) / 1e12
-        roofline = dict(bound="int32", kernel="k_cost_gf<16>", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
+        roofline = dict(bound="int32", kernel="k_cost_affine", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
                         frac=achieved / (peak_ops / 1e12), traffic=None,
                         note="INT32 issue roofline: algorithmic scalar add/min per cell (%d, gap-free cost-only cell) x cells / "
                              "launch time, vs the IADD3-class issue rate measured live by poy_microbench_int "
                              "(DPX VIADDMNMX measured %.2f Tops/s). Launch time from CUDA events around the cost-only "
-                             "call on the L=%d segment (about 10%% of its pairs carry gap bits and run the 4-state kernel)."
+                             "calls on the L=%d segment (about 10%% of its pairs carry gap bits and run the 4-state path, 16 ops/cell, but are counted at 9)."
                              % (OPS_PER_CELL["gapfree"], dpx_ops / 1e12, Ltop),
-                        hbm_bytes_per_launch=None, sm_clock_mhz_microbench=peak_clock)
+                        sm_clock_mhz_microbench=peak_clock,
+                        hbm=dict(algorithmic_bytes_per_launch=int(k_bytes), achieved_gbs=k_bytes / (k_ms * 1e-3) / 1e9,
+                                 peak_gbs=hbm_peak, frac=k_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                                 note="sequence bytes in + 4 B cost out per pair (SURVEY 8d): this path is integer-issue bound, not HBM bound"))
         cpu = None
         if not args.no_cpu:
             try:

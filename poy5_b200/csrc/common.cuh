@@ -104,12 +104,9 @@ struct PairState {        // survives across band fills of the same pair
 // launchers (defined in the .cu files)
 cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool);
 cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, const int *d_a, const int *d_b,
-                                   CostJob *d_free, CostJob *d_gen, int *d_counts);
-cudaError_t launch_cost_affine_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs_free,
-                                     const CostJob *d_jobs_gen, const int *d_counts, int *d_counters, int4 *d_bound,
-                                     size_t bound_stride, int blocks, int *d_cost);
-cudaError_t launch_cost_gf(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs,
-                           const int *d_count, int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost);
+                                   CostJob *d_jobs, int *d_counts);
+cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
+                               int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost);
 cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                              int dclass, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,

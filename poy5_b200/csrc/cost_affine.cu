@@ -18,11 +18,13 @@
 //   CB = diag + min(CB', EV' + [ic has gap]go_j, EH' + [jc has gap]go_i, EB' + max(go_i,go_j))
 // evaluated with the DPX fused add-min instructions (__viaddmin_s32, __vimin3_s32).
 //
-// Two instantiations: GAPFREE (neither sequence contains a gap-bit symbol, the
-// case of all leaf/observed DNA) drops the EB state -- provably EB >= CB in every
-// cell when every table entry is <= INF, so it can never win a minimum -- and
-// folds min3(CB,EV,EH) of the diagonal cell into one carried value; the general
-// instantiation keeps all four states.
+// Two code paths inside one persistent kernel: gap-free pairs (neither sequence
+// contains a gap-bit symbol, the case of all leaf/observed DNA) drop the EB state
+// -- provably EB >= CB in every cell when every table entry is <= INF, so it can
+// never win a minimum -- and fold min3(CB,EV,EH) of the diagonal cell into one
+// carried value M:  CB = M' + diag, EH = min(EH[j-1], CB[j-1]+GO) + ge_j,
+// EV = min(EV[i-1], CB[i-1]+GO) + ge_i, M = min3(CB,EH,EV): 3 DPX instructions, 3
+// adds and one table lookup per cell.  General pairs keep all four states.
 //
 // The reference's row-buffer aliasing is reproduced in closed
 // form: for lenj >= 3 its only observable effect is that on every even row i>=2
@@ -84,189 +86,270 @@ __device__ int cost_affine_tiny(const DevCM *cm, const int *s_cost16, const int4
     return res;
 }
 
-// ---- the wavefront kernel ------------------------------------------------------------
-template <int C, bool GAPFREE>
-__global__ void __launch_bounds__(128)
-k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
-              const int *__restrict__ g0v, const CostJob *__restrict__ jobs, const int *__restrict__ njobs_ptr, int *counter,
-              int4 *bound, size_t bound_stride, int *__restrict__ cost_out) {
+#define GF_TAB_COLS 17                       // 16 symbols + 1 "padding" column whose entries are INF
+#define TAB_ROW_INTS (GF_TAB_COLS * 32)      // ints between consecutive table rows (32 bank replicas per entry)
+
+// ---- general pairs: 4 states, C columns per lane, left-aligned columns ---------------------------------
+template <int C>
+__device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_tab, const int *s_cost16, const CostJob &J,
+                                                  const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
+                                                  const int *__restrict__ g0v, int4 *bnd0, int4 *bnd1, int GO, int lane,
+                                                  int *__restrict__ cost_out) {
     constexpr int W = 32 * C;
-    __shared__ int s_cost16[256];
-    __shared__ int s_rep[256 * 32];  // cost16 replicated once per bank: entry e of lane l at [e*32 + l]
+    const int lasti = J.lasti, lastj = J.lastj;
+    const int4 *rp = rowp + J.off_i;
+    const int4 *cp = colp + J.off_j;
+    const int *g0 = g0v + J.off_j;
+    if (lastj + 1 <= TINY_L) {
+        if (lane == 0) cost_out[J.out] = cost_affine_tiny(cm, s_cost16, rp, cp, g0, lasti, lastj);
+        return;
+    }
+    if (lasti == 0) {  // no rows: minimum over row 0 at the last column (src/algn.c:2105-2109)
+        if (lane == 0) cost_out[J.out] = imin(GO + g0[lastj], POY_INF);
+        return;
+    }
+    const int nb = (lastj + W - 1) / W;
+    const int jres = lastj - 1 - (nb - 1) * W;  // position of column lastj inside the last block
+    const int tl = jres / C, cl = jres % C;
+    for (int b = 0; b < nb; ++b) {
+        const int jb = b * W + lane * C;  // slot c <-> column jb + c + 1
+        const int4 *bin = (b & 1) ? bnd0 : bnd1;
+        int4 *bout = (b & 1) ? bnd1 : bnd0;
+        const bool last_block = (b == nb - 1);
+        const bool owns_last = last_block && lane == tl;
+        int c_ext[C], c_opn[C], c_go[C], c_fl[C];
+        int CBu[C], EVu[C], EHu[C], EBu[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = jb + c + 1;
+            if (j <= lastj) {
+                const int4 v = cp[j];
+                c_ext[c] = v.x; c_opn[c] = v.y; c_go[c] = v.z; c_fl[c] = v.w;
+                EHu[c] = GO + g0[j];
+            } else {
+                c_ext[c] = 0; c_opn[c] = 0; c_go[c] = 0; c_fl[c] = 0;
+                EHu[c] = POY_INF;
+            }
+            CBu[c] = POY_INF; EVu[c] = POY_INF; EBu[c] = POY_INF;
+        }
+        int dCB, dEV, dEH, dEB;   // cell (i-1, jb): diagonal predecessor of slot 0
+        if (jb == 0) { dCB = 0; dEV = GO; dEH = GO; dEB = POY_INF; }
+        else { dCB = POY_INF; dEV = POY_INF; dEH = GO + g0[jb]; dEB = POY_INF; }
+        int ev_col0 = GO;  // EV[i][0] running sum (lane 0 of block 0), src/algn.c:2066-2070
+        int oCB = POY_INF, oEH = POY_INF, oEV = POY_INF, oEB = POY_INF;
+        int4 rnext = rp[1];
+        int4 bnext = make_int4(0, 0, 0, 0);
+        if (b > 0 && lane == 0) bnext = bin[1];
+        const int nsteps = lasti + 31;
+        for (int s = 0; s < nsteps; ++s) {
+            const int i = s - lane + 1;
+            int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
+            int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
+            int lEV = __shfl_up_sync(0xffffffffu, oEV, 1);
+            int lEB = __shfl_up_sync(0xffffffffu, oEB, 1);
+            if (i >= 1 && i <= lasti) {
+                const int4 r = rnext;
+                if (i < lasti) rnext = rp[i + 1];
+                if (lane == 0) {
+                    if (b == 0) {
+                        ev_col0 += r.x;
+                        lCB = POY_INF; lEH = POY_INF; lEV = ev_col0; lEB = POY_INF;
+                    } else {
+                        lCB = bnext.x; lEH = bnext.y; lEV = bnext.z; lEB = bnext.w;
+                        if (i < lasti) bnext = bin[i + 1];
+                    }
+                }
+                int cbL = lCB, ehL = lEH;
+                const int *rowbase = s_tab + (r.w & 15) * TAB_ROW_INTS + lane;
+                const int vext = r.x, opnV = r.y, go_i = r.z;
+                const int mask_i = (r.w & PF_HASGAP) ? -1 : 0;
+                int xCB = dCB, xEV = dEV, xEH = dEH, xEB = dEB;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int fl = c_fl[c];
+                    const int go_j = c_go[c];
+                    const int eh = __viaddmin_s32(ehL, c_ext[c], cbL + c_opn[c]);
+                    const int ev = __viaddmin_s32(EVu[c], vext, CBu[c] + opnV);
+                    const bool both = (r.w & fl & PF_HASGAP) != 0;
+                    const bool clean = ((r.w | fl) & PF_PREVGAP) == 0;
+                    const int dg = both ? 0 : POY_INF;
+                    const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
+                    const int eb = __viaddmin_s32(xEB, dg, xCB + od);
+                    const int diag = rowbase[(fl & 15) << 5];
+                    const int gv = go_j & mask_i;
+                    const int gh = (fl & PF_HASGAP) ? go_i : 0;
+                    const int xgo = go_j < go_i ? go_i : go_j;
+                    int m = __viaddmin_s32(xEV, gv, xCB);
+                    m = __viaddmin_s32(xEH, gh, m);
+                    m = __viaddmin_s32(xEB, xgo, m);
+                    const int cb = m + diag;
+                    xCB = CBu[c]; xEV = EVu[c]; xEH = EHu[c]; xEB = EBu[c];
+                    CBu[c] = cb; EVu[c] = ev; EHu[c] = eh; EBu[c] = eb;
+                    cbL = cb; ehL = eh;
+                }
+                // F5: EV at the last column of an even row comes from clobbered predecessors
+                if (owns_last && !(i & 1)) {
+                    const int pv = POY_INF + imin(r.x, r.y);
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        if (c == cl) EVu[c] = pv;
+                }
+                dCB = lCB; dEV = lEV; dEH = lEH; dEB = lEB;
+                oCB = CBu[C - 1]; oEH = EHu[C - 1]; oEV = EVu[C - 1]; oEB = EBu[C - 1];
+                if (lane == 31 && !last_block) bout[i] = make_int4(oCB, oEH, oEV, oEB);
+            }
+        }
+        if (owns_last) {
+            int res = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (c == cl) res = imin(imin(EHu[c], EVu[c]), imin(CBu[c], EBu[c]));
+            cost_out[J.out] = res;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- gap-free pairs: 3 states (see the header of this file and DESIGN.md section 4) -------------------------
+// Right-aligned columns: column lastj is always slot C-1 of lane 31 of the last block, so the result and the
+// reference's even-row/last-column EV quirk touch one fixed register.  The padding on the left of block 0
+// consists of replicas of column 0 (ge = 0, table entry INF): they reproduce EH = INF, EV[i][0] and M[i][0]
+// exactly and their CB stays >= INF.  Row parameters are loaded 32 rows at a time, lane 0 picks its row by
+// shuffle and every row then travels down the lanes with the DP values.
+template <int C>
+__device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &J, const unsigned *__restrict__ rowpk,
+                                             const int4 *__restrict__ colp, const int *__restrict__ g0v, int4 *bnd0,
+                                             int4 *bnd1, int GO, int lane, int *__restrict__ cost_out) {
+    constexpr int W = 32 * C;
+    const char *s_tab = (const char *)s_tab_i;
+    {
+        const int lasti = J.lasti, lastj = J.lastj;
+        const unsigned *rp = rowpk + J.off_i;
+        const int4 *cp = colp + J.off_j;
+        const int *g0 = g0v + J.off_j;
+        if (lasti == 0) {  // no rows: minimum over row 0 at the last column (src/algn.c:2105-2109)
+            if (lane == 0) cost_out[J.out] = lastj >= 1 ? min(GO + g0[lastj], POY_INF) : 0;
+            return;
+        }
+        const int nb = (lastj + W - 1) / W;
+        const int pad = nb * W - lastj;
+        for (int b = 0; b < nb; ++b) {
+            const int jb = b * W + lane * C - pad;  // slot c <-> column jb + c + 1 (<= 0: replica of column 0)
+            const int4 *bin = (b & 1) ? bnd0 : bnd1;
+            int4 *bout = (b & 1) ? bnd1 : bnd0;
+            const bool last_block = (b == nb - 1);
+            int c_ge[C], c_off[C], CBu[C], EVu[C], Mu[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jb + c + 1;
+                if (j >= 1) {
+                    const int4 v = cp[j];
+                    c_ge[c] = v.x;
+                    c_off[c] = ((v.w & 15) << 7) + (lane << 2);
+                    CBu[c] = POY_INF; EVu[c] = POY_INF;
+                    Mu[c] = min(GO + g0[j], POY_INF);       // min3(INF, INF, EH[0][j])
+                } else {
+                    c_ge[c] = 0;
+                    c_off[c] = (16 << 7) + (lane << 2);
+                    CBu[c] = 0; EVu[c] = GO;                  // CB[0][0], EV[0][0]
+                    Mu[c] = min(0, GO);
+                }
+            }
+            // cell (0, jb): row-0 neighbour to the left of slot 0 (diagonal predecessor of row 1)
+            int dM;
+            if (jb >= 1) dM = min(GO + g0[jb], POY_INF); else dM = min(0, GO);
+            int ev_col0 = GO;                                 // EV[i][0] = GO + sum ge_r (src/algn.c:2066-2070)
+            int oCB = POY_INF, oEH = POY_INF, oM = POY_INF;
+            unsigned rk = 0, win = 0;
+            int4 bnext = make_int4(0, 0, 0, 0);
+            if (b > 0 && lane == 0) bnext = bin[1];
+
+            const int nsteps = lasti + 31;
+            for (int s = 0; s < nsteps; ++s) {
+                if ((s & 31) == 0) {                          // next 32 packed rows, one coalesced load
+                    const int r = s + lane + 1;
+                    win = rp[r <= lasti ? r : lasti];
+                }
+                const int i = s - lane + 1;
+                int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
+                int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
+                int lM = __shfl_up_sync(0xffffffffu, oM, 1);
+                unsigned rprev = __shfl_up_sync(0xffffffffu, rk, 1);
+                const unsigned rfirst = __shfl_sync(0xffffffffu, win, s & 31);
+                rk = lane == 0 ? rfirst : rprev;              // row i's parameters travel down the lanes
+                if (i >= 1) {
+                    const int ge_i = (int)(rk >> 16);
+                    const char *rowbase = s_tab + (rk & 0xFFFFu);
+                    if (lane == 0) {
+                        if (b == 0) {
+                            ev_col0 += ge_i;
+                            lCB = POY_INF; lEH = POY_INF; lM = ev_col0;
+                        } else {
+                            lCB = bnext.x; lEH = bnext.y; lM = bnext.z;
+                            bnext = bin[i < lasti ? i + 1 : lasti];
+                        }
+                    }
+                    int cbL = lCB, ehL = lEH, mD = dM;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int diag = *(const int *)(rowbase + c_off[c]);
+                        const int cb = mD + diag;
+                        const int eh = __viaddmin_s32(cbL, GO, ehL) + c_ge[c];
+                        const int ev = __viaddmin_s32(CBu[c], GO, EVu[c]) + ge_i;
+                        mD = Mu[c];
+                        Mu[c] = __vimin3_s32(cb, eh, ev);
+                        CBu[c] = cb; EVu[c] = ev;
+                        cbL = cb; ehL = eh;
+                    }
+                    // F5: EV at the last column of an even row comes from clobbered predecessors
+                    if (last_block && lane == 31 && !(i & 1)) EVu[C - 1] = POY_INF + ge_i;
+                    dM = lM;
+                    oCB = cbL; oEH = ehL; oM = Mu[C - 1];
+                    if (lane == 31 && !last_block && i <= lasti) bout[i] = make_int4(oCB, oEH, oM, 0);
+                }
+            }
+            if (last_block && lane == 31)                    // lane 31 finished row lasti in the last step
+                cost_out[J.out] = __vimin3_s32(oCB, oEH, EVu[C - 1]);
+            __syncwarp();
+        }
+    }
+}
+
+// ---- one persistent kernel for both kinds of pair ------------------------------------------------------------
+// Jobs sit in ONE list (general pairs first: they are the slower ones), warps pull them with an atomic counter and
+// dispatch on J.gapfree, so the tail of either kind is filled by the other.
+__global__ void __launch_bounds__(128, 4)
+k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const unsigned *__restrict__ rowpk,
+              const int4 *__restrict__ colp, const int *__restrict__ g0v, const CostJob *__restrict__ jobs, int njobs,
+              int *counter, int4 *bound, size_t bound_stride, int *__restrict__ cost_out) {
+    __shared__ int s_tab[16 * GF_TAB_COLS * 32];   // 16 x 17 cost table, every entry replicated once per bank
+    __shared__ int s_cost16[256];                   // plain copy for the tiny-pair emulation
+    for (int x = threadIdx.x; x < 16 * GF_TAB_COLS * 32; x += blockDim.x) {
+        const int e = x >> 5, a = e / GF_TAB_COLS, b = e % GF_TAB_COLS;
+        s_tab[x] = b < 16 ? cm->cost16[a * 16 + b] : POY_INF;
+    }
     for (int x = threadIdx.x; x < 256; x += blockDim.x) s_cost16[x] = cm->cost16[x];
-    for (int x = threadIdx.x; x < 256 * 32; x += blockDim.x) s_rep[x] = cm->cost16[x >> 5];
     __syncthreads();
     const int GO = cm->gap_open;
-    const int njobs = *njobs_ptr;
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int4 *bnd0 = bound + (size_t)warp_global * 2 * bound_stride;
     int4 *bnd1 = bnd0 + bound_stride;
-
     for (;;) {
         int job = 0;
         if (lane == 0) job = atomicAdd(counter, 1);
         job = __shfl_sync(0xffffffffu, job, 0);
         if (job >= njobs) break;
         const CostJob J = jobs[job];
-        const int lasti = J.lasti, lastj = J.lastj;
-        const int4 *rp = rowp + J.off_i;
-        const int4 *cp = colp + J.off_j;
-        const int *g0 = g0v + J.off_j;
-
-        if (lastj + 1 <= TINY_L) {
-            if (lane == 0) cost_out[J.out] = cost_affine_tiny(cm, s_cost16, rp, cp, g0, lasti, lastj);
-            continue;
-        }
-        if (lasti == 0) {  // no rows: minimum over row 0 at the last column (src/algn.c:2105-2109)
-            if (lane == 0) cost_out[J.out] = imin(GO + g0[lastj], POY_INF);
-            continue;
-        }
-
-        const int nb = (lastj + W - 1) / W;
-        const int jres = lastj - 1 - (nb - 1) * W;  // position of column lastj inside the last block
-        const int tl = jres / C, cl = jres % C;
-        for (int b = 0; b < nb; ++b) {
-            const int jb = b * W + lane * C;  // slot c <-> column jb + c + 1
-            const int4 *bin = (b & 1) ? bnd0 : bnd1;
-            int4 *bout = (b & 1) ? bnd1 : bnd0;
-            const bool last_block = (b == nb - 1);
-            const bool owns_last = last_block && lane == tl;
-
-            // per-column constants
-            int c_ext[C], c_opn[C], c_go[C], c_fl[C];
-            // previous-row state of the owned columns
-            int CBu[C], EVu[C], EHu[C], EBu[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const int j = jb + c + 1;
-                if (j <= lastj) {
-                    const int4 v = cp[j];
-                    c_ext[c] = v.x; c_opn[c] = v.y; c_go[c] = v.z;
-                    c_fl[c] = GAPFREE ? ((v.w & 15) << 2) : v.w;
-                    EHu[c] = GO + g0[j];
-                } else {
-                    c_ext[c] = 0; c_opn[c] = 0; c_go[c] = 0; c_fl[c] = 0;
-                    EHu[c] = POY_INF;
-                }
-                CBu[c] = POY_INF; EVu[c] = POY_INF; EBu[c] = POY_INF;
-                if (GAPFREE) EBu[c] = __vimin3_s32(CBu[c], EVu[c], EHu[c]);  // M = min3 of the cell
-            }
-            // cell (i-1, jb): diagonal predecessor of slot 0
-            int dCB, dEV, dEH, dEB;
-            if (jb == 0) { dCB = 0; dEV = GO; dEH = GO; dEB = POY_INF; }
-            else { dCB = POY_INF; dEV = POY_INF; dEH = GO + g0[jb]; dEB = POY_INF; }
-            if (GAPFREE) dEB = __vimin3_s32(dCB, dEV, dEH);
-            int ev_col0 = GO;  // EV[i][0] running sum (lane 0 of block 0), src/algn.c:2066-2070
-            int oCB = POY_INF, oEH = POY_INF, oEV = POY_INF, oEB = POY_INF;
-            int4 rnext = rp[1 <= lasti ? 1 : 0];
-            int4 bnext = make_int4(0, 0, 0, 0);
-            if (b > 0 && lane == 0) bnext = bin[1];
-
-            const int nsteps = lasti + 31;
-            for (int s = 0; s < nsteps; ++s) {
-                const int i = s - lane + 1;
-                int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
-                int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
-                int lEV = GAPFREE ? 0 : __shfl_up_sync(0xffffffffu, oEV, 1);
-                int lEB = __shfl_up_sync(0xffffffffu, oEB, 1);
-                if (i >= 1 && i <= lasti) {
-                    const int4 r = rnext;
-                    if (i < lasti) rnext = rp[i + 1];
-                    if (lane == 0) {
-                        if (b == 0) {
-                            ev_col0 += r.x;
-                            lCB = POY_INF; lEH = POY_INF; lEV = ev_col0;
-                            lEB = GAPFREE ? __vimin3_s32(POY_INF, ev_col0, POY_INF) : POY_INF;
-                        } else {
-                            lCB = bnext.x; lEH = bnext.y; lEV = bnext.z; lEB = bnext.w;
-                            if (i < lasti) bnext = bin[i + 1];
-                        }
-                    }
-                    int cbL = lCB, ehL = lEH;
-                    if (GAPFREE) {
-                        const int *rowbase = s_cost16 + (r.w & 15) * 16;
-                        const int ge_i = r.x;
-                        int mD = dEB;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const int diag = *(const int *)((const char *)rowbase + c_fl[c]);
-                            const int cb = mD + diag;
-                            const int eh = __viaddmin_s32(cbL, GO, ehL) + c_ext[c];
-                            const int ev = __viaddmin_s32(CBu[c], GO, EVu[c]) + ge_i;
-                            mD = EBu[c];
-                            EBu[c] = __vimin3_s32(cb, eh, ev);
-                            CBu[c] = cb; EVu[c] = ev; EHu[c] = eh;
-                            cbL = cb; ehL = eh;
-                        }
-                    } else {
-                        const int *rowbase = s_rep + (r.w & 15) * 512 + lane;
-                        const int vext = r.x, opnV = r.y, go_i = r.z;
-                        const int mask_i = (r.w & PF_HASGAP) ? -1 : 0;
-                        int xCB = dCB, xEV = dEV, xEH = dEH, xEB = dEB;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const int fl = c_fl[c];
-                            const int go_j = c_go[c];
-                            const int eh = __viaddmin_s32(ehL, c_ext[c], cbL + c_opn[c]);
-                            const int ev = __viaddmin_s32(EVu[c], vext, CBu[c] + opnV);
-                            const bool both = (r.w & fl & PF_HASGAP) != 0;
-                            const bool clean = ((r.w | fl) & PF_PREVGAP) == 0;
-                            const int dg = both ? 0 : POY_INF;
-                            const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
-                            const int eb = __viaddmin_s32(xEB, dg, xCB + od);
-                            const int diag = rowbase[(fl & 15) << 5];
-                            const int gv = go_j & mask_i;
-                            const int gh = (fl & PF_HASGAP) ? go_i : 0;
-                            const int xgo = go_j < go_i ? go_i : go_j;
-                            int m = __viaddmin_s32(xEV, gv, xCB);
-                            m = __viaddmin_s32(xEH, gh, m);
-                            m = __viaddmin_s32(xEB, xgo, m);
-                            const int cb = m + diag;
-                            xCB = CBu[c]; xEV = EVu[c]; xEH = EHu[c]; xEB = EBu[c];
-                            CBu[c] = cb; EVu[c] = ev; EHu[c] = eh; EBu[c] = eb;
-                            cbL = cb; ehL = eh;
-                        }
-                    }
-                    // F5: EV at the last column of an even row comes from clobbered predecessors
-                    if (owns_last && !(i & 1)) {
-                        const int pv = POY_INF + imin(r.x, r.y);
-#pragma unroll
-                        for (int c = 0; c < C; ++c)
-                            if (c == cl) {
-                                EVu[c] = pv;
-                                if (GAPFREE) EBu[c] = __vimin3_s32(CBu[c], EHu[c], pv);
-                            }
-                    }
-                    dCB = lCB; dEV = lEV; dEH = lEH; dEB = lEB;
-                    oCB = CBu[C - 1]; oEH = EHu[C - 1]; oEV = EVu[C - 1]; oEB = EBu[C - 1];
-                    if (lane == 31 && !last_block) bout[i] = make_int4(oCB, oEH, oEV, oEB);
-                }
-            }
-            if (owns_last) {
-                int res = 0;
-#pragma unroll
-                for (int c = 0; c < C; ++c)
-                    if (c == cl) {
-                        res = imin(imin(EHu[c], EVu[c]), CBu[c]);
-                        if (!GAPFREE) res = imin(res, EBu[c]);
-                    }
-                cost_out[J.out] = res;
-            }
-            __syncwarp();
-        }
+        if (J.gapfree) cost_pair_gf<16>(s_tab, J, rowpk, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
+        else cost_pair_general<8>(cm, s_tab, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
     }
 }
 
-// Two launches: gap-free jobs with the 3-state kernel, the rest with the 4-state kernel.  The job
-// lists are built on the device (misc.cu: k_build_cost_jobs); d_counts[0..1] hold their lengths.
-cudaError_t launch_cost_affine_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs_free,
-                                     const CostJob *d_jobs_gen, const int *d_counts, int *d_counters, int4 *d_bound,
-                                     size_t bound_stride, int blocks, int *d_cost) {
-    cudaError_t e = launch_cost_gf(ctx, cm, pool, d_jobs_free, d_counts, d_counters, d_bound, bound_stride, blocks, d_cost);
-    if (e != cudaSuccess) return e;
-    k_cost_affine<8, false><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_g0, d_jobs_gen,
-                                                              d_counts + 1, d_counters + 1, d_bound, bound_stride, d_cost);
+cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
+                               int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost) {
+    k_cost_affine<<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
+                                                   d_counter, d_bound, bound_stride, d_cost);
     ctx->launches++;
     return cudaGetLastError();
 }

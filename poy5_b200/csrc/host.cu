@@ -421,19 +421,16 @@ extern "C" poy_status poy_batch_cost_affine_dev(poy_ctx *ctx, const poy_cm *cm, 
     if (s != POY_OK) return s;
     s = ensure_params(ctx, cm, pool);
     if (s != POY_OK) return s;
-    void *jobs_free, *jobs_gen, *misc, *bound;
-    if ((s = scratch(ctx, SL_JOBS, sizeof(CostJob) * (size_t)n, &jobs_free)) != POY_OK) return s;
-    if ((s = scratch(ctx, SL_JOBS2, sizeof(CostJob) * (size_t)n, &jobs_gen)) != POY_OK) return s;
+    void *jobs, *misc, *bound;
+    if ((s = scratch(ctx, SL_JOBS, sizeof(CostJob) * (size_t)n, &jobs)) != POY_OK) return s;
     if ((s = scratch(ctx, SL_MISC, 64, &misc)) != POY_OK) return s;
     const int blocks = ctx->sm_count * 4;
     const size_t bound_stride = (size_t)ml + 2;
     if ((s = scratch(ctx, SL_BOUND, sizeof(int4) * 2 * bound_stride * (size_t)blocks * 4, &bound)) != POY_OK) return s;
     int *counts = (int *)misc;  // [0],[1] = work counters; [2],[3] = job counts
     CK(cudaMemsetAsync(counts, 0, 16, ctx->stream));
-    CK(launch_build_cost_jobs(ctx, pool, n, d_a, d_b, (CostJob *)jobs_free, (CostJob *)jobs_gen, counts + 2));
-    // the job counts stay on the device: both kernels read them there
-    CK(launch_cost_affine_split(ctx, cm, pool, (CostJob *)jobs_free, (CostJob *)jobs_gen, counts + 2, counts, (int4 *)bound,
-                                bound_stride, blocks, d_cost));
+    CK(launch_build_cost_jobs(ctx, pool, n, d_a, d_b, (CostJob *)jobs, counts + 2));
+    CK(launch_cost_affine(ctx, cm, pool, (CostJob *)jobs, n, counts, (int4 *)bound, bound_stride, blocks, d_cost));
     return POY_OK;
 }
 

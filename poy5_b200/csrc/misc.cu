@@ -4,9 +4,10 @@
 
 // ---- cost-only job construction (device side, so pair lists may stay resident in HBM) -----------
 // Rows are the shorter sequence (algn_CAML_cost_affine_3 swaps internally, src/algn.c:2496-2513).
+// One list: general (4-state) pairs are appended from the front, gap-free pairs from the back, so the slower
+// general pairs are started first and the gap-free ones fill the tail.
 __global__ void k_build_cost_jobs(const int64_t *__restrict__ off, const uint8_t *__restrict__ gapfree, int n,
-                                  const int *__restrict__ a, const int *__restrict__ b, CostJob *jfree, CostJob *jgen,
-                                  int *counts) {
+                                  const int *__restrict__ a, const int *__restrict__ b, CostJob *jobs, int *counts) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int sa = a[p], sb = b[p];
@@ -18,13 +19,13 @@ __global__ void k_build_cost_jobs(const int64_t *__restrict__ off, const uint8_t
     j.out = p;
     // tiny pairs take the exact flat-layout emulation inside the general kernel (cost_affine.cu, TINY_L)
     j.gapfree = gapfree[sa] && gapfree[sb] && (j.lastj + 1 > 8);
-    if (j.gapfree) jfree[atomicAdd(counts, 1)] = j;
-    else jgen[atomicAdd(counts + 1, 1)] = j;
+    if (j.gapfree) jobs[n - 1 - atomicAdd(counts, 1)] = j;
+    else jobs[atomicAdd(counts + 1, 1)] = j;
 }
 
 cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, const int *d_a, const int *d_b,
-                                   CostJob *d_free, CostJob *d_gen, int *d_counts) {
-    k_build_cost_jobs<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pool->d_off, pool->d_gapfree, n, d_a, d_b, d_free, d_gen, d_counts);
+                                   CostJob *d_jobs, int *d_counts) {
+    k_build_cost_jobs<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pool->d_off, pool->d_gapfree, n, d_a, d_b, d_jobs, d_counts);
     ctx->launches++;
     return cudaGetLastError();
 }
