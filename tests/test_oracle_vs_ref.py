@@ -46,3 +46,53 @@ def test_witnesses(reflib, port):
     a, b = w["R3"]
     assert reflib.cost_affine(rc, a, b) == port.cost_affine(pc, a, b) == 5
     assert reflib.align_affine(rc, a, b)[0] == port.align_affine(pc, a, b)[0] == 4
+
+
+@pytest.mark.parametrize("tcm", [(1, 1), (2, 1), (1, 2), (3, 2)])
+def test_linear_and_helpers(reflib, port, tcm):
+    """linear-gap align_2d (full plane and Ukkonen band) + column-wise helpers vs the compiled reference"""
+    rng = np.random.default_rng(tcm[0] * 7 + tcm[1])
+    for m in cmo.dna_matrices(tcm[0], tcm[1], None):
+        rc, pc = reflib.cm(m), port.cm(m)
+        modes = [0, 0]
+        for it in range(400):
+            L = int(rng.integers(0, 140)) if it % 5 else int(rng.integers(0, 12))
+            anc = synth.random_seq(rng, L)
+            a, b = synth.evolve(rng, anc, 0.15, 0.05), synth.evolve(rng, anc, 0.15, 0.05)
+            if it % 3 == 0:
+                a, b = synth.decorate(rng, a, 0.1, 0.1), synth.decorate(rng, b, 0.1, 0.1)
+            if it % 7 == 0:
+                b = synth.random_seq(rng, int(rng.integers(0, 200)))
+            a, b = synth.with_gap(a), synth.with_gap(b)
+            s1, s2 = (a, b) if len(a) <= len(b) else (b, a)
+            dw, sw = int(rng.integers(0, 30)), int(rng.integers(0, 2))
+            r1 = reflib.align_linear(rc, s1, s2, dw, sw)
+            c2, st = port.cost_linear(pc, s1, s2, dw, with_stats=True)
+            r2 = port.align_linear(pc, s1, s2, dw, sw)
+            modes[1 if st.iterations > 0 else 0] += 1
+            assert r1[0] == r2[0] == c2 and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+            x, y = r1[1], r1[2]
+            for wg in (0, 1):
+                assert np.array_equal(reflib.median_2(rc, x, y, wg), port.median_2(pc, x, y, wg))
+            assert np.array_equal(reflib.union(x, y), port.union(x, y))
+            assert reflib.worst_2(rc, x, y) == port.worst_2(pc, x, y) and reflib.verify_2(rc, x, y) == port.verify_2(pc, x, y)
+            assert np.array_equal(reflib.ancestor_2(rc, x, y), port.ancestor_2(pc, x, y))
+        assert modes[0] > 20 and modes[1] > 20   # both the full plane and the Ukkonen band were exercised
+
+
+def test_affine_helpers(reflib, port):
+    rng = np.random.default_rng(4)
+    for reg in ((1, 1, 3), (2, 1, 5), (1, 2, 0)):
+        m = cmo.dna_matrices(*reg)[0]
+        rc, pc = reflib.cm(m), port.cm(m)
+        for it in range(200):
+            anc = synth.random_seq(rng, int(rng.integers(0, 80)))
+            a = synth.with_gap(synth.decorate(rng, synth.evolve(rng, anc, 0.15, 0.06), 0.1, 0.1))
+            b = synth.with_gap(synth.decorate(rng, synth.evolve(rng, anc, 0.15, 0.06), 0.1, 0.1))
+            si, sj = (a, b) if len(a) <= len(b) else (b, a)
+            r = reflib.align_affine(rc, si, sj, 0)
+            x, y = r[3], r[4]
+            assert reflib.worst_2(rc, x, y) == port.worst_2(pc, x, y) and reflib.verify_2(rc, x, y) == port.verify_2(pc, x, y)
+            assert np.array_equal(reflib.ancestor_2(rc, x, y), port.ancestor_2(pc, x, y))
+            for wg in (0, 1):
+                assert np.array_equal(reflib.median_2(rc, x, y, wg), port.median_2(pc, x, y, wg))
