@@ -152,7 +152,7 @@ __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed)
 
 // NW warps cooperate on one pair.  NW == 1: a CTA holds WPB independent warps (each with its own
 // pair) that only share the replicated cost table.
-template <int D, int NW, bool GF, int WPB>
+template <int D, int NW, int WPB>
 __global__ void __launch_bounds__(WPB * 32)
 k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
         const int *__restrict__ h0v, const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state,
@@ -184,9 +184,12 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         }
         if (job >= njobs) break;
         const BandJob J = jobs[job];
+        if (J.lasti == 0) continue;
+        // both kinds of pair run in the same launch: gap-free pairs (J.swaped bit 2) take the 3-state code path
+        auto run = [&](auto gf_c) {
+        constexpr bool GF = decltype(gf_c)::value;
         const int lasti = J.lasti, lastj = J.lastj, k = J.k;
-        const bool swaped = J.swaped != 0;
-        if (lasti == 0) continue;
+        const bool swaped = (J.swaped & 1) != 0;
         const int delta = lastj - lasti, B = delta + 2 * k + 1;
         const int4 *rp = rowp + J.off_i;
         const int4 *cp = colp + J.off_j;
@@ -343,6 +346,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             });
         }
         if (tid == 0 && min(k, lasti) >= 2) st->eh00 = POY_INF;  // an even row wrote EH[.][0] = INF into row buffer 0
+        };
+        if (J.swaped & 4) run(std::true_type{}); else run(std::false_type{});
     }
 }
 
@@ -356,12 +361,9 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
     int blocks = (njobs + groups_per_block - 1) / groups_per_block;
     const int cap = ctx->sm_count * 6;   // more CTAs than can be resident just queue behind the persistent ones
     if (blocks > cap) blocks = cap;
-    if (gapfree)
-        k_band2<D, NW, true, WPB><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
-                                                                         d_counter, d_state, d_ebrow, d_dir);
-    else
-        k_band2<D, NW, false, WPB><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
-                                                                          d_counter, d_state, d_ebrow, d_dir);
+    (void)gapfree;
+    k_band2<D, NW, WPB><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
+                                                              d_counter, d_state, d_ebrow, d_dir);
     ctx->launches++;
     return cudaGetLastError();
 }

@@ -8,8 +8,9 @@
 // a "left border" (EH = INF), the cell j = i+delta+k a "right border" (EV = INF).
 // In diagonal coordinates d = j - i + k the band is d in [0, B), B = delta + 2k + 1.
 //
-// Parallelisation: one WARP per pair, anti-diagonal wavefront.  Lane t owns the D
-// consecutive diagonals [t*D, (t+1)*D) and keeps, per diagonal, only the state of the
+// Parallelisation (register-resident kernels: band2.cu; this file keeps the reference-shaped
+// cell, the generic any-width fallback and the traceback): anti-diagonal wavefront.  Thread t
+// owns D consecutive diagonals [t*D, (t+1)*D) and keeps, per diagonal, only the state of the
 // LATEST cell on it (CB, EV, EH, EB and the two gap counters) in registers.  Cells of
 // one anti-diagonal a = i + j all have d = a + k (mod 2), so a step updates every
 // other diagonal in place: the left neighbour (i, j-1) is the latest cell of diagonal
@@ -122,137 +123,6 @@ __device__ __forceinline__ void band_cell(const CellIn &in, const int4 r, const 
     o.CB = CB; o.EV = EV; o.EH = EH; o.EB = EB; o.fin = fin;
 }
 
-// ---- warp-per-pair register-resident band fill ------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(128)
-k_band_fill(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
-            const int *__restrict__ h0v, const BandJob *__restrict__ jobs, int njobs, int *counter,
-            PairState *state, int *ebrow, uint8_t *dir) {
-    constexpr int H = D / 2;  // cells per lane per sub-step
-    __shared__ int s_cost16[256];
-    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_cost16[x] = cm->cost16[x];
-    __syncthreads();
-    const int GO = cm->gap_open;
-    const int lane = threadIdx.x & 31;
-
-    for (;;) {
-        int job = 0;
-        if (lane == 0) job = atomicAdd(counter, 1);
-        job = __shfl_sync(0xffffffffu, job, 0);
-        if (job >= njobs) break;
-        const BandJob J = jobs[job];
-        const int lasti = J.lasti, lastj = J.lastj, k = J.k, swaped = J.swaped;
-        if (lasti == 0) continue;  // no rows: nothing to fill (k_band_finish supplies the cost)
-        const int delta = lastj - lasti, B = delta + 2 * k + 1;
-        const int4 *rp = rowp + J.off_i;
-        const int4 *cp = colp + J.off_j;
-        const int *h0 = h0v + J.off_j;
-        int *eb = ebrow + J.eb_off;
-        PairState *st = state + J.pair;
-        uint8_t *dbase = dir + J.dir_off;
-        const int stride = J.stride;
-        const int d0 = lane * D;
-        const int eh00 = st->eh00;
-
-        int CB[D], EV[D], EH[D], EB[D], G1[D], G2[D];
-        static_for<D>([&](auto uc) {
-            constexpr int u = decltype(uc)::value;
-            const int d = d0 + u, j0 = d - k;
-            if (d < B && j0 >= 0 && j0 <= lastj) {  // row 0 as set up by the band fill (src/algn.c:2222-2247, A1)
-                CB[u] = h0[j0];
-                EH[u] = j0 == 0 ? eh00 : h0[j0];
-                EV[u] = POY_INF;
-                EB[u] = eb[j0];
-                G1[u] = j0 & 0xFFFF; G2[u] = 0;
-            } else {
-                CB[u] = EV[u] = EH[u] = EB[u] = POY_INF; G1[u] = G2[u] = 0;
-            }
-        });
-        __syncwarp();
-
-        const int a_end = lasti + lastj;
-        for (int a = (k & 1); a <= a_end; a += 2) {
-            // ---- even diagonals: anti-diagonal a; left neighbour of slot 0 comes from lane-1 ----
-            {
-                int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
-                int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
-                int sG1 = __shfl_up_sync(0xffffffffu, G1[D - 1], 1);
-                int sG2 = __shfl_up_sync(0xffffffffu, G2[D - 1], 1);
-                unsigned long long packed = 0;
-                static_for<H>([&](auto hc) {
-                    constexpr int h = decltype(hc)::value;
-                    constexpr int u = 2 * h;
-                    const int d = d0 + u;
-                    const int i = (a - d + k) >> 1, j = a - i;
-                    if (d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) {
-                        CellIn in;
-                        if constexpr (u == 0) { in.lCB = sCB; in.lEH = sEH; in.lG1 = sG1; in.lG2 = sG2; }
-                        else { constexpr int ul = u > 0 ? u - 1 : 0; in.lCB = CB[ul]; in.lEH = EH[ul]; in.lG1 = G1[ul]; in.lG2 = G2[ul]; }
-                        in.uCB = CB[u + 1]; in.uEV = EV[u + 1]; in.uG1 = G1[u + 1]; in.uG2 = G2[u + 1];
-                        in.dCB = CB[u]; in.dEV = EV[u]; in.dEH = EH[u]; in.dEB = EB[u]; in.dG1 = G1[u]; in.dG2 = G2[u];
-                        CellOut o;
-                        band_cell(in, rp[i], cp[j], s_cost16, GO, d == 0 || j == 0, d == B - 1, j > 0, swaped, o);
-                        CB[u] = o.CB; EV[u] = o.EV; EH[u] = o.EH; EB[u] = o.EB; G1[u] = o.G1; G2[u] = o.G2;
-                        packed |= (unsigned long long)o.dirbyte << (8 * h);
-                        if (!(i & 1) && (d <= 1 || i >= lasti - 1)) eb[j] = o.EB;
-                    }
-                });
-                if (a >= 1) {
-                    uint8_t *p = dbase + (size_t)a * stride + lane * H;
-                    if (H == 1) *p = (uint8_t)packed;
-                    else if (H == 2) *(uint16_t *)p = (uint16_t)packed;
-                    else if (H == 4) *(uint32_t *)p = (uint32_t)packed;
-                    else *(unsigned long long *)p = packed;
-                }
-            }
-            // ---- odd diagonals: anti-diagonal a+1; upper neighbour of slot D-1 comes from lane+1 ----
-            if (a + 1 <= a_end) {
-                int sCB = __shfl_down_sync(0xffffffffu, CB[0], 1);
-                int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
-                int sG1 = __shfl_down_sync(0xffffffffu, G1[0], 1);
-                int sG2 = __shfl_down_sync(0xffffffffu, G2[0], 1);
-                unsigned long long packed = 0;
-                static_for<H>([&](auto hc) {
-                    constexpr int h = decltype(hc)::value;
-                    constexpr int u = 2 * h + 1;
-                    const int d = d0 + u;
-                    const int i = (a + 1 - d + k) >> 1, j = a + 1 - i;
-                    if (d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) {
-                        CellIn in;
-                        in.lCB = CB[u - 1]; in.lEH = EH[u - 1]; in.lG1 = G1[u - 1]; in.lG2 = G2[u - 1];
-                        if constexpr (u == D - 1) { in.uCB = sCB; in.uEV = sEV; in.uG1 = sG1; in.uG2 = sG2; }
-                        else { constexpr int uu = u < D - 1 ? u + 1 : u; in.uCB = CB[uu]; in.uEV = EV[uu]; in.uG1 = G1[uu]; in.uG2 = G2[uu]; }
-                        in.dCB = CB[u]; in.dEV = EV[u]; in.dEH = EH[u]; in.dEB = EB[u]; in.dG1 = G1[u]; in.dG2 = G2[u];
-                        CellOut o;
-                        band_cell(in, rp[i], cp[j], s_cost16, GO, j == 0, d == B - 1, j > 0, swaped, o);
-                        CB[u] = o.CB; EV[u] = o.EV; EH[u] = o.EH; EB[u] = o.EB; G1[u] = o.G1; G2[u] = o.G2;
-                        packed |= (unsigned long long)o.dirbyte << (8 * h);
-                        if (!(i & 1) && (d <= 1 || i >= lasti - 1)) eb[j] = o.EB;
-                    }
-                });
-                uint8_t *p = dbase + (size_t)(a + 1) * stride + lane * H;
-                if (H == 1) *p = (uint8_t)packed;
-                else if (H == 2) *(uint16_t *)p = (uint16_t)packed;
-                else if (H == 4) *(uint32_t *)p = (uint32_t)packed;
-                else *(unsigned long long *)p = packed;
-            }
-        }
-        // result: the cell (lasti, lastj) is the latest cell of diagonal delta + k
-        const int dstar = delta + k;
-        if (lane == dstar / D) {
-            static_for<D>([&](auto uc) {
-                constexpr int u = decltype(uc)::value;
-                if (u == dstar % D) {
-                    st->cost = imin_(imin_(EH[u], EV[u]), imin_(EB[u], CB[u]));
-                    st->gapnum = imax_(G1[u], G2[u]);
-                }
-            });
-        }
-        if (lane == 0 && imin_(k, lasti) >= 2) st->eh00 = POY_INF;  // an even row wrote EH[.][0] = INF into row buffer 0
-        __syncwarp();
-    }
-}
-
 // ---- generic fallback: one CTA per pair, diagonal state in global memory -------------------
 // Used for bands wider than the register-resident kernel covers (very dissimilar pairs).
 // work layout per job: 6 planes of `wstride` ints (CB, EV, EH, EB, G1, G2).
@@ -266,7 +136,7 @@ k_band_generic(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, cons
     const int GO = cm->gap_open;
     for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
         const BandJob J = jobs[job];
-        const int lasti = J.lasti, lastj = J.lastj, k = J.k, swaped = J.swaped;
+        const int lasti = J.lasti, lastj = J.lastj, k = J.k, swaped = J.swaped & 1;
         if (lasti == 0) continue;
         const int delta = lastj - lasti, B = delta + 2 * k + 1;
         const int4 *rp = rowp + J.off_i;
@@ -434,28 +304,6 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
 #undef PUT
 #undef PUT_M
 #undef INDEL
-}
-
-cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
-                             int dclass, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
-    if (njobs <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
-    if (e != cudaSuccess) return e;
-    int blocks = (njobs + 3) / 4;
-    const int maxb = ctx->sm_count * 4;
-    if (blocks > maxb) blocks = maxb;
-#define LAUNCH_BAND(DD) k_band_fill<DD><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, \
-                                        d_jobs, njobs, d_counter, d_state, d_ebrow, d_dir)
-    switch (dclass) {
-        case 2: LAUNCH_BAND(2); break;
-        case 4: LAUNCH_BAND(4); break;
-        case 8: LAUNCH_BAND(8); break;
-        case 16: LAUNCH_BAND(16); break;
-        default: return cudaErrorInvalidValue;
-    }
-#undef LAUNCH_BAND
-    ctx->launches++;
-    return cudaGetLastError();
 }
 
 cudaError_t launch_band_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,

@@ -70,6 +70,10 @@ struct poy_ctx {
     size_t scratch_cap[8];
     void *h_pinned[4];
     size_t pinned_cap[4];
+    // auxiliary streams + events: independent launches of one wave run concurrently so that the tail of one
+    // overlaps the body of the next
+    cudaStream_t aux[4];
+    cudaEvent_t ev_fork, ev_join[4];
 };
 
 // ---- work descriptors ----------------------------------------------------------------
@@ -107,8 +111,6 @@ cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, co
                                    CostJob *d_jobs, int *d_counts);
 cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
                                int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost);
-cudaError_t launch_band_fill(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
-                             int dclass, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
                          bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 int band2_class_for(long long B);

@@ -54,6 +54,11 @@ extern "C" poy_status poy_ctx_create(int device, void *stream, poy_ctx **out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return POY_ERR_CUDA; }
         ctx->owns_stream = true;
     }
+    for (int a = 0; a < 4; ++a) {
+        cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     {   // direction arena: up to 40% of the free HBM, at most 64 GiB
         size_t fr = 0, tot = 0;
         ctx->arena_limit = 8ull << 30;
@@ -73,6 +78,8 @@ extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int s = 0; s < 8; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
     for (int s = 0; s < 4; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
+    for (int a = 0; a < 4; ++a) { cudaStreamDestroy(ctx->aux[a]); cudaEventDestroy(ctx->ev_join[a]); }
+    cudaEventDestroy(ctx->ev_fork);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -527,7 +534,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     if ((s = scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
     if ((s = scratch(ctx, SL_EBROW, sizeof(int) * (size_t)eb_total, &v_eb)) != POY_OK) return s;
     if ((s = scratch(ctx, SL_JOBS, sizeof(BandJob) * (size_t)n, &v_jobs)) != POY_OK) return s;
-    if ((s = scratch(ctx, SL_MISC, 64, &v_misc)) != POY_OK) return s;
+    if ((s = scratch(ctx, SL_MISC, 256, &v_misc)) != POY_OK) return s;
     if ((s = pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (size_t)n, &v_pin)) != POY_OK) return s;
     if ((s = pinned(ctx, 1, (size_t)n + sizeof(int32_t) * (size_t)n, &v_pin2)) != POY_OK) return s;
     PairState *d_state = (PairState *)v_state;
@@ -572,7 +579,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         order = active;
         std::sort(order.begin(), order.end(), [&](int x, int y) {
             if (hp[x].dclass != hp[y].dclass) return hp[x].dclass > hp[y].dclass;
-            if (hp[x].gapfree != hp[y].gapfree) return hp[x].gapfree > hp[y].gapfree;
+            if (hp[x].gapfree != hp[y].gapfree) return hp[x].gapfree < hp[y].gapfree;   // slower 4-state pairs first
             if (hp[x].dir_bytes != hp[y].dir_bytes) return hp[x].dir_bytes > hp[y].dir_bytes;
             return x < y;
         });
@@ -599,31 +606,51 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 const HostPair &h = hp[p];
                 BandJob &j = hj[q];
                 j.off_i = h.off_i; j.off_j = h.off_j; j.lasti = h.lasti; j.lastj = h.lastj; j.k = h.k; j.pair = p;
-                j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0);
+                j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0) | ((!linear && h.gapfree) ? 4 : 0);
                 j.stride = h.stride; j.dir_off = doff; j.eb_off = h.eb_off;
                 doff += (h.dir_bytes + 255) & ~255ll;
                 if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
             }
             CK(cudaMemcpyAsync(d_jobs, hj, sizeof(BandJob) * (size_t)nj, cudaMemcpyHostToDevice, ctx->stream));
-            // launch per (class, gap-free) group (contiguous after the sort); each launch gets its own work counter
+            // launch per band class (contiguous after the sort).  The launches of a wave are independent: they go to
+            // round-robin auxiliary streams (fork / join with events) and each gets its own work counter.
             int q0 = 0, nlaunch = 0;
+            cudaStream_t main_stream = ctx->stream;
+            CK(cudaEventRecord(ctx->ev_fork, main_stream));
+            unsigned used_aux = 0;
             while (q0 < nj) {
+                const int ax = nlaunch & 3;
+                ctx->stream = ctx->aux[ax];
+                if (!(used_aux & (1u << ax))) { cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0); used_aux |= 1u << ax; }
                 const int cls = hp[order[pos + q0]].dclass, gf = hp[order[pos + q0]].gapfree;
                 int q1 = q0;
-                while (q1 < nj && hp[order[pos + q1]].dclass == cls && hp[order[pos + q1]].gapfree == gf) ++q1;
+                while (q1 < nj && hp[order[pos + q1]].dclass == cls) ++q1;
                 if (cls != 0) {
-                    if (linear) CK(launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch++ & 7), d_state, d_dir));
-                    else CK(launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, d_counter + (nlaunch++ & 7), d_state, d_eb, d_dir));
+                    cudaError_t le;
+                    if (linear) le = launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch & 15), d_state, d_dir);
+                    else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir);
+                    if (le != cudaSuccess) { ctx->stream = main_stream; return cuda_fail(ctx, le, "band fill launch"); }
                 } else {
                     void *v_work;
                     const size_t wstride = 6 * (size_t)((gen_width + 31) & ~31ll);
                     const int blocks = std::min(gen_blocks, q1 - q0);
+                    ctx->stream = main_stream;
                     if ((s = scratch(ctx, SL_WORK, sizeof(int) * wstride * (size_t)blocks, &v_work)) != POY_OK) return s;
-                    if (linear) CK(launch_band_lin_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_dir, (int *)v_work, wstride, blocks));
-                    else CK(launch_band_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_eb, d_dir, (int *)v_work, wstride, blocks));
+                    ctx->stream = ctx->aux[ax];
+                    cudaError_t le;
+                    if (linear) le = launch_band_lin_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_dir, (int *)v_work, wstride, blocks);
+                    else le = launch_band_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_eb, d_dir, (int *)v_work, wstride, blocks);
+                    if (le != cudaSuccess) { ctx->stream = main_stream; return cuda_fail(ctx, le, "generic band fill launch"); }
                 }
+                ++nlaunch;
                 q0 = q1;
             }
+            ctx->stream = main_stream;
+            for (int ax = 0; ax < 4; ++ax)
+                if (used_aux & (1u << ax)) {
+                    CK(cudaEventRecord(ctx->ev_join[ax], ctx->aux[ax]));
+                    CK(cudaStreamWaitEvent(main_stream, ctx->ev_join[ax], 0));
+                }
             // stop rule on the device, then traceback of the pairs that stopped (others return immediately)
             if (linear) CK(launch_lin_finish(ctx, pool, d_jobs, nj, d_state, d_done));
             else CK(launch_band_finish(ctx, d_jobs, nj, d_state, d_done, pool->d_g0, cm->h.gap_open));
