@@ -49,6 +49,16 @@ def parse():
     return ap.parse_args()
 
 
+def make_config(pairs, lengths, world, total_bytes=None):
+    cfg = dict(workload="configs[1]: batched pairwise affine alignment sweep, %d pairs per length per GPU, lengths %s bp, "
+                        "Ukkonen band off (cost-only) and on (align+traceback+median), 1 GPU per rank" % (pairs, list(lengths)),
+               regime="subst %d indel %d gap_open %d" % REGIME,
+               l2="inputs larger than L2 (%.1f GB of sequences per step)" % ((total_bytes or sum(2.0 * pairs * (L + 1) for L in lengths)) / 1e9),
+               pairs_per_length=pairs, lengths=list(lengths),
+               parallelism="pairs sharded over %d GPU(s), NCCL min-reduce of candidate costs" % world)
+    return cfg
+
+
 # ---------------------------------------------------------------------------------------------
 def chunks_for(npairs, length, chunk_bases):
     """equal-sized batches of at most chunk_bases sequence bytes"""
@@ -82,12 +92,13 @@ def cpu_reference(lengths, threads, budget_core_s=24.0, seed=SEED):
         lib = Port()
         cm = lib.cm(full)
         kind = "port"
-    # per-length sample sized from the probe rates: ~0.17 GCUPS/core cost-only
-    share = budget_core_s / (2 * len(lengths))
+    # Bounded sample with the SAME proportions as the GPU workload (equal pair counts per length, so the longest
+    # length dominates the cells exactly as it does there): n pairs per length, n a multiple of the thread count,
+    # sized from the probe rate of SURVEY.md section 6 (~0.17 GCUPS/core).
+    per_pair_core_s = 2.0 * sum(float(L) * L for L in lengths) / 0.17e9
+    n = max(1, int(round(budget_core_s / (threads * per_pair_core_s)))) * threads
     cells_tot, secs_tot, aln_tot, sample = 0, 0.0, 0, []
     for L in lengths:
-        n = int(max(threads, min(20000, share * 0.17e9 / (L * L))))
-        n = (n + threads - 1) // threads * threads
         data, off = synth.pair_pool(seed + L, 0, n, L)
         lens = np.diff(off).astype(np.int32)
         la, lb = lens[0::2], lens[1::2]
@@ -171,8 +182,8 @@ def main():
         line = dict(metric=METRIC, value=val, unit="GCUPS", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=1e3 * float(np.mean([x["seconds"] for x in steps])), higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="int32", data="synthetic", impl="reference",
-                    config=dict(workload="batched pairwise affine alignment sweep, lengths %s, band off + band on; each step a bounded CPU sample" % (list(lengths),),
-                                regime="subst %d indel %d gap_open %d" % REGIME),
+                    config=dict(make_config(args.pairs, lengths, max(1, args.gpus)),
+                                reference_arm="POY5 algn.c on the host cores; each step is a bounded sample of this workload: " + r["sample"]),
                     cpu_baseline=dict(value=val, unit="GCUPS", cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                     alignments_per_s=r["alignments_per_s"],
                     e2e=dict(value=val, unit="GCUPS", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -371,10 +382,7 @@ def main():
         line = dict(metric=METRIC, value=world * total_cells / (ms * 1e-3) / 1e9, unit="GCUPS", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="int32", data="synthetic",
-                    config=dict(workload="configs[1]: batched pairwise affine alignment sweep, %d pairs per length per GPU, lengths %s bp, "
-                                         "Ukkonen band off (cost-only) and on (align+traceback+median), 1 GPU per rank" % (args.pairs, list(lengths)),
-                                regime="subst %d indel %d gap_open %d" % REGIME, l2="inputs larger than L2 (%.1f GB of sequences per step)" % (sum(w["data"].nbytes for w in work) / 1e9),
-                                pairs_per_length=args.pairs, lengths=list(lengths), parallelism="pairs sharded over %d GPU(s), NCCL min-reduce of candidate costs" % world),
+                    config=make_config(args.pairs, lengths, world, sum(w["data"].nbytes for w in work)),
                     alignments_per_s=world * total_aln / (ms * 1e-3), breakdown=breakdown, clocks=clocks, e2e=e2e,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
         print(json.dumps(line))

@@ -1,0 +1,284 @@
+"""Tree-level driver for the candidate-list seam: Wagner build and one TBR round over
+dynamic-homology sequence characters, written so that EVERY alignment is issued in large batches:
+
+* all-direction medians (the three directional medians per node of ``AllDirNode``) are computed level by
+  level, one ``DOS.median`` batch per level (the downpass / join path, src/allDirChar.ml:2033-2125);
+* candidate evaluation is the Parmap seam of src/ptree.ml:1226-1268 (Wagner) and :1356-1453 (SPR/TBR):
+  collect every (clade median, edge median) pair of every break / reroot / join edge, ONE
+  ``DOS.distance`` batch (cost-only alignments under c2_original, src/allDirChar.ml:2132-2177), then a MIN
+  reduction (over ranks too when the batch is sharded, see shard.py).
+
+This is a workload driver, not a re-implementation of POY's search managers: acceptance rules, tabu lists and
+lazy edges are out of scope.  The algorithms only talk to a *backend* with two methods
+
+    median(pairs)   -> [(median_sequence, cost2), ...]      (SeqCS.DOS.median semantics)
+    distance(pairs) -> [cost, ...]                           (SeqCS.DOS.distance semantics)
+
+``GpuBackend`` below is the product path; tests replay the identical call sequence through an oracle-backed
+implementation of the same interface and compare tree costs bit for bit."""
+import numpy as np
+
+
+class GpuBackend:
+    """Batches go through libpoy5b200.so (seqcs.DOS.median / DOS.distance)."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+        self.n_median = self.n_distance = 0
+        self.cells_distance = 0
+
+    def _pool(self, pairs):
+        from .api import Pool
+        ids, seqs, ia, ib = {}, [], [], []
+        for a, b in pairs:
+            for s, out in ((a, ia), (b, ib)):
+                k = id(s)
+                if k not in ids:
+                    ids[k] = len(seqs); seqs.append(s)
+                out.append(ids[k])
+        return Pool(self.ctx, seqs), np.asarray(ia, np.int32), np.asarray(ib, np.int32)
+
+    def median(self, pairs):
+        from .seqcs import DOS
+        if not pairs:
+            return []
+        pool, ia, ib = self._pool(pairs)
+        r = DOS.median(self.ctx, self.h, pool, ia, ib)
+        pool.close()
+        self.n_median += len(pairs)
+        return [(np.array(r["sequence"][p], np.uint8), int(r["cost2"][p])) for p in range(len(pairs))]
+
+    def distance(self, pairs):
+        from .seqcs import DOS
+        if not pairs:
+            return []
+        pool, ia, ib = self._pool(pairs)
+        d = DOS.distance(self.ctx, self.h, pool, ia, ib, missing_distance=0)
+        self.cells_distance += int(((pool.lens[ia] - 1) * (pool.lens[ib] - 1)).sum())
+        pool.close()
+        self.n_distance += len(pairs)
+        return [int(x) for x in d]
+
+
+class Tree:
+    """Unrooted binary tree: leaves 0..n-1 hold observed sequences, internal nodes are created on insertion."""
+
+    def __init__(self):
+        self.adj = {}
+
+    def copy(self):
+        t = Tree()
+        t.adj = {u: list(vs) for u, vs in self.adj.items()}
+        return t
+
+    def add_edge(self, u, v):
+        self.adj.setdefault(u, []).append(v)
+        self.adj.setdefault(v, []).append(u)
+
+    def remove_edge(self, u, v):
+        self.adj[u].remove(v); self.adj[v].remove(u)
+
+    def edges(self):
+        return sorted((u, v) for u in self.adj for v in self.adj[u] if u < v)
+
+    def new_node(self):
+        return max(self.adj) + 1
+
+    def insert_leaf(self, leaf, edge):
+        """split `edge` with a new internal node and hang `leaf` on it"""
+        u, v = edge
+        w = self.new_node()
+        self.remove_edge(u, v)
+        self.add_edge(u, w); self.add_edge(w, v); self.add_edge(w, leaf)
+        return w
+
+    def component(self, start, banned):
+        seen, stack = {start}, [start]
+        while stack:
+            x = stack.pop()
+            for y in self.adj[x]:
+                if y != banned and y not in seen:
+                    seen.add(y); stack.append(y)
+        return seen
+
+
+def directional_medians(tree, leaf_seq, backend, nodes=None):
+    """dm[(u, v)] = (median, accumulated cost) of the subtree that contains u once edge (u, v) is cut, seen from
+    u.  Level-synchronous: every round issues ONE median batch with all directed edges whose two inputs are
+    ready (AllDirNode's three lazy medians per node, evaluated eagerly and in bulk)."""
+    nodes = set(tree.adj) if nodes is None else nodes
+    dm = {}
+    pending = []
+    for u in nodes:
+        for v in tree.adj[u]:
+            if v not in nodes:
+                continue
+            others = [w for w in tree.adj[u] if w != v and w in nodes]
+            if len(others) == 0:
+                dm[(u, v)] = (leaf_seq[u], 0)
+            elif len(others) == 1:              # a degree-2 node left behind by a break: pass the clade through
+                pending.append((u, v, others))
+            else:
+                pending.append((u, v, others))
+    while pending:
+        ready, rest = [], []
+        for u, v, others in pending:
+            (ready if all((w, u) in dm for w in others) else rest).append((u, v, others))
+        if not ready:
+            raise RuntimeError("cyclic dependency in directional medians")
+        batch = [(u, v, others) for u, v, others in ready if len(others) == 2]
+        res = backend.median([(dm[(o[0], u)][0], dm[(o[1], u)][0]) for u, v, o in batch])
+        for (u, v, o), (seq, c2) in zip(batch, res):
+            dm[(u, v)] = (seq, c2 + dm[(o[0], u)][1] + dm[(o[1], u)][1])
+        for u, v, o in ready:
+            if len(o) == 1:
+                dm[(u, v)] = dm[(o[0], u)]
+        pending = rest
+    return dm
+
+
+def edge_medians(tree, dm, backend, edges=None):
+    """median + total cost for every edge taken as the root: the data `cost_fn` compares a clade against"""
+    edges = tree.edges() if edges is None else edges
+    res = backend.median([(dm[(u, v)][0], dm[(v, u)][0]) for u, v in edges])
+    return {e: (seq, c2 + dm[(e[0], e[1])][1] + dm[(e[1], e[0])][1]) for e, (seq, c2) in zip(edges, res)}
+
+
+def tree_cost(tree, leaf_seq, backend):
+    """cost of the tree rooted on its first edge (sum of cost2 over the downpass + the root median)"""
+    dm = directional_medians(tree, leaf_seq, backend)
+    e = tree.edges()[0]
+    return edge_medians(tree, dm, backend, [e])[e][1]
+
+
+def wagner_build(leaf_seq, backend, order=None):
+    """sequential-addition build (src/ptree.ml:1144-1270): for every new taxon ONE distance batch over all edges"""
+    n = len(leaf_seq)
+    order = list(range(n)) if order is None else list(order)
+    tree = Tree()
+    tree.add_edge(order[0], order[1])
+    seqs = dict(enumerate(leaf_seq))
+    for t in order[2:]:
+        dm = directional_medians(tree, seqs, backend)
+        em = edge_medians(tree, dm, backend)
+        edges = tree.edges()
+        d = backend.distance([(leaf_seq[t], em[e][0]) for e in edges])
+        best = int(np.argmin(d))                    # ties: first edge in sorted order
+        w = max(max(tree.adj) + 1, n)
+        u, v = edges[best]
+        tree.remove_edge(u, v)
+        tree.add_edge(u, w); tree.add_edge(w, v); tree.add_edge(w, t)
+    return tree
+
+
+def tbr_round(tree, leaf_seq, backend, reduce_best=None):
+    """One TBR neighbourhood, evaluated speculatively for ALL break edges at once (multi-break
+    batching).  For each break: all-direction medians inside the two components, then every
+    (reroot edge of the pruned clade) x (join edge of the rest) pair goes into one global distance batch.
+    Returns (best_estimate, move, n_candidates); move = (break_edge, clade_edge, join_edge) or None."""
+    seqs = dict(enumerate(leaf_seq))
+    breaks = []
+    for (u, v) in tree.edges():
+        t = tree.copy()
+        t.remove_edge(u, v)
+        A, B = t.component(u, None), t.component(v, None)
+        if len([x for x in A if x < len(leaf_seq)]) < 1 or len([x for x in B if x < len(leaf_seq)]) < 1:
+            continue
+        breaks.append(((u, v), t, A, B))
+    # medians of both components of every break: one pass of level-synchronous batches per break
+    cand, meta = [], []
+    for (brk, t, A, B) in breaks:
+        sides = []
+        for comp in (A, B):
+            if len(comp) == 1:
+                x = next(iter(comp))
+                sides.append({None: (seqs[x], 0)})
+                continue
+            dm = directional_medians(t, seqs, backend, nodes=comp)
+            es = [(a, b) for (a, b) in t.edges() if a in comp and b in comp]
+            sides.append(edge_medians(t, dm, backend, es))
+        for ea, (sa, ca) in sides[0].items():
+            for eb, (sb, cb) in sides[1].items():
+                cand.append((sa, sb)); meta.append((brk, ea, eb, ca + cb))
+    d = backend.distance(cand)
+    est = np.array([dd + m[3] for dd, m in zip(d, meta)], np.int64)
+    if len(est) == 0:
+        return None, None, 0
+    k = int(np.argmin(est))
+    best = (int(est[k]), k)
+    if reduce_best is not None:
+        best = reduce_best(best)
+    return best[0], meta[best[1]][:3], len(cand)
+
+
+def apply_tbr(tree, move):
+    """reconnect: remove the break edge, suppress the two degree-2 nodes, join the midpoints of the two edges"""
+    (u, v), ea, eb = move
+    t = tree.copy()
+    t.remove_edge(u, v)
+
+    def suppress(x):
+        if x in t.adj and len(t.adj[x]) == 2:
+            a, b = t.adj[x]
+            t.remove_edge(x, a); t.remove_edge(x, b); del t.adj[x]
+            t.add_edge(a, b)
+            return (x, a, b)
+        return None
+    su, sv = suppress(u), suppress(v)
+
+    def fix(e, s):
+        # an edge of the component that touched the suppressed node now runs between its two neighbours
+        if e is None or s is None:
+            return e
+        x, a, b = s
+        if x in e:
+            return tuple(sorted((a, b)))
+        return e
+    ea, eb = fix(ea, su), fix(eb, sv)
+    nxt = max(t.adj) + 1
+
+    def midpoint(e, lone):
+        nonlocal nxt
+        if e is None:
+            return lone
+        a, b = e
+        w = nxt; nxt += 1
+        t.remove_edge(a, b); t.add_edge(a, w); t.add_edge(w, b)
+        return w
+    lone_u = u if u in t.adj else None
+    lone_v = v if v in t.adj else None
+    ma = midpoint(ea, lone_u)
+    mb = midpoint(eb, lone_v)
+    t.add_edge(ma, mb)
+    return t
+
+
+class ShardedBackend:
+    """N>1: candidates are independent, so `distance` batches are dealt to the ranks by estimated cells (LPT),
+    every rank evaluates its shard and the per-candidate costs are combined with ONE all-reduce (each rank
+    contributes its own entries, zeros elsewhere).  Medians (the downpass) are replicated: every rank needs
+    every node sequence for the next level anyway."""
+
+    def __init__(self, backend, device=None):
+        import torch.distributed as dist
+        self.b, self.device = backend, device
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+
+    def median(self, pairs):
+        return self.b.median(pairs)
+
+    def distance(self, pairs):
+        import torch
+        import torch.distributed as dist
+        from . import shard
+        if self.world == 1 or not pairs:
+            return self.b.distance(pairs)
+        work = [(len(a) - 1) * (len(b) - 1) for a, b in pairs]
+        mine = shard.lpt_partition(work, self.world)[self.rank]
+        out = torch.zeros(len(pairs), dtype=torch.int64, device=self.device)
+        if len(mine):
+            vals = self.b.distance([pairs[i] for i in mine])
+            out[torch.as_tensor(mine, device=self.device)] = torch.as_tensor(vals, dtype=torch.int64, device=self.device)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return [int(x) for x in out.cpu().tolist()]

@@ -1,0 +1,51 @@
+"""TEST INFRASTRUCTURE: the treesearch backend interface implemented on the CPU oracle (SeqCS.DOS.median /
+DOS.distance semantics, src/seqCS.ml:701-774, 985-1084), used to replay the GPU driver's call sequence."""
+import numpy as np
+
+
+class OracleBackend:
+    def __init__(self, port, full, orig):
+        self.P, self.full, self.orig = port, full, orig
+        self.pf, self.po = port.cm(full), port.cm(orig)
+        self.affine = full.cost_model_type == 1
+
+    @staticmethod
+    def _empty(s):
+        return bool((np.asarray(s) == 16).all())
+
+    def _lin(self, pc, a, b, deltaw):
+        sw = int(len(a) > len(b))
+        s1, s2 = (b, a) if sw else (a, b)
+        gaps = max(int((np.asarray(a) & 16 != 0).sum()), int((np.asarray(b) & 16 != 0).sum()))
+        lower = int(len(s1) * 0.10); dif = len(s1) - len(s2)
+        dcalc = (lower // 2 if dif < lower else 2) if deltaw is None else (lower if dif < lower else deltaw)
+        c, r1, r2 = self.P.align_linear(pc, s1, s2, gaps + dcalc, sw)
+        return (c, r2, r1) if sw else (c, r1, r2)
+
+    def median(self, pairs):
+        out = []
+        for a, b in pairs:
+            if self._empty(a):
+                out.append((np.array(b, np.uint8), 0)); continue
+            if self._empty(b):
+                out.append((np.array(a, np.uint8), 0)); continue
+            if self.affine:
+                sw = int(len(a) > len(b))
+                si, sj = (b, a) if sw else (a, b)
+                c, m, _, _, _ = self.P.align_affine(self.pf, si, sj, sw)
+                out.append((m, int(c)))
+            else:
+                c, ra, rb = self._lin(self.pf, a, b, None)
+                out.append((self.P.ancestor_2(self.pf, ra, rb), int(c)))
+        return out
+
+    def distance(self, pairs):
+        out = []
+        for a, b in pairs:
+            if self._empty(a) or self._empty(b):
+                out.append(0)
+            elif self.affine:
+                out.append(int(self.P.cost_affine(self.po, a, b)))
+            else:
+                out.append(int(self._lin(self.po, a, b, max(abs(len(a) - len(b)), 8))[0]))
+        return out
