@@ -35,6 +35,7 @@ struct DevCM {
 #define PF_PREVGAP 32
 
 struct poy_cm {
+    uint64_t uid;          // unique per upload: pools remember which cost model their parameters belong to
     DevCM *d;
     poy_cm_host h;
     int min_non0, max_entry;
@@ -54,7 +55,8 @@ struct poy_pool {
     int32_t nseq;
     int64_t nbytes;
     bool owns_data;
-    const poy_cm *params_for;  // cost model the parameters were computed for
+    uint64_t params_for;       // uid of the cost model the parameters were computed for (0 = none)
+    size_t caps[8];            // capacities of the cached device blocks backing the arrays above
 };
 
 struct poy_ctx {
@@ -74,6 +76,11 @@ struct poy_ctx {
     // overlaps the body of the next
     cudaStream_t aux[4];
     cudaEvent_t ev_fork, ev_join[4];
+    // small cache of device blocks released by freed pools: tree-search drivers create and destroy thousands of
+    // short-lived pools, and cudaMalloc / cudaFree (a device-wide sync) would dominate their batches
+    void *cache_ptr[64];
+    size_t cache_cap[64];
+    int cache_n;
 };
 
 // ---- work descriptors ----------------------------------------------------------------

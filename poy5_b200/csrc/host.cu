@@ -77,6 +77,7 @@ extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int s = 0; s < 8; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
+    for (int i = 0; i < ctx->cache_n; ++i) cudaFree(ctx->cache_ptr[i]);
     for (int s = 0; s < 4; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
     for (int a = 0; a < 4; ++a) { cudaStreamDestroy(ctx->aux[a]); cudaEventDestroy(ctx->ev_join[a]); }
     cudaEventDestroy(ctx->ev_fork);
@@ -94,6 +95,36 @@ extern "C" poy_status poy_ctx_synchronize(poy_ctx *ctx) {
     return POY_OK;
 }
 extern "C" uint64_t poy_ctx_launch_count(const poy_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// cached device blocks (all users are ordered on ctx->stream, so stream-ordered reuse is safe)
+static cudaError_t cached_alloc(poy_ctx *ctx, void **out, size_t bytes, size_t *cap_out) {
+    if (bytes < 256) bytes = 256;
+    int best = -1;
+    for (int i = 0; i < ctx->cache_n; ++i)
+        if (ctx->cache_cap[i] >= bytes && ctx->cache_cap[i] <= 4 * bytes && (best < 0 || ctx->cache_cap[i] < ctx->cache_cap[best])) best = i;
+    if (best >= 0) {
+        *out = ctx->cache_ptr[best]; *cap_out = ctx->cache_cap[best];
+        ctx->cache_ptr[best] = ctx->cache_ptr[ctx->cache_n - 1]; ctx->cache_cap[best] = ctx->cache_cap[ctx->cache_n - 1];
+        --ctx->cache_n;
+        return cudaSuccess;
+    }
+    size_t cap = 256;
+    while (cap < bytes) cap += cap / 2 + 256;   // geometric size classes so that blocks get reused
+    cudaError_t e = cudaMalloc(out, cap);
+    if (e != cudaSuccess) {                      // out of memory: drop the cache and retry with the exact size
+        for (int i = 0; i < ctx->cache_n; ++i) cudaFree(ctx->cache_ptr[i]);
+        ctx->cache_n = 0;
+        cap = bytes;
+        e = cudaMalloc(out, cap);
+    }
+    *cap_out = cap;
+    return e;
+}
+static void cached_free(poy_ctx *ctx, void *p, size_t cap) {
+    if (!p) return;
+    if (ctx && ctx->cache_n < 64 && cap <= (512u << 20)) { ctx->cache_ptr[ctx->cache_n] = p; ctx->cache_cap[ctx->cache_n] = cap; ++ctx->cache_n; }
+    else cudaFree(p);
+}
 
 // grow-only scratch slots
 static poy_status scratch(poy_ctx *ctx, int slot, size_t bytes, void **out) {
@@ -290,7 +321,9 @@ extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm *
     }
     if (h->gap_open < 0 || max_entry >= POY_INF || h->gap_open >= POY_INF)
         return fail(ctx, POY_ERR_COST_RANGE, "cost entry or gap opening >= HIGH_NUM");
+    static uint64_t next_uid = 0;
     poy_cm *cm = new poy_cm;
+    cm->uid = ++next_uid;
     cm->h = *h;
     cm->min_non0 = poy_cm_min_non0(h);
     cm->max_entry = max_entry;
@@ -325,20 +358,21 @@ extern "C" void poy_cm_free(poy_ctx *ctx, poy_cm *cm) {
 // ---- pool ----------------------------------------------------------------------------------------
 static poy_status pool_alloc(poy_ctx *ctx, poy_pool *p) {
     const size_t nb = (size_t)std::max<int64_t>(p->nbytes, 1);
-    CK(cudaMalloc(&p->d_rowp, nb * sizeof(int4)));
-    CK(cudaMalloc(&p->d_colp, nb * sizeof(int4)));
-    CK(cudaMalloc(&p->d_rowpk, nb * sizeof(unsigned)));
-    CK(cudaMalloc(&p->d_h0, nb * sizeof(int)));
-    CK(cudaMalloc(&p->d_g0, nb * sizeof(int)));
-    CK(cudaMalloc(&p->d_gapfree, (size_t)std::max(p->nseq, 1)));
+    CK(cached_alloc(ctx, (void **)&p->d_rowp, nb * sizeof(int4), &p->caps[0]));
+    CK(cached_alloc(ctx, (void **)&p->d_colp, nb * sizeof(int4), &p->caps[1]));
+    CK(cached_alloc(ctx, (void **)&p->d_rowpk, nb * sizeof(unsigned), &p->caps[2]));
+    CK(cached_alloc(ctx, (void **)&p->d_h0, nb * sizeof(int), &p->caps[3]));
+    CK(cached_alloc(ctx, (void **)&p->d_g0, nb * sizeof(int), &p->caps[4]));
+    CK(cached_alloc(ctx, (void **)&p->d_gapfree, (size_t)std::max(p->nseq, 1), &p->caps[5]));
     return POY_OK;
 }
 
 extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
     if (!p) return;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
-    if (p->owns_data) { cudaFree(p->d_data); cudaFree(p->d_off); }
-    cudaFree(p->d_rowp); cudaFree(p->d_colp); cudaFree(p->d_rowpk); cudaFree(p->d_h0); cudaFree(p->d_g0); cudaFree(p->d_gapfree);
+    // no device sync: the blocks go back to the context's cache and are only reused in stream order
+    if (p->owns_data) { cached_free(ctx, p->d_data, p->caps[6]); cached_free(ctx, p->d_off, p->caps[7]); }
+    cached_free(ctx, p->d_rowp, p->caps[0]); cached_free(ctx, p->d_colp, p->caps[1]); cached_free(ctx, p->d_rowpk, p->caps[2]);
+    cached_free(ctx, p->d_h0, p->caps[3]); cached_free(ctx, p->d_g0, p->caps[4]); cached_free(ctx, p->d_gapfree, p->caps[5]);
     free(p->h_off);
     free(p->h_gapfree);
     delete p;
@@ -366,8 +400,8 @@ extern "C" poy_status poy_pool_upload(poy_ctx *ctx, const uint8_t *data, const i
     poy_status s = pool_new(ctx, offsets, nseq, &p);
     if (s != POY_OK) return s;
     p->owns_data = true;
-    cudaError_t e = cudaMalloc(&p->d_data, (size_t)std::max<int64_t>(p->nbytes, 1));
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_off, sizeof(int64_t) * (nseq + 1));
+    cudaError_t e = cached_alloc(ctx, (void **)&p->d_data, (size_t)std::max<int64_t>(p->nbytes, 1), &p->caps[6]);
+    if (e == cudaSuccess) e = cached_alloc(ctx, (void **)&p->d_off, sizeof(int64_t) * (nseq + 1), &p->caps[7]);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_data, data, (size_t)p->nbytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_off, offsets, sizeof(int64_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { poy_pool_free(ctx, p); return cuda_fail(ctx, e, "poy_pool_upload"); }
@@ -395,11 +429,11 @@ extern "C" poy_status poy_pool_from_device(poy_ctx *ctx, const uint8_t *d_data, 
 
 static poy_status ensure_params(poy_ctx *ctx, const poy_cm *cm, const poy_pool *cpool) {
     poy_pool *pool = const_cast<poy_pool *>(cpool);
-    if (pool->params_for == cm) return POY_OK;
+    if (pool->params_for == cm->uid) return POY_OK;
     CK(launch_params(ctx, cm, pool));
     CK(cudaMemcpyAsync(pool->h_gapfree, pool->d_gapfree, (size_t)pool->nseq, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    pool->params_for = cm;
+    pool->params_for = cm->uid;
     return POY_OK;
 }
 
@@ -553,6 +587,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     CK(launch_fill_int(ctx, d_eb, eb_total, POY_INF));
     CK(cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
 
+    // POY_FORCE_GENERIC=1 routes every pair through the any-width fallback kernels (test hook)
+    const char *fg = getenv("POY_FORCE_GENERIC");
+    const bool force_generic = fg && fg[0] == '1';
     std::vector<int> active((size_t)n);
     for (int p = 0; p < n; ++p) active[p] = p;
     std::vector<int> order;
@@ -569,7 +606,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             if (h.lasti == 0) h.k = 0;
             const int64_t B = (int64_t)delta + 2 * (int64_t)h.k + 1;
             // the packed 16x2 gap counters of k_band2 are exact while len_i + len_j < 65535
-            h.dclass = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2 >= 65535) ? 0 : band2_class_for(B);
+            h.dclass = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2 >= 65535 || force_generic) ? 0 : band2_class_for(B);
             h.stride = h.dclass ? band2_stride_for(h.dclass, B) : (int)(((B + 1) / 2 + 31) & ~31ll);
             h.dir_bytes = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2) * h.stride;
             h.iterations++;

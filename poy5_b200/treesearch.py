@@ -102,46 +102,68 @@ class Tree:
         return seen
 
 
-def directional_medians(tree, leaf_seq, backend, nodes=None):
+def directional_medians_multi(problems, backend):
     """dm[(u, v)] = (median, accumulated cost) of the subtree that contains u once edge (u, v) is cut, seen from
-    u.  Level-synchronous: every round issues ONE median batch with all directed edges whose two inputs are
-    ready (AllDirNode's three lazy medians per node, evaluated eagerly and in bulk)."""
-    nodes = set(tree.adj) if nodes is None else nodes
-    dm = {}
-    pending = []
-    for u in nodes:
-        for v in tree.adj[u]:
-            if v not in nodes:
+    u -- for SEVERAL (tree, leaf_seq, nodes) problems in lockstep.  Level-synchronous: every round issues ONE
+    median batch with all directed edges, of all problems, whose two inputs are ready (AllDirNode's three lazy
+    medians per node, evaluated eagerly and in bulk)."""
+    dms, pend = [], []
+    for tree, leaf_seq, nodes in problems:
+        nodes = set(tree.adj) if nodes is None else nodes
+        dm, pending = {}, []
+        for u in nodes:
+            for v in tree.adj[u]:
+                if v not in nodes:
+                    continue
+                others = [w for w in tree.adj[u] if w != v and w in nodes]
+                if len(others) == 0:
+                    dm[(u, v)] = (leaf_seq[u], 0)
+                else:                       # 1 other: a degree-2 node left behind by a break passes its clade through
+                    pending.append((u, v, others))
+        dms.append(dm); pend.append(pending)
+    while any(pend):
+        batch, owners = [], []
+        progressed = False
+        for k, pending in enumerate(pend):
+            dm = dms[k]
+            ready = [x for x in pending if all((w, x[0]) in dm for w in x[2])]
+            if not ready:
                 continue
-            others = [w for w in tree.adj[u] if w != v and w in nodes]
-            if len(others) == 0:
-                dm[(u, v)] = (leaf_seq[u], 0)
-            elif len(others) == 1:              # a degree-2 node left behind by a break: pass the clade through
-                pending.append((u, v, others))
-            else:
-                pending.append((u, v, others))
-    while pending:
-        ready, rest = [], []
-        for u, v, others in pending:
-            (ready if all((w, u) in dm for w in others) else rest).append((u, v, others))
-        if not ready:
+            progressed = True
+            pend[k] = [x for x in pending if not all((w, x[0]) in dm for w in x[2])]
+            for u, v, o in ready:
+                if len(o) == 2:
+                    batch.append((dm[(o[0], u)][0], dm[(o[1], u)][0])); owners.append((k, u, v, o))
+            for u, v, o in ready:            # pass-throughs only depend on entries that were already there
+                if len(o) == 1:
+                    dm[(u, v)] = dm[(o[0], u)]
+        if not progressed:
             raise RuntimeError("cyclic dependency in directional medians")
-        batch = [(u, v, others) for u, v, others in ready if len(others) == 2]
-        res = backend.median([(dm[(o[0], u)][0], dm[(o[1], u)][0]) for u, v, o in batch])
-        for (u, v, o), (seq, c2) in zip(batch, res):
-            dm[(u, v)] = (seq, c2 + dm[(o[0], u)][1] + dm[(o[1], u)][1])
-        for u, v, o in ready:
-            if len(o) == 1:
-                dm[(u, v)] = dm[(o[0], u)]
-        pending = rest
-    return dm
+        for (k, u, v, o), (seq, c2) in zip(owners, backend.median(batch)):
+            dms[k][(u, v)] = (seq, c2 + dms[k][(o[0], u)][1] + dms[k][(o[1], u)][1])
+    return dms
+
+
+def directional_medians(tree, leaf_seq, backend, nodes=None):
+    return directional_medians_multi([(tree, leaf_seq, nodes)], backend)[0]
+
+
+def edge_medians_multi(problems, dms, backend):
+    """median + total cost for every edge taken as the root (the data `cost_fn` compares a clade against), for
+    several (tree, edges) problems in ONE batch"""
+    batch, owners = [], []
+    for k, (tree, edges) in enumerate(problems):
+        for (u, v) in edges:
+            batch.append((dms[k][(u, v)][0], dms[k][(v, u)][0])); owners.append((k, (u, v)))
+    out = [dict() for _ in problems]
+    for (k, e), (seq, c2) in zip(owners, backend.median(batch)):
+        out[k][e] = (seq, c2 + dms[k][(e[0], e[1])][1] + dms[k][(e[1], e[0])][1])
+    return out
 
 
 def edge_medians(tree, dm, backend, edges=None):
-    """median + total cost for every edge taken as the root: the data `cost_fn` compares a clade against"""
     edges = tree.edges() if edges is None else edges
-    res = backend.median([(dm[(u, v)][0], dm[(v, u)][0]) for u, v in edges])
-    return {e: (seq, c2 + dm[(e[0], e[1])][1] + dm[(e[1], e[0])][1]) for e, (seq, c2) in zip(edges, res)}
+    return edge_medians_multi([(tree, edges)], [dm], backend)[0]
 
 
 def tree_cost(tree, leaf_seq, backend):
@@ -185,18 +207,27 @@ def tbr_round(tree, leaf_seq, backend, reduce_best=None):
         if len([x for x in A if x < len(leaf_seq)]) < 1 or len([x for x in B if x < len(leaf_seq)]) < 1:
             continue
         breaks.append(((u, v), t, A, B))
-    # medians of both components of every break: one pass of level-synchronous batches per break
+    # medians of both components of every break: all (break, side) problems advance in lockstep, so each tree
+    # level costs ONE median batch for the whole neighbourhood
+    probs, where = [], []
+    for bi, (brk, t, A, B) in enumerate(breaks):
+        for side, comp in enumerate((A, B)):
+            if len(comp) > 1:
+                probs.append((t, seqs, comp)); where.append((bi, side))
+    dms = directional_medians_multi(probs, backend)
+    eprobs = [(t, [(a, b) for (a, b) in t.edges() if a in comp and b in comp]) for (t, _, comp) in probs]
+    ems = edge_medians_multi(eprobs, dms, backend)
+    sides_of = {}
+    for (bi, side), em in zip(where, ems):
+        sides_of[(bi, side)] = em
     cand, meta = [], []
-    for (brk, t, A, B) in breaks:
+    for bi, (brk, t, A, B) in enumerate(breaks):
         sides = []
-        for comp in (A, B):
+        for side, comp in enumerate((A, B)):
             if len(comp) == 1:
-                x = next(iter(comp))
-                sides.append({None: (seqs[x], 0)})
-                continue
-            dm = directional_medians(t, seqs, backend, nodes=comp)
-            es = [(a, b) for (a, b) in t.edges() if a in comp and b in comp]
-            sides.append(edge_medians(t, dm, backend, es))
+                sides.append({None: (seqs[next(iter(comp))], 0)})
+            else:
+                sides.append(sides_of[(bi, side)])
         for ea, (sa, ca) in sides[0].items():
             for eb, (sb, cb) in sides[1].items():
                 cand.append((sa, sb)); meta.append((brk, ea, eb, ca + cb))

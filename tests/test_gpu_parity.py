@@ -308,3 +308,80 @@ def test_median_3_union(ctx, port, go):
         assert np.array_equal(got["sequence"][t], port.median_2(pf, ra, rb, False))
         assert got["cost_max"][t] == port.worst_2(pf, ra, rb)
     pool.close()
+
+
+# ---- fallback kernels, custom prepend/tail tables ------------------------------------------------------------
+def test_generic_fallback_kernels(ctx, port, monkeypatch):
+    """the any-width fallback (k_band_generic / k_band_lin_generic) must agree with the register kernels"""
+    monkeypatch.setenv("POY_FORCE_GENERIC", "1")
+    seqs, ia, ib = edge_pairs(91, n=150, maxlen=60)
+    more, ja, jb = synth.pair_batch(92, 12, 700, frac_decorated=0.4, jitter=0.3)
+    base = len(seqs); seqs = seqs + more
+    ia = np.concatenate([ia, ja + base]); ib = np.concatenate([ib, jb + base])
+    check_batch(ctx, port, REGIMES["R2"], seqs, ia, ib)
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.sequence import Align
+    cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 2, None).full)
+    pc = port.cm(cmo.dna_matrices(1, 2, None)[0])
+    pool = pb.Pool(ctx, seqs)
+    r = Align.align_2(ctx, cm, pool, ia, ib)
+    for p in range(len(ia)):
+        oc, ra, rb = _oracle_linear(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r["cost"][p] and np.array_equal(ra, r["res_a"][p]) and np.array_equal(rb, r["res_b"][p]), p
+    cm.close(); pool.close()
+
+
+@pytest.mark.parametrize("go", [None, 4])
+def test_custom_prepend_tail_and_nonmetric(ctx, port, go):
+    """transform(prepend:..., tail:...) and a non-metric input matrix: the affine kernels take their column gap
+    costs from prepend_cost, the linear ones use prepend / tail on row 0, column 0 and the last column"""
+    import ctypes
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.sequence import Align
+    rows = [[0, 2, 1, 2, 3], [2, 0, 2, 1, 3], [1, 2, 0, 2, 2], [2, 1, 2, 0, 3], [3, 3, 2, 3, 0]]
+    t2d = Two_D.of_list(rows, go)
+    full, _ = cmo.of_list(rows)
+    if go is not None:
+        full = cmo.set_cost_model(full.clone(), 1, go)
+    rng = np.random.default_rng(2)
+    pre = rng.integers(0, 5, size=32).astype(np.int32); tail = rng.integers(0, 5, size=32).astype(np.int32)
+    pre[0] = tail[0] = 0
+    full.prepend[:] = pre; full.tail[:] = tail
+    for a in range(32):
+        t2d.full.prepend[a] = int(pre[a]); t2d.full.tail[a] = int(tail[a])
+    cm = pb.CostModel(ctx, t2d.full)
+    pc = port.cm(full)
+    seqs, ia, ib = edge_pairs(61, n=250, maxlen=80)
+    pool = pb.Pool(ctx, seqs)
+    if go is None:
+        r = Align.align_2(ctx, cm, pool, ia, ib)
+        for p in range(len(ia)):
+            oc, ra, rb = _oracle_linear(port, pc, seqs[ia[p]], seqs[ib[p]])
+            assert oc == r["cost"][p] and np.array_equal(ra, r["res_a"][p]) and np.array_equal(rb, r["res_b"][p]), p
+    else:
+        cost = Align.cost_2(ctx, cm, pool, ia, ib)
+        r = Align.align_affine_3(ctx, cm, pool, ia, ib)
+        for p in range(len(ia)):
+            assert cost[p] == port.cost_affine(pc, seqs[ia[p]], seqs[ib[p]]), p
+            oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+            assert oc == r["cost"][p] and np.array_equal(om, r["median"][p]) and np.array_equal(ra, r["res_a"][p]), p
+    cm.close(); pool.close()
+
+
+def test_long_pair_over_16k(ctx, port):
+    """len1 + len2 > 16382 needs --enable-long-sequences in the reference; no such limit here"""
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES["R1"])
+    pc = port.cm(full)
+    seqs, ia, ib = synth.pair_batch(404, 2, 12000, jitter=0.02)
+    pool = pb.Pool(ctx, seqs)
+    cost = Align.cost_2(ctx, cm, pool, ia, ib)
+    r = Align.align_affine_3(ctx, cm, pool, ia, ib)
+    for p in range(2):
+        assert cost[p] == port.cost_affine(pc, seqs[ia[p]], seqs[ib[p]])
+        oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r["cost"][p] and np.array_equal(om, r["median"][p]) and np.array_equal(ra, r["res_a"][p])
+    cm.close(); pool.close()
