@@ -221,7 +221,8 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
                                              const int4 *__restrict__ colp, const int *__restrict__ g0v, int4 *bnd0,
                                              int4 *bnd1, int GO, int lane, int *__restrict__ cost_out) {
     constexpr int W = 32 * C;
-    const char *s_tab = (const char *)s_tab_i;
+    const unsigned tab_base = (unsigned)__cvta_generic_to_shared(s_tab_i);
+    const unsigned GF_ROW_BYTES_U = GF_TAB_COLS * 128;
     {
         const int lasti = J.lasti, lastj = J.lastj;
         const unsigned *rp = rowpk + J.off_i;
@@ -245,12 +246,12 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
                 if (j >= 1) {
                     const int4 v = cp[j];
                     c_ge[c] = v.x;
-                    c_off[c] = ((v.w & 15) << 7) + (lane << 2);
+                    c_off[c] = (int)tab_base + ((v.w & 15) << 7) + (lane << 2);
                     CBu[c] = POY_INF; EVu[c] = POY_INF;
                     Mu[c] = min(GO + g0[j], POY_INF);       // min3(INF, INF, EH[0][j])
                 } else {
                     c_ge[c] = 0;
-                    c_off[c] = (16 << 7) + (lane << 2);
+                    c_off[c] = (int)tab_base + (16 << 7) + (lane << 2);
                     CBu[c] = 0; EVu[c] = GO;                  // CB[0][0], EV[0][0]
                     Mu[c] = min(0, GO);
                 }
@@ -278,8 +279,8 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
                 const unsigned rfirst = __shfl_sync(0xffffffffu, win, s & 31);
                 rk = lane == 0 ? rfirst : rprev;              // row i's parameters travel down the lanes
                 if (i >= 1) {
-                    const int ge_i = (int)(rk >> 16);
-                    const char *rowbase = s_tab + (rk & 0xFFFFu);
+                    const int ge_i = (int)(rk & 0xFFFFu);
+                    const unsigned irow = rk >> 16;
                     if (lane == 0) {
                         if (b == 0) {
                             ev_col0 += ge_i;
@@ -292,7 +293,12 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
                     int cbL = lCB, ehL = lEH, mD = dM;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const int diag = *(const int *)(rowbase + c_off[c]);
+                        // address = row * (17 columns x 128 B) + column offset as ONE multiply-add: it runs on the
+                        // FMA pipe and leaves the ALU pipe to the three min instructions
+                        unsigned addr;
+                        int diag;
+                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(irow), "r"(GF_ROW_BYTES_U), "r"(c_off[c]));
+                        asm("ld.shared.s32 %0, [%1];" : "=r"(diag) : "r"(addr));
                         const int cb = mD + diag;
                         const int eh = __viaddmin_s32(cbL, GO, ehL) + c_ge[c];
                         const int ev = __viaddmin_s32(CBu[c], GO, EVu[c]) + ge_i;

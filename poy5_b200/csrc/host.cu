@@ -563,6 +563,25 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     if (s != POY_OK) return s;
     if ((s = ensure_params(ctx, cm, pool)) != POY_OK) return s;
     for (int p = 0; p < n; ++p) hp[p].gapfree = linear ? 1 : (pool->h_gapfree[h_si[p]] && pool->h_gapfree[h_sj[p]]);
+    // Threshold doublings that provably cannot stop are skipped.  Every path from (0,0) to (leni,lenj) has
+    // (#insertions - #deletions) = delta, and the gap counters are maxima over tie paths, so gap_num >= delta;
+    // the stop rule (affine: gap_num < p, linear: gap_num + 1 < p) therefore fails while p <= delta (+1), and
+    // unless the "band spans the matrix" clause fires the reference just doubles T.  A skipped fill leaves no
+    // trace in the result -- except through the stale EB row / EH[0][0] of the affine path, which only pairs
+    // with gap-bit symbols can observe, so those pairs run every fill.
+    for (int p = 0; p < n; ++p) {
+        HostPair &h = hp[p];
+        if (h.lasti == 0 || h.fullplane || (!linear && !h.gapfree)) continue;
+        const int delta = h.lastj - h.lasti;
+        for (;;) {
+            const int pp = (h.T - delta) / 2, newp = (2 * h.T - delta) / 2;
+            const bool spans = linear ? (newp - (h.lastj + 1) + 1 >= 0) : (newp - h.lastj + 1 >= 0);
+            const bool cannot_stop = linear ? (pp <= delta + 1) : (pp <= delta);
+            if (spans || !cannot_stop || h.T > (1 << 28)) break;
+            h.T *= 2;
+            h.iterations++;
+        }
+    }
 
     void *v_state, *v_eb, *v_jobs, *v_misc, *v_pin, *v_pin2;
     if ((s = scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;

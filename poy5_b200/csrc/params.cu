@@ -58,9 +58,8 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
                 }
                 rowp[base + x] = r;
                 colp[base + x] = c;
-                // gap-free cost kernel: ge_i in the high half, byte offset of the cost row (17 columns x 32
-                // bank replicas x 4 B) in the low half
-                rowpk[base + x] = ((unsigned)min(max(s_gapext[code], 0), 0xFFFF) << 16) | (unsigned)((code & POY_NOGAP) * 17 * 128);
+                // gap-free cost kernel: ge_i in the low half, row index of the cost table in the high half
+                rowpk[base + x] = (unsigned)min(max(s_gapext[code], 0), 0xFFFF) | ((unsigned)(code & POY_NOGAP) << 16);
             }
             // inclusive warp scans of hl and ge_c
             int sh = hl, sg = ge_c;
