@@ -360,8 +360,16 @@ def main():
         except Exception:
             pass
         achieved = k_cells * OPS_PER_CELL["gapfree"] / (k_ms * 1e-3) / 1e12
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same shape, from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_cost_affine"]
+            top = [w for w in work if w["L"] == Ltop]
+            if tj["length"] == Ltop and all(w["n"] == tj["pairs_per_launch"] for w in top):
+                traffic = tj["dram_bytes_per_launch"] * len(top)
+        except Exception:
+            pass
         roofline = dict(bound="int32", kernel="k_cost_affine", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
-                        frac=achieved / (peak_ops / 1e12), traffic=None,
+                        frac=achieved / (peak_ops / 1e12), traffic=traffic,
                         note="INT32 issue roofline: algorithmic scalar add/min per cell (%d, gap-free cost-only cell) x cells / "
                              "launch time, vs the IADD3-class issue rate measured live by poy_microbench_int "
                              "(DPX VIADDMNMX measured %.2f Tops/s). Launch time from CUDA events around the cost-only "
