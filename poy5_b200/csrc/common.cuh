@@ -117,7 +117,7 @@ cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool);
 cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, const int *d_a, const int *d_b,
                                    CostJob *d_jobs, int *d_counts);
 cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
-                               int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost);
+                               int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost, int wide);
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
                          bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 int band2_class_for(long long B);

@@ -31,6 +31,7 @@
 // EV[i][lastj] is computed from clobbered predecessors (both INF), i.e.
 // EV[i][lastj] = INF + min(vext_i, go_i+ge_i).  Pairs with lenj <= TINY_L are run
 // through an exact emulation of the reference's flat scratch layout instead.
+#include <stdlib.h>
 #include "common.cuh"
 
 #define TINY_L 8
@@ -324,7 +325,8 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
 // ---- one persistent kernel for both kinds of pair ------------------------------------------------------------
 // Jobs sit in ONE list (general pairs first: they are the slower ones), warps pull them with an atomic counter and
 // dispatch on J.gapfree, so the tail of either kind is filled by the other.
-__global__ void __launch_bounds__(128, 4)
+template <int CG, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const unsigned *__restrict__ rowpk,
               const int4 *__restrict__ colp, const int *__restrict__ g0v, const CostJob *__restrict__ jobs, int njobs,
               int *counter, int4 *bound, size_t bound_stride, int *__restrict__ cost_out) {
@@ -347,15 +349,24 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
         job = __shfl_sync(0xffffffffu, job, 0);
         if (job >= njobs) break;
         const CostJob J = jobs[job];
-        if (J.gapfree) cost_pair_gf<16>(s_tab, J, rowpk, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
+        if (J.gapfree) cost_pair_gf<CG>(s_tab, J, rowpk, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
         else cost_pair_general<8>(cm, s_tab, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
     }
 }
 
 cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
-                               int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost) {
-    k_cost_affine<<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
-                                                   d_counter, d_bound, bound_stride, d_cost);
+                               int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost, int wide) {
+    // columns per lane of the gap-free path: 32 (column blocks of 1024, half the boundary traffic, fewer per-step
+    // overheads) pays off once the sequences span more than one such block; 16 wastes fewer lanes on short pairs.
+    // POY_COST_C=16|32 overrides (tuning knob).
+    int cg = wide ? 32 : 16;
+    { const char *e = getenv("POY_COST_C"); if (e && (atoi(e) == 16 || atoi(e) == 32)) cg = atoi(e); }
+    if (cg == 32)
+        k_cost_affine<32, 2><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
+                                                               d_counter, d_bound, bound_stride, d_cost);
+    else
+        k_cost_affine<16, 4><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
+                                                               d_counter, d_bound, bound_stride, d_cost);
     ctx->launches++;
     return cudaGetLastError();
 }

@@ -471,7 +471,7 @@ extern "C" poy_status poy_batch_cost_affine_dev(poy_ctx *ctx, const poy_cm *cm, 
     int *counts = (int *)misc;  // [0],[1] = work counters; [2],[3] = job counts
     CK(cudaMemsetAsync(counts, 0, 16, ctx->stream));
     CK(launch_build_cost_jobs(ctx, pool, n, d_a, d_b, (CostJob *)jobs, counts + 2));
-    CK(launch_cost_affine(ctx, cm, pool, (CostJob *)jobs, n, counts, (int4 *)bound, bound_stride, blocks, d_cost));
+    CK(launch_cost_affine(ctx, cm, pool, (CostJob *)jobs, n, counts, (int4 *)bound, bound_stride, blocks, d_cost, ml >= 1500));
     return POY_OK;
 }
 
