@@ -140,6 +140,11 @@ __device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, uns
     return b;
 }
 
+// Named-barrier producer / consumer pair (the PTX manual's bar.arrive / bar.sync idiom): the producing warp
+// arrives without waiting, the consuming warp waits until both have reached the barrier.
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 template <int H>
 __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed) {
     if (H == 1) *p = (uint8_t)packed;
@@ -152,7 +157,7 @@ __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed)
 
 // NW warps cooperate on one pair.  NW == 1: a CTA holds WPB independent warps (each with its own
 // pair) that only share the replicated cost table.
-template <int D, int NW, int WPB>
+template <int D, int NW, int WPB, bool GFK>
 __global__ void __launch_bounds__(WPB * 32)
 k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
         const int *__restrict__ h0v, const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state,
@@ -185,7 +190,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         if (job >= njobs) break;
         const BandJob J = jobs[job];
         if (J.lasti == 0) continue;
-        // both kinds of pair run in the same launch: gap-free pairs (J.swaped bit 2) take the 3-state code path
+        // gap-free pairs (J.swaped bit 2, all jobs of a GFK launch) take the 3-state code path
         auto run = [&](auto gf_c) {
         constexpr bool GF = decltype(gf_c)::value;
         const int lasti = J.lasti, lastj = J.lastj, k = J.k;
@@ -227,10 +232,22 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; R[h] = load_row(i0 - h); });
         sfor<H + 1>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = load_col(j0 + h); });
 
+        // Neighbouring warps synchronise pairwise (P2P) instead of CTA wide: warp w waits for the odd sub-step of
+        // warp w-1 on barrier O(w-1) and for the even sub-step of warp w+1 on barrier E(w+1); the producer side only
+        // arrives.  Program order makes every arrive / wait pair up and keeps the 12-byte mailboxes race free
+        // (DESIGN.md section 5).  Warps wholly right of the band take no part.  16 warps would need 30 barrier
+        // ids, so that class keeps __syncthreads.
+        constexpr bool P2P = (NW > 1 && NW <= 8);
+        const bool warp_in_band = (NW == 1) || (warp * 32 * D < B);
+        const bool has_left = P2P && warp > 0;
+        const bool has_right = P2P && warp + 1 < NW && (warp + 1) * 32 * D < B;
+        const int bar_E_mine = warp, bar_E_right = warp + 1;            // E(w) = id w, w = 1 .. NW-1
+        const int bar_O_mine = NW + warp, bar_O_left = NW + warp - 1;   // O(w) = id NW + w, w = 0 .. NW-2
         if (NW > 1) {
             if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
             if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
             __syncthreads();
+            if (P2P && warp_in_band && has_right) pair_arrive(bar_O_mine);   // row 0 stands in for "odd sub-step -1"
         } else {
             __syncwarp();
         }
@@ -239,7 +256,6 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         int a_main = delta + k + 2;                     // first anti-diagonal whose band cells all have i >= 1, j >= 1
         if ((a_main ^ a) & 1) ++a_main;
         const int istar = lasti & ~1;                   // last even row: source of the stale EB row
-        const bool warp_in_band = (NW == 1) || (warp * 32 * D < B);   // warps wholly right of the band just keep the barriers company
 
         // one loop iteration = anti-diagonals a (even diagonals) and a+1 (odd diagonals)
         auto iteration = [&](auto edge_c) {
@@ -254,6 +270,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             }
             // ---- even diagonals ----
             {
+                if (has_left) pair_wait(bar_O_left);
                 int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
                 int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
                 unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
@@ -284,11 +301,13 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 if (warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, packed);
                 if (NW > 1) {
                     if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
-                    __syncthreads();
+                    if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
+                    else __syncthreads();
                 }
             }
             // ---- odd diagonals ----
             {
+                if (has_right) pair_wait(bar_E_right);
                 int sCB = __shfl_down_sync(0xffffffffu, CB[0], 1);
                 int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
                 unsigned sG = __shfl_down_sync(0xffffffffu, G[0], 1);
@@ -318,7 +337,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 if (warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, packed);
                 if (NW > 1) {
                     if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
-                    __syncthreads();
+                    if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
+                    else __syncthreads();
                 }
             }
             // ---- slide the windows one row down / one column right ----
@@ -329,8 +349,11 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             C[H] = col_entry<GF>(ncol, lane);
         };
 
-        for (; a <= a_end && a < a_main; a += 2) iteration(std::true_type{});
-        for (; a <= a_end; a += 2) iteration(std::false_type{});
+        if (!P2P || warp_in_band) {
+            for (; a <= a_end && a < a_main; a += 2) iteration(std::true_type{});
+            for (; a <= a_end; a += 2) iteration(std::false_type{});
+            if (has_left) pair_wait(bar_O_left);   // drains the last arrive of the left neighbour
+        }
 
         // result: the cell (lasti, lastj) is the latest cell of diagonal delta + k
         const int dstar = delta + k;
@@ -347,7 +370,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         }
         if (tid == 0 && min(k, lasti) >= 2) st->eh00 = POY_INF;  // an even row wrote EH[.][0] = INF into row buffer 0
         };
-        if (J.swaped & 4) run(std::true_type{}); else run(std::false_type{});
+        // one kind of pair per launch (GFK): the 3-state path needs ~35 fewer registers, i.e. one more resident CTA
+        if constexpr (GFK) run(std::true_type{}); else run(std::false_type{});
     }
 }
 
@@ -361,9 +385,12 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
     int blocks = (njobs + groups_per_block - 1) / groups_per_block;
     const int cap = ctx->sm_count * 6;   // more CTAs than can be resident just queue behind the persistent ones
     if (blocks > cap) blocks = cap;
-    (void)gapfree;
-    k_band2<D, NW, WPB><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
-                                                              d_counter, d_state, d_ebrow, d_dir);
+    if (gapfree)
+        k_band2<D, NW, WPB, true><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
+                                                                         d_counter, d_state, d_ebrow, d_dir);
+    else
+        k_band2<D, NW, WPB, false><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
+                                                                          d_counter, d_state, d_ebrow, d_dir);
     ctx->launches++;
     return cudaGetLastError();
 }

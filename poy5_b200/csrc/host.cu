@@ -7,6 +7,7 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <chrono>
 #include "common.cuh"
 
 // ---- error plumbing ---------------------------------------------------------------------
@@ -612,9 +613,16 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     std::vector<int> active((size_t)n);
     for (int p = 0; p < n; ++p) active[p] = p;
     std::vector<int> order;
+    std::vector<uint64_t> keys;
     const int gen_blocks = ctx->sm_count * 2;
 
+    const char *tr = getenv("POY_TRACE");
+    const bool trace = tr && tr[0] == '1';
+    double t_prep = 0, t_wait = 0; int rounds = 0, waves = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
     while (!active.empty()) {
+        ++rounds;
         // band geometry of this round (algn_newkk_increaseT_aff / algn_newkk_test_aff, src/algn.c:2311-2336, 2195-2196)
         for (int p : active) {
             HostPair &h = hp[p];
@@ -631,14 +639,18 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             h.iterations++;
             h.cells += h.fullplane ? (int64_t)h.lasti * (h.lastj + 1) : band_cells(h.lasti, h.lastj, h.k);
         }
-        // order: by kernel class, then by size (largest first) for load balance
-        order = active;
-        std::sort(order.begin(), order.end(), [&](int x, int y) {
-            if (hp[x].dclass != hp[y].dclass) return hp[x].dclass > hp[y].dclass;
-            if (hp[x].gapfree != hp[y].gapfree) return hp[x].gapfree < hp[y].gapfree;   // slower 4-state pairs first
-            if (hp[x].dir_bytes != hp[y].dir_bytes) return hp[x].dir_bytes > hp[y].dir_bytes;
-            return x < y;
-        });
+        // order: by kernel class, 4-state pairs before gap-free ones, then by size (largest first, in 1 KiB steps) for
+        // load balance; packed into one integer key so the sort touches no other memory
+        keys.resize(active.size());
+        for (size_t q = 0; q < active.size(); ++q) {
+            const HostPair &h = hp[active[q]];
+            const uint64_t size_q = (uint64_t)std::min<int64_t>(h.dir_bytes >> 10, (1 << 18) - 1);
+            keys[q] = ((uint64_t)(4096 - h.dclass) << 51) | ((uint64_t)(h.gapfree ? 1 : 0) << 50) |
+                      ((((uint64_t)1 << 18) - 1 - size_q) << 32) | (uint32_t)active[q];
+        }
+        std::sort(keys.begin(), keys.end());
+        order.resize(active.size());
+        for (size_t q = 0; q < active.size(); ++q) order[q] = (int)(uint32_t)keys[q];
         size_t pos = 0;
         while (pos < order.size()) {
             // one wave: as many pairs as fit in the direction arena
@@ -680,7 +692,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 if (!(used_aux & (1u << ax))) { cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0); used_aux |= 1u << ax; }
                 const int cls = hp[order[pos + q0]].dclass, gf = hp[order[pos + q0]].gapfree;
                 int q1 = q0;
-                while (q1 < nj && hp[order[pos + q1]].dclass == cls) ++q1;
+                // (the fallback kernels take both kinds of pair in one launch: they share one work buffer)
+                while (q1 < nj && hp[order[pos + q1]].dclass == cls && (linear || cls == 0 || hp[order[pos + q1]].gapfree == gf)) ++q1;
                 if (cls != 0) {
                     cudaError_t le;
                     if (linear) le = launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch & 15), d_state, d_dir);
@@ -715,7 +728,10 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 else CK(launch_traceback(ctx, cm, pool, d_jobs, nj, d_done, d_dir, d_out_off, d_median, d_medianwg, d_resi,
                                          d_resj, d_out_len));
             }
+            { const double t = now(); t_prep += t - t_mark; t_mark = t; }
             CK(cudaStreamSynchronize(ctx->stream));  // the pinned job staging and the arena are reused by the next wave
+            { const double t = now(); t_wait += t - t_mark; t_mark = t; }
+            ++waves;
             pos = end;
         }
         CK(cudaMemcpyAsync(h_done, d_done, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -731,6 +747,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     if (d_cost) {
         CK(launch_gather_cost(ctx, d_state, n, d_cost));
     }
+    if (trace) fprintf(stderr, "[poy5_b200] align n=%d rounds=%d waves=%d host prep %.1f ms, device wait %.1f ms\n", n, rounds, waves, t_prep * 1e3, t_wait * 1e3);
     if (h_stats)
         for (int p = 0; p < n; ++p) {
             h_stats[4 * p + 0] = hp[p].iterations; h_stats[4 * p + 1] = hp[p].T; h_stats[4 * p + 2] = hp[p].k;
