@@ -14,7 +14,7 @@ lazy edges are out of scope.  The algorithms only talk to a *backend* with two m
     median(pairs)   -> [(median_sequence, cost2), ...]      (SeqCS.DOS.median semantics)
     distance(pairs) -> [cost, ...]                           (SeqCS.DOS.distance semantics)
 
-``GpuBackend`` below is the product path; tests replay the identical call sequence through an oracle-backed
+``GpuBackend`` below is the product path; tests replay the identical call sequence through a CPU checker
 implementation of the same interface and compare tree costs bit for bit."""
 import numpy as np
 
