@@ -395,10 +395,11 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
     return cudaGetLastError();
 }
 
-// class = number of diagonals one CTA covers: 64, 128, 256, 512, 1024, 2048, 4096
+// class = number of diagonals one CTA covers.  Warps right of the band idle, so the in-between sizes (3, 5, 6
+// warps) only buy occupancy: their registers would otherwise sit unused in a 4- or 8-warp CTA.
 int band2_class_for(long long B) {
-    const int classes[7] = { 64, 128, 256, 512, 1024, 2048, 4096 };
-    for (int c = 0; c < 7; ++c) if (B <= classes[c]) return classes[c];
+    const int classes[10] = { 64, 128, 256, 512, 768, 1024, 1280, 1536, 2048, 4096 };
+    for (int c = 0; c < 10; ++c) if (B <= classes[c]) return classes[c];
     return 0;
 }
 // bytes per anti-diagonal: one per two diagonals; above 256 diagonals only the warps that reach into the
@@ -417,7 +418,10 @@ cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, c
         case 128: L1(4, 1);
         case 256: L1(8, 1);
         case 512: L1(8, 2);    // 8 diagonals per thread measured faster than 16 (registers -> occupancy)
+        case 768: L1(8, 3);
         case 1024: L1(8, 4);
+        case 1280: L1(8, 5);
+        case 1536: L1(8, 6);
         case 2048: L1(8, 8);
         case 4096: L1(8, 16);
     }

@@ -430,7 +430,10 @@ cudaError_t launch_band_lin(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool
         case 128: LL(4, 1);
         case 256: LL(8, 1);
         case 512: LL(8, 2);
+        case 768:
         case 1024: LL(8, 4);
+        case 1280:
+        case 1536:
         case 2048: LL(8, 8);
         case 4096: LL(8, 16);
     }
