@@ -353,7 +353,8 @@ def main():
         # dominant kernel: the cost-only wavefront (k_cost_affine) on the longest length
         Ltop = max(kernel_ms) if kernel_ms else lengths[-1]
         k_ms, k_cells = kernel_ms.get(Ltop, (ms, total_cells))
-        k_bytes = sum(int(w["data"].nbytes) + 4 * w["n"] for w in work if w["L"] == Ltop)
+        n_top = max(1, sum(1 for w in work if w["L"] == Ltop))   # launches of the dominant kernel per step
+        k_bytes = sum(int(w["data"].nbytes) + 4 * w["n"] for w in work if w["L"] == Ltop) / n_top   # per launch
         hbm_peak = 6550.7
         try:
             hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -365,7 +366,7 @@ def main():
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_cost_affine"]
             top = [w for w in work if w["L"] == Ltop]
             if tj["length"] == Ltop and all(w["n"] == tj["pairs_per_launch"] for w in top):
-                traffic = tj["dram_bytes_per_launch"] * len(top)
+                traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
         roofline = dict(bound="int32", kernel="k_cost_affine", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
@@ -376,8 +377,8 @@ def main():
                              "calls on the L=%d segment (about 10%% of its pairs carry gap bits and run the 4-state path, 16 ops/cell, but are counted at 9)."
                              % (OPS_PER_CELL["gapfree"], dpx_ops / 1e12, Ltop),
                         sm_clock_mhz_microbench=peak_clock,
-                        hbm=dict(algorithmic_bytes_per_launch=int(k_bytes), achieved_gbs=k_bytes / (k_ms * 1e-3) / 1e9,
-                                 peak_gbs=hbm_peak, frac=k_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                        hbm=dict(algorithmic_bytes_per_launch=int(k_bytes), achieved_gbs=k_bytes * n_top / (k_ms * 1e-3) / 1e9,
+                                 peak_gbs=hbm_peak, frac=k_bytes * n_top / (k_ms * 1e-3) / 1e9 / hbm_peak,
                                  note="sequence bytes in + 4 B cost out per pair (SURVEY 8d): this path is integer-issue bound, not HBM bound"))
         cpu = None
         if not args.no_cpu:
