@@ -46,7 +46,7 @@ struct poy_pool {
     int64_t *d_off;        // nseq+1 offsets
     int4 *d_rowp;          // per-base parameters, row role
     int4 *d_colp;          // per-base parameters, column role
-    unsigned *d_rowpk;     // row role, packed for the gap-free cost kernel: ge << 16 | table row offset
+    unsigned *d_rowpk;     // row role, packed for the gap-free cost kernel: prefix sum of cost[s][gap] | table row << 28
     int *d_h0;             // banded entry point: CB[0][j] = sum of in-loop hext (src/algn.c:2244)
     int *d_g0;             // cost-only entry point: EH[0][j] - GO = sum of prepend (src/algn.c:1847)
     uint8_t *d_gapfree;    // per sequence: 1 if no base at index >= 1 carries the gap bit

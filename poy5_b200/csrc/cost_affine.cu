@@ -35,6 +35,7 @@
 #include "common.cuh"
 
 #define TINY_L 8
+#define GF_TAB_COLS 17                       // 16 symbols + 1 "padding" column whose entries are INF
 
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 
@@ -68,7 +69,7 @@ __device__ int cost_affine_tiny(const DevCM *cm, const int *s_cost16, const int4
             ext = pEB[j - 1] + (both ? 0 : POY_INF);
             opn = pCB[j - 1] + (both ? (clean ? 0 : 2 * go) : POY_INF);
             EB[j] = ext < opn ? ext : opn;
-            const int diag = s_cost16[(r.w & 15) * 16 + (c.w & 15)];
+            const int diag = s_cost16[(r.w & 15) * GF_TAB_COLS + (c.w & 15)];
             int a = pCB[j - 1] + diag;
             const int v = pEV[j - 1] + diag + ((r.w & PF_HASGAP) ? c.z : 0);
             const int h = pEH[j - 1] + diag + ((c.w & PF_HASGAP) ? r.z : 0);
@@ -87,12 +88,10 @@ __device__ int cost_affine_tiny(const DevCM *cm, const int *s_cost16, const int4
     return res;
 }
 
-#define GF_TAB_COLS 17                       // 16 symbols + 1 "padding" column whose entries are INF
-#define TAB_ROW_INTS (GF_TAB_COLS * 32)      // ints between consecutive table rows (32 bank replicas per entry)
 
 // ---- general pairs: 4 states, C columns per lane, left-aligned columns ---------------------------------
 template <int C>
-__device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_tab, const int *s_cost16, const CostJob &J,
+__device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_cost16, const CostJob &J,
                                                   const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
                                                   const int *__restrict__ g0v, int4 *bnd0, int4 *bnd1, int GO, int lane,
                                                   int *__restrict__ cost_out) {
@@ -161,7 +160,7 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
                     }
                 }
                 int cbL = lCB, ehL = lEH;
-                const int *rowbase = s_tab + (r.w & 15) * TAB_ROW_INTS + lane;
+                const int *rowbase = s_cost16 + (r.w & 15) * GF_TAB_COLS;
                 const int vext = r.x, opnV = r.y, go_i = r.z;
                 const int mask_i = (r.w & PF_HASGAP) ? -1 : 0;
                 int xCB = dCB, xEV = dEV, xEH = dEH, xEB = dEB;
@@ -176,7 +175,7 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
                     const int dg = both ? 0 : POY_INF;
                     const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
                     const int eb = __viaddmin_s32(xEB, dg, xCB + od);
-                    const int diag = rowbase[(fl & 15) << 5];
+                    const int diag = rowbase[fl & 15];
                     const int gv = go_j & mask_i;
                     const int gh = (fl & PF_HASGAP) ? go_i : 0;
                     const int xgo = go_j < go_i ? go_i : go_j;
@@ -211,12 +210,23 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
     }
 }
 
-// ---- gap-free pairs: 3 states (see the header of this file and DESIGN.md section 4) -------------------------
-// Right-aligned columns: column lastj is always slot C-1 of lane 31 of the last block, so the result and the
-// reference's even-row/last-column EV quirk touch one fixed register.  The padding on the left of block 0
-// consists of replicas of column 0 (ge = 0, table entry INF): they reproduce EH = INF, EV[i][0] and M[i][0]
-// exactly and their CB stays >= INF.  Row parameters are loaded 32 rows at a time, lane 0 picks its row by
-// shuffle and every row then travels down the lanes with the DP values.
+// ---- gap-free pairs: 3 states in a shifted domain (see the header of this file and DESIGN.md section 4) ----
+// Every DP value of cell (i,j) is carried as  X'(i,j) = X(i,j) - S_j - R_i,  S_j = sum of the column gap
+// extensions ge_1..ge_j (pool->d_g0), R_i = sum of the row gap extensions (low bits of pool->d_rowpk).  The
+// shift is the same for all states of a cell, so every minimum is unchanged, and the additive constants move
+// into the cost table:  tab'[a][b] = cost[a][b] - prepend[b] - cost[a][gap].  What is left per cell is
+//     CB' = M'(i-1,j-1) + tab'[a_i][b_j]
+//     EH' = min(EH'(i,j-1), CB'(i,j-1) + GO)           <- the only in-row dependency: ONE instruction per column
+//     EV' = min(EV'(i-1,j), CB'(i-1,j) + GO)
+//     M'  = min3(CB', EH', EV')
+// and the answer is min3(..)(lasti,lastj) + S_lastj + R_lasti.  Values that stand for "infinity" only ever lose
+// minima against finite values (the domain check keeps every finite value below INF and all costs are >= 0), so
+// any stand-in >= INF gives the same result: INF itself is used for CB/EV of row 0, EH of column 0 and for the
+// reference's clobbered EV of the last column on even rows (F5).
+// Right-aligned columns: column lastj is always slot C-1 of lane 31 of the last block.  The padding on the left
+// of block 0 consists of replicas of column 0 (table entry INF): they reproduce EH = INF, EV'[i][0] = GO and
+// M'[i][0] = GO exactly and their CB stays >= INF.  Row codes are loaded 32 rows at a time, lane 0 picks its row
+// by shuffle and every row then travels down the lanes with the DP values.
 template <int C>
 __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &J, const unsigned *__restrict__ rowpk,
                                              const int4 *__restrict__ colp, const int *__restrict__ g0v, int4 *bnd0,
@@ -224,101 +234,96 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
     constexpr int W = 32 * C;
     const unsigned tab_base = (unsigned)__cvta_generic_to_shared(s_tab_i);
     const unsigned GF_ROW_BYTES_U = GF_TAB_COLS * 128;
-    {
-        const int lasti = J.lasti, lastj = J.lastj;
-        const unsigned *rp = rowpk + J.off_i;
-        const int4 *cp = colp + J.off_j;
-        const int *g0 = g0v + J.off_j;
-        if (lasti == 0) {  // no rows: minimum over row 0 at the last column (src/algn.c:2105-2109)
-            if (lane == 0) cost_out[J.out] = lastj >= 1 ? min(GO + g0[lastj], POY_INF) : 0;
-            return;
-        }
-        const int nb = (lastj + W - 1) / W;
-        const int pad = nb * W - lastj;
-        for (int b = 0; b < nb; ++b) {
-            const int jb = b * W + lane * C - pad;  // slot c <-> column jb + c + 1 (<= 0: replica of column 0)
-            const int4 *bin = (b & 1) ? bnd0 : bnd1;
-            int4 *bout = (b & 1) ? bnd1 : bnd0;
-            const bool last_block = (b == nb - 1);
-            int c_ge[C], c_off[C], CBu[C], EVu[C], Mu[C];
+    const int lasti = J.lasti, lastj = J.lastj;
+    const unsigned *rp = rowpk + J.off_i;
+    const int4 *cp = colp + J.off_j;
+    const int *g0 = g0v + J.off_j;
+    if (lasti == 0) {  // no rows: minimum over row 0 at the last column (src/algn.c:2105-2109)
+        if (lane == 0) cost_out[J.out] = lastj >= 1 ? min(GO + g0[lastj], POY_INF) : 0;
+        return;
+    }
+    const int M0 = min(0, GO);
+    const int nb = (lastj + W - 1) / W;
+    const int pad = nb * W - lastj;
+    for (int b = 0; b < nb; ++b) {
+        const int jb = b * W + lane * C - pad;  // slot c <-> column jb + c + 1 (<= 0: replica of column 0)
+        const int4 *bin = (b & 1) ? bnd0 : bnd1;
+        int4 *bout = (b & 1) ? bnd1 : bnd0;
+        const bool last_block = (b == nb - 1);
+        int c_off[C], CBu[C], EVu[C], Mu[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const int j = jb + c + 1;
-                if (j >= 1) {
-                    const int4 v = cp[j];
-                    c_ge[c] = v.x;
-                    c_off[c] = (int)tab_base + ((v.w & 15) << 7) + (lane << 2);
-                    CBu[c] = POY_INF; EVu[c] = POY_INF;
-                    Mu[c] = min(GO + g0[j], POY_INF);       // min3(INF, INF, EH[0][j])
-                } else {
-                    c_ge[c] = 0;
-                    c_off[c] = (int)tab_base + (16 << 7) + (lane << 2);
-                    CBu[c] = 0; EVu[c] = GO;                  // CB[0][0], EV[0][0]
-                    Mu[c] = min(0, GO);
-                }
+        for (int c = 0; c < C; ++c) {
+            const int j = jb + c + 1;
+            if (j >= 1) {
+                c_off[c] = (int)tab_base + ((cp[j].w & 15) << 7) + (lane << 2);
+                CBu[c] = POY_INF; EVu[c] = POY_INF;
+                Mu[c] = GO;                               // min3(INF, INF, EH[0][j] = GO + S_j) - S_j
+            } else {
+                c_off[c] = (int)tab_base + (16 << 7) + (lane << 2);
+                CBu[c] = 0; EVu[c] = GO;                  // CB[0][0], EV[0][0]
+                Mu[c] = M0;
             }
-            // cell (0, jb): row-0 neighbour to the left of slot 0 (diagonal predecessor of row 1)
-            int dM;
-            if (jb >= 1) dM = min(GO + g0[jb], POY_INF); else dM = min(0, GO);
-            int ev_col0 = GO;                                 // EV[i][0] = GO + sum ge_r (src/algn.c:2066-2070)
-            int oCB = POY_INF, oEH = POY_INF, oM = POY_INF;
-            unsigned rk = 0, win = 0;
-            int4 bnext = make_int4(0, 0, 0, 0);
-            if (b > 0 && lane == 0) bnext = bin[1];
+        }
+        int dM = jb >= 1 ? GO : M0;                       // M'(0, jb): diagonal predecessor of slot 0 in row 1
+        int oCB = POY_INF, oEH = POY_INF, oM = POY_INF;
+        unsigned rk = 0, win = 0;
+        int4 bnext = make_int4(0, 0, 0, 0);
+        if (b > 0 && lane == 0) bnext = bin[1];
 
-            const int nsteps = lasti + 31;
-            for (int s = 0; s < nsteps; ++s) {
-                if ((s & 31) == 0) {                          // next 32 packed rows, one coalesced load
-                    const int r = s + lane + 1;
-                    win = rp[r <= lasti ? r : lasti];
-                }
-                const int i = s - lane + 1;
-                int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
-                int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
-                int lM = __shfl_up_sync(0xffffffffu, oM, 1);
-                unsigned rprev = __shfl_up_sync(0xffffffffu, rk, 1);
-                const unsigned rfirst = __shfl_sync(0xffffffffu, win, s & 31);
-                rk = lane == 0 ? rfirst : rprev;              // row i's parameters travel down the lanes
-                if (i >= 1) {
-                    const int ge_i = (int)(rk & 0xFFFFu);
-                    const unsigned irow = rk >> 16;
-                    if (lane == 0) {
-                        if (b == 0) {
-                            ev_col0 += ge_i;
-                            lCB = POY_INF; lEH = POY_INF; lM = ev_col0;
-                        } else {
-                            lCB = bnext.x; lEH = bnext.y; lM = bnext.z;
-                            bnext = bin[i < lasti ? i + 1 : lasti];
-                        }
-                    }
-                    int cbL = lCB, ehL = lEH, mD = dM;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        // address = row * (17 columns x 128 B) + column offset as ONE multiply-add: it runs on the
-                        // FMA pipe and leaves the ALU pipe to the three min instructions
-                        unsigned addr;
-                        int diag;
-                        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(irow), "r"(GF_ROW_BYTES_U), "r"(c_off[c]));
-                        asm("ld.shared.s32 %0, [%1];" : "=r"(diag) : "r"(addr));
-                        const int cb = mD + diag;
-                        const int eh = __viaddmin_s32(cbL, GO, ehL) + c_ge[c];
-                        const int ev = __viaddmin_s32(CBu[c], GO, EVu[c]) + ge_i;
-                        mD = Mu[c];
-                        Mu[c] = __vimin3_s32(cb, eh, ev);
-                        CBu[c] = cb; EVu[c] = ev;
-                        cbL = cb; ehL = eh;
-                    }
-                    // F5: EV at the last column of an even row comes from clobbered predecessors
-                    if (last_block && lane == 31 && !(i & 1)) EVu[C - 1] = POY_INF + ge_i;
-                    dM = lM;
-                    oCB = cbL; oEH = ehL; oM = Mu[C - 1];
-                    if (lane == 31 && !last_block && i <= lasti) bout[i] = make_int4(oCB, oEH, oM, 0);
-                }
+        const int nsteps = lasti + 31;
+        for (int s = 0; s < nsteps; ++s) {
+            if ((s & 31) == 0) {                          // next 32 packed rows, one coalesced load
+                const int r = s + lane + 1;
+                win = rp[r <= lasti ? r : lasti] >> 28;
             }
-            if (last_block && lane == 31)                    // lane 31 finished row lasti in the last step
-                cost_out[J.out] = __vimin3_s32(oCB, oEH, EVu[C - 1]);
-            __syncwarp();
+            const int i = s - lane + 1;
+            int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
+            int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
+            int lM = __shfl_up_sync(0xffffffffu, oM, 1);
+            unsigned rprev = __shfl_up_sync(0xffffffffu, rk, 1);
+            const unsigned rfirst = __shfl_sync(0xffffffffu, win, s & 31);
+            rk = lane == 0 ? rfirst : rprev;              // row i's table row travels down the lanes
+            if (i >= 1) {
+                const unsigned irow = rk;
+                if (lane == 0) {
+                    if (b == 0) {                         // column 0: CB = EH = INF, EV'[i][0] = M'[i][0] = GO
+                        lCB = POY_INF; lEH = POY_INF; lM = GO;
+                    } else {
+                        lCB = bnext.x; lEH = bnext.y; lM = bnext.z;
+                        bnext = bin[i < lasti ? i + 1 : lasti];
+                    }
+                }
+                // Three passes, each of which overwrites its state array in place (no register copies at the loop
+                // back edge): EV from the old CB, then CB from the old M, then the EH chain and the new M.
+#pragma unroll
+                for (int c = 0; c < C; ++c) EVu[c] = __viaddmin_s32(CBu[c], GO, EVu[c]);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    // address = row * (17 columns x 128 B) + column offset as ONE multiply-add: it runs on the
+                    // FMA pipe and leaves the ALU pipe to the three min instructions
+                    unsigned addr;
+                    int diag;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(irow), "r"(GF_ROW_BYTES_U), "r"(c_off[c]));
+                    asm("ld.shared.s32 %0, [%1];" : "=r"(diag) : "r"(addr));
+                    CBu[c] = (c == 0 ? dM : Mu[c > 0 ? c - 1 : 0]) + diag;
+                }
+                int cbL = lCB, ehL = lEH;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    ehL = __viaddmin_s32(cbL, GO, ehL);
+                    cbL = CBu[c];
+                    Mu[c] = __vimin3_s32(cbL, ehL, EVu[c]);
+                }
+                // F5: EV at the last column of an even row comes from clobbered predecessors (>= INF)
+                if (last_block && lane == 31 && !(i & 1)) EVu[C - 1] = POY_INF;
+                dM = lM;
+                oCB = cbL; oEH = ehL; oM = Mu[C - 1];
+                if (lane == 31 && !last_block && i <= lasti) bout[i] = make_int4(oCB, oEH, oM, 0);
+            }
         }
+        if (last_block && lane == 31)                    // lane 31 finished row lasti in the last step
+            cost_out[J.out] = __vimin3_s32(oCB, oEH, EVu[C - 1]) + g0[lastj] + (int)(rp[lasti] & 0x0FFFFFFFu);
+        __syncwarp();
     }
 }
 
@@ -330,13 +335,16 @@ __global__ void __launch_bounds__(128, MINB)
 k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const unsigned *__restrict__ rowpk,
               const int4 *__restrict__ colp, const int *__restrict__ g0v, const CostJob *__restrict__ jobs, int njobs,
               int *counter, int4 *bound, size_t bound_stride, int *__restrict__ cost_out) {
-    __shared__ int s_tab[16 * GF_TAB_COLS * 32];   // 16 x 17 cost table, every entry replicated once per bank
-    __shared__ int s_cost16[256];                   // plain copy for the tiny-pair emulation
+    __shared__ int s_tab[16 * GF_TAB_COLS * 32];   // gap-free path: shifted 16 x 17 table, every entry replicated once per bank
+    __shared__ int s_cost16[16 * GF_TAB_COLS];      // 4-state path and tiny pairs: plain table, rows padded to 17 entries
     for (int x = threadIdx.x; x < 16 * GF_TAB_COLS * 32; x += blockDim.x) {
         const int e = x >> 5, a = e / GF_TAB_COLS, b = e % GF_TAB_COLS;
-        s_tab[x] = b < 16 ? cm->cost16[a * 16 + b] : POY_INF;
+        s_tab[x] = b < 16 ? cm->cost16[a * 16 + b] - cm->prepend[b] - cm->gapext[a] : POY_INF;
     }
-    for (int x = threadIdx.x; x < 256; x += blockDim.x) s_cost16[x] = cm->cost16[x];
+    for (int x = threadIdx.x; x < 16 * GF_TAB_COLS; x += blockDim.x) {
+        const int a = x / GF_TAB_COLS, b = x % GF_TAB_COLS;
+        s_cost16[x] = b < 16 ? cm->cost16[a * 16 + b] : POY_INF;
+    }
     __syncthreads();
     const int GO = cm->gap_open;
     const int lane = threadIdx.x & 31;
@@ -350,7 +358,7 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
         if (job >= njobs) break;
         const CostJob J = jobs[job];
         if (J.gapfree) cost_pair_gf<CG>(s_tab, J, rowpk, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
-        else cost_pair_general<8>(cm, s_tab, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
+        else cost_pair_general<8>(cm, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
     }
 }
 

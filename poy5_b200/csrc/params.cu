@@ -32,11 +32,11 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
     for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < nseq; s += gridDim.x * warps_per_block) {
         const int64_t base = off[s];
         const int len = (int)(off[s + 1] - base);
-        int carry_h = 0, carry_g = 0;
+        int carry_h = 0, carry_g = 0, carry_r = 0;
         unsigned anygap = 0;
         for (int x0 = 0; x0 < len; x0 += 32) {
             const int x = x0 + lane;
-            int hl = 0, ge_c = 0;
+            int hl = 0, ge_c = 0, ge_row = 0, code15 = 0;
             if (x < len) {
                 const int code = data[base + x] & 31;
                 const int prev = x > 0 ? (data[base + x - 1] & 31) : 0;
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
                 if (x >= 1) {
                     const int gopen = gap_opening_at(x, prev, code, go);
                     const int ge_r = s_gapext[code];
+                    ge_row = ge_r;
                     ge_c = s_prepend[code];
                     r.x = (x > 1 && prevgap && !curgap) ? gopen + ge_r : ge_r;
                     r.y = gopen + ge_r;
@@ -58,23 +59,27 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
                 }
                 rowp[base + x] = r;
                 colp[base + x] = c;
-                // gap-free cost kernel: ge_i in the low half, row index of the cost table in the high half
-                rowpk[base + x] = (unsigned)min(max(s_gapext[code], 0), 0xFFFF) | ((unsigned)(code & POY_NOGAP) << 16);
+                code15 = code & POY_NOGAP;
             }
-            // inclusive warp scans of hl and ge_c
-            int sh = hl, sg = ge_c;
+            // inclusive warp scans of hl, ge_c and the row-role gap extension
+            int sh = hl, sg = ge_c, sr = ge_row;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 int th = __shfl_up_sync(0xffffffffu, sh, d);
                 int tg = __shfl_up_sync(0xffffffffu, sg, d);
-                if (lane >= d) { sh += th; sg += tg; }
+                int tr = __shfl_up_sync(0xffffffffu, sr, d);
+                if (lane >= d) { sh += th; sg += tg; sr += tr; }
             }
             if (x < len) {
                 h0[base + x] = carry_h + sh;
                 g0[base + x] = carry_g + sg;
+                // gap-free cost kernel: R_i = sum of cost[s_r][gap], r = 1..i, in the low 28 bits (the domain check
+                // keeps it below HIGH_NUM), row index of the cost table in the top 4
+                rowpk[base + x] = ((unsigned)(carry_r + sr) & 0x0FFFFFFFu) | ((unsigned)code15 << 28);
             }
             carry_h += __shfl_sync(0xffffffffu, sh, 31);
             carry_g += __shfl_sync(0xffffffffu, sg, 31);
+            carry_r += __shfl_sync(0xffffffffu, sr, 31);
         }
         anygap = __any_sync(0xffffffffu, anygap);
         if (lane == 0) gapfree[s] = anygap ? 0 : 1;
