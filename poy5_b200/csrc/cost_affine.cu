@@ -32,12 +32,22 @@
 // EV[i][lastj] = INF + min(vext_i, go_i+ge_i).  Pairs with lenj <= TINY_L are run
 // through an exact emulation of the reference's flat scratch layout instead.
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 
 #define TINY_L 8
 #define GF_TAB_COLS 17                       // 16 symbols + 1 "padding" column whose entries are INF
 
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+
+// compile-time loop N-1 .. 0 (register arrays stay scalar-replaced)
+template <int N, class F>
+__device__ __forceinline__ void sfor_down(F &&f) {
+    if constexpr (N > 0) {
+        f(std::integral_constant<int, N - 1>{});
+        sfor_down<N - 1>(f);
+    }
+}
 
 // ---- exact emulation for tiny pairs (lane 0 only) -------------------------------
 __device__ int cost_affine_tiny(const DevCM *cm, const int *s_cost16, const int4 *rp, const int4 *cp, const int *g0,
@@ -89,7 +99,12 @@ __device__ int cost_affine_tiny(const DevCM *cm, const int *s_cost16, const int4
 }
 
 
-// ---- general pairs: 4 states, C columns per lane, left-aligned columns ---------------------------------
+// ---- general pairs: 4 states, C columns per lane ------------------------------------------------------------
+// Right-aligned columns like the gap-free path: column lastj is slot C-1 of lane 31 of the last block and the
+// padding on the left of block 0 replicates column 0 (CB = EH = EB = INF, EV[i][0] = GO + sum vext, table entry
+// INF).  Everything a cell needs from the column's flags is decoded once per block into per-column constants,
+// and the state arrays are updated in place (right to left for the states that read the diagonal neighbour,
+// then left to right for the EH chain), so the loop carries no register copies.
 template <int C>
 __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_cost16, const CostJob &J,
                                                   const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
@@ -109,31 +124,40 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
         return;
     }
     const int nb = (lastj + W - 1) / W;
-    const int jres = lastj - 1 - (nb - 1) * W;  // position of column lastj inside the last block
-    const int tl = jres / C, cl = jres % C;
+    const int pad = nb * W - lastj;
     for (int b = 0; b < nb; ++b) {
-        const int jb = b * W + lane * C;  // slot c <-> column jb + c + 1
+        const int jb = b * W + lane * C - pad;  // slot c <-> column jb + c + 1 (<= 0: replica of column 0)
         const int4 *bin = (b & 1) ? bnd0 : bnd1;
         int4 *bout = (b & 1) ? bnd1 : bnd0;
         const bool last_block = (b == nb - 1);
-        const bool owns_last = last_block && lane == tl;
-        int c_ext[C], c_opn[C], c_go[C], c_fl[C];
+        const bool owns_last = last_block && lane == 31;
+        // per-column constants:
+        //   c_odc = 2GO if the previous column symbol has the gap bit, else 0  (EB opening when the row side is clean)
+        //   c_lim = -INF if the column symbol has the gap bit, else INF         (EB is alive only where both have it)
+        //   c_cap = INF if the column symbol has the gap bit, else 0            (go_i is charged on CB <- EH there)
+        //   c_tab = byte offset of the column inside a row of the cost table
+        int c_ext[C], c_opn[C], c_go[C], c_odc[C], c_lim[C], c_cap[C], c_tab[C];
         int CBu[C], EVu[C], EHu[C], EBu[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int j = jb + c + 1;
-            if (j <= lastj) {
+            if (j >= 1) {
                 const int4 v = cp[j];
-                c_ext[c] = v.x; c_opn[c] = v.y; c_go[c] = v.z; c_fl[c] = v.w;
-                EHu[c] = GO + g0[j];
+                c_ext[c] = v.x; c_opn[c] = v.y; c_go[c] = v.z;
+                c_odc[c] = (v.w & PF_PREVGAP) ? 2 * GO : 0;
+                c_lim[c] = (v.w & PF_HASGAP) ? -POY_INF : POY_INF;
+                c_cap[c] = (v.w & PF_HASGAP) ? POY_INF : 0;
+                c_tab[c] = (v.w & 15) * 4;
+                CBu[c] = POY_INF; EVu[c] = POY_INF; EHu[c] = GO + g0[j];
             } else {
-                c_ext[c] = 0; c_opn[c] = 0; c_go[c] = 0; c_fl[c] = 0;
-                EHu[c] = POY_INF;
+                c_ext[c] = 0; c_opn[c] = 0; c_go[c] = GO; c_odc[c] = 0; c_lim[c] = POY_INF; c_cap[c] = 0;
+                c_tab[c] = 16 * 4;                            // the INF column of the table
+                CBu[c] = 0; EVu[c] = GO; EHu[c] = GO;         // CB[0][0], EV[0][0], EH[0][0]
             }
-            CBu[c] = POY_INF; EVu[c] = POY_INF; EBu[c] = POY_INF;
+            EBu[c] = POY_INF;
         }
         int dCB, dEV, dEH, dEB;   // cell (i-1, jb): diagonal predecessor of slot 0
-        if (jb == 0) { dCB = 0; dEV = GO; dEH = GO; dEB = POY_INF; }
+        if (jb <= 0) { dCB = 0; dEV = GO; dEH = GO; dEB = POY_INF; }
         else { dCB = POY_INF; dEV = POY_INF; dEH = GO + g0[jb]; dEB = POY_INF; }
         int ev_col0 = GO;  // EV[i][0] running sum (lane 0 of block 0), src/algn.c:2066-2070
         int oCB = POY_INF, oEH = POY_INF, oEV = POY_INF, oEB = POY_INF;
@@ -159,53 +183,58 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
                         if (i < lasti) bnext = bin[i + 1];
                     }
                 }
-                int cbL = lCB, ehL = lEH;
-                const int *rowbase = s_cost16 + (r.w & 15) * GF_TAB_COLS;
+                const char *rowbase = (const char *)(s_cost16 + (r.w & 15) * GF_TAB_COLS);
                 const int vext = r.x, opnV = r.y, go_i = r.z;
-                const int mask_i = (r.w & PF_HASGAP) ? -1 : 0;
-                int xCB = dCB, xEV = dEV, xEH = dEH, xEB = dEB;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const int fl = c_fl[c];
+                const bool rH = (r.w & PF_HASGAP) != 0, rP = (r.w & PF_PREVGAP) != 0;
+                const int mask_i = rH ? -1 : 0;
+                const int rowlim = rH ? -POY_INF : POY_INF;
+                const int rowod = rP ? 2 * GO : 0;
+                // pass 1, right to left: column c reads the old states of column c-1 and of itself, writes itself
+                sfor_down<C>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    int xCB, xEV, xEH, xEB;
+                    if constexpr (c == 0) { xCB = dCB; xEV = dEV; xEH = dEH; xEB = dEB; }
+                    else { xCB = CBu[c - 1]; xEV = EVu[c - 1]; xEH = EHu[c - 1]; xEB = EBu[c - 1]; }
                     const int go_j = c_go[c];
-                    const int eh = __viaddmin_s32(ehL, c_ext[c], cbL + c_opn[c]);
-                    const int ev = __viaddmin_s32(EVu[c], vext, CBu[c] + opnV);
-                    const bool both = (r.w & fl & PF_HASGAP) != 0;
-                    const bool clean = ((r.w | fl) & PF_PREVGAP) == 0;
-                    const int dg = both ? 0 : POY_INF;
-                    const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
-                    const int eb = __viaddmin_s32(xEB, dg, xCB + od);
-                    const int diag = rowbase[fl & 15];
+                    // EB = min(EB' + dg, CB' + od) where both symbols carry the gap bit, >= INF elsewhere (values
+                    // >= INF never win a minimum against the finite states, so any such value will do)
+                    const int od = max(rowod, c_odc[c]);
+                    const int lim = max(rowlim, c_lim[c]);
+                    const int eb = max(__viaddmin_s32(xCB, od, xEB), lim);
+                    const int diag = *(const int *)(rowbase + c_tab[c]);
                     const int gv = go_j & mask_i;
-                    const int gh = (fl & PF_HASGAP) ? go_i : 0;
-                    const int xgo = go_j < go_i ? go_i : go_j;
+                    const int gh = min(go_i, c_cap[c]);
+                    const int xgo = max(go_i, go_j);
                     int m = __viaddmin_s32(xEV, gv, xCB);
                     m = __viaddmin_s32(xEH, gh, m);
                     m = __viaddmin_s32(xEB, xgo, m);
-                    const int cb = m + diag;
-                    xCB = CBu[c]; xEV = EVu[c]; xEH = EHu[c]; xEB = EBu[c];
-                    CBu[c] = cb; EVu[c] = ev; EHu[c] = eh; EBu[c] = eb;
-                    cbL = cb; ehL = eh;
-                }
-                // F5: EV at the last column of an even row comes from clobbered predecessors
-                if (owns_last && !(i & 1)) {
-                    const int pv = POY_INF + imin(r.x, r.y);
+                    EVu[c] = __viaddmin_s32(EVu[c], vext, CBu[c] + opnV);
+                    CBu[c] = m + diag;
+                    EBu[c] = eb;
+                });
+                // column 0 has no opening alternative (EV[i][0] = EV[i-1][0] + vext, src/algn.c:2066-2070); its replicas
+                // could only find one in row 1, from CB[0][0] = 0 when the first row symbol opens for free
+                if (i == 1 && b == 0) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        if (c == cl) EVu[c] = pv;
+                        if (c_tab[c] == 16 * 4) EVu[c] = GO + vext;
                 }
+                // pass 2, left to right: the EH chain over the new CB
+                int cbL = lCB, ehL = lEH;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    ehL = __viaddmin_s32(ehL, c_ext[c], cbL + c_opn[c]);
+                    EHu[c] = ehL;
+                    cbL = CBu[c];
+                }
+                // F5: EV at the last column of an even row comes from clobbered predecessors
+                if (owns_last && !(i & 1)) EVu[C - 1] = POY_INF + imin(r.x, r.y);
                 dCB = lCB; dEV = lEV; dEH = lEH; dEB = lEB;
                 oCB = CBu[C - 1]; oEH = EHu[C - 1]; oEV = EVu[C - 1]; oEB = EBu[C - 1];
                 if (lane == 31 && !last_block) bout[i] = make_int4(oCB, oEH, oEV, oEB);
             }
         }
-        if (owns_last) {
-            int res = 0;
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-                if (c == cl) res = imin(imin(EHu[c], EVu[c]), imin(CBu[c], EBu[c]));
-            cost_out[J.out] = res;
-        }
+        if (owns_last) cost_out[J.out] = imin(imin(EHu[C - 1], EVu[C - 1]), imin(CBu[C - 1], EBu[C - 1]));
         __syncwarp();
     }
 }
