@@ -165,7 +165,9 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
         int4 bnext = make_int4(0, 0, 0, 0);
         if (b > 0 && lane == 0) bnext = bin[1];
         const int nsteps = lasti + 31;
-        for (int s = 0; s < nsteps; ++s) {
+        // one wavefront step; ROW1 = some lane may be on row 1 (the first 32 steps), see the column-0 note below
+        auto step = [&](auto row1_c, int s) {
+            constexpr bool ROW1 = decltype(row1_c)::value;
             const int i = s - lane + 1;
             int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
             int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
@@ -214,7 +216,7 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
                 });
                 // column 0 has no opening alternative (EV[i][0] = EV[i-1][0] + vext, src/algn.c:2066-2070); its replicas
                 // could only find one in row 1, from CB[0][0] = 0 when the first row symbol opens for free
-                if (i == 1 && b == 0) {
+                if (ROW1 && i == 1 && b == 0) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         if (c_tab[c] == 16 * 4) EVu[c] = GO + vext;
@@ -233,7 +235,10 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
                 oCB = CBu[C - 1]; oEH = EHu[C - 1]; oEV = EVu[C - 1]; oEB = EBu[C - 1];
                 if (lane == 31 && !last_block) bout[i] = make_int4(oCB, oEH, oEV, oEB);
             }
-        }
+        };
+        int s = 0;
+        for (; s < 32 && s < nsteps; ++s) step(std::true_type{}, s);
+        for (; s < nsteps; ++s) step(std::false_type{}, s);
         if (owns_last) cost_out[J.out] = imin(imin(EHu[C - 1], EVu[C - 1]), imin(CBu[C - 1], EBu[C - 1]));
         __syncwarp();
     }
@@ -387,7 +392,7 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
         if (job >= njobs) break;
         const CostJob J = jobs[job];
         if (J.gapfree) cost_pair_gf<CG>(s_tab, J, rowpk, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
-        else cost_pair_general<8>(cm, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
+        else cost_pair_general<(CG >= 32 ? 16 : 8)>(cm, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
     }
 }
 
@@ -402,7 +407,7 @@ cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *p
         k_cost_affine<32, 2><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
                                                                d_counter, d_bound, bound_stride, d_cost);
     else
-        k_cost_affine<16, 4><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
+        k_cost_affine<16, 3><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
                                                                d_counter, d_bound, bound_stride, d_cost);
     ctx->launches++;
     return cudaGetLastError();
