@@ -72,10 +72,10 @@ __device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, uns
     // extend horizontal / vertical: ties take the opening (END_* flag)
     bool stopH, stopV;
     int nEH, nEV;
-    if (GF) {   // no gap bits: ext = ge, opn = GO + ge, so the common ge is added after the minimum
+    if (GF) {   // no gap bits: ext = ge, opn = GO + ge, and the common ge lives in the shifted table (see k_band2)
         const int tH = lCB + GO, tV = uCB + GO;
-        stopH = !(lEH < tH); nEH = min(lEH, tH) + c.ext;
-        stopV = !(uEV < tV); nEV = min(uEV, tV) + r.ext;
+        stopH = !(lEH < tH); nEH = min(lEH, tH);
+        stopV = !(uEV < tV); nEV = min(uEV, tV);
     } else {
         const int tH = lCB + c.opn, xH = lEH + c.ext;
         stopH = !(xH < tH); nEH = min(xH, tH);
@@ -160,8 +160,8 @@ __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed)
 template <int D, int NW, int WPB, bool GFK>
 __global__ void __launch_bounds__(WPB * 32)
 k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
-        const int *__restrict__ h0v, const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state,
-        int *ebrow, uint8_t *dir) {
+        const int *__restrict__ h0v, const int *__restrict__ g0v, const unsigned *__restrict__ rowpk,
+        const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state, int *ebrow, uint8_t *dir) {
     constexpr int H = D / 2;
     __shared__ int s_tab_i[256 * 32];  // cost16 replicated per bank: entry e of lane l at [e*32 + l]
     __shared__ int s_job;
@@ -170,7 +170,14 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     static_assert(NW == 1 || WPB == NW, "cooperating warps fill the whole CTA");
     const int lane = threadIdx.x & 31, warp = (NW == 1) ? 0 : (threadIdx.x >> 5);
     const int tid = (NW == 1) ? lane : (int)threadIdx.x;   // thread index within the group that owns the pair
-    for (int x = threadIdx.x; x < 256 * 32; x += WPB * 32) s_tab_i[x] = cm->cost16[x >> 5];
+    // Gap-free launches work in a shifted domain: every state of cell (i,j) is carried minus S_j + R_i (the sums
+    // of the column / row gap extensions up to j / i), which moves the "+ ge" of EH and EV into the table as
+    // cost[a][b] - prepend[b] - cost[a][gap].  All comparisons of a cell are between states of the same shift, so
+    // the direction bytes and gap counters do not change; the cost is shifted back when it is stored.
+    for (int x = threadIdx.x; x < 256 * 32; x += WPB * 32) {
+        const int e = x >> 5;
+        s_tab_i[x] = cm->cost16[e] - (GFK ? cm->prepend[e & 15] + cm->gapext[e >> 4] : 0);
+    }
     __syncthreads();
     const char *s_tab = (const char *)s_tab_i;
     const int GO = cm->gap_open;
@@ -199,6 +206,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         const int4 *rp = rowp + J.off_i;
         const int4 *cp = colp + J.off_j;
         const int *h0 = h0v + J.off_j;
+        const int *g0 = g0v + J.off_j;
         int *eb = ebrow + J.eb_off;
         PairState *st = state + J.pair;
         uint8_t *dbase = dir + J.dir_off;
@@ -213,8 +221,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             constexpr int u = decltype(uc)::value;
             const int d = d0 + u, j0 = d - k;
             if (d < B && j0 >= 0 && j0 <= lastj) {  // row 0 (src/algn.c:2222-2247)
-                CB[u] = h0[j0];
-                EH[u] = j0 == 0 ? eh00 : h0[j0];
+                CB[u] = h0[j0] - (GF ? g0[j0] : 0);
+                EH[u] = j0 == 0 ? eh00 : CB[u];
                 EV[u] = POY_INF;
                 EB[u] = GF ? POY_INF : eb[j0];
                 G[u] = (unsigned)j0 & 0xFFFFu;
@@ -363,6 +371,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 if (u == dstar % D) {
                     int fin = __vimin3_s32(EH[u], EV[u], CB[u]);
                     if (!GF) fin = min(fin, EB[u]);
+                    if (GF) fin += g0[lastj] + (int)(rowpk[J.off_i + lasti] & 0x0FFFFFFFu);
                     st->cost = fin;
                     st->gapnum = max((int)(G[u] & 0xFFFFu), (int)(G[u] >> 16));
                 }
@@ -386,10 +395,10 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
     const int cap = ctx->sm_count * 6;   // more CTAs than can be resident just queue behind the persistent ones
     if (blocks > cap) blocks = cap;
     if (gapfree)
-        k_band2<D, NW, WPB, true><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
+        k_band2<D, NW, WPB, true><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, pool->d_g0, pool->d_rowpk, d_jobs, njobs,
                                                                          d_counter, d_state, d_ebrow, d_dir);
     else
-        k_band2<D, NW, WPB, false><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, d_jobs, njobs,
+        k_band2<D, NW, WPB, false><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, pool->d_g0, pool->d_rowpk, d_jobs, njobs,
                                                                           d_counter, d_state, d_ebrow, d_dir);
     ctx->launches++;
     return cudaGetLastError();
