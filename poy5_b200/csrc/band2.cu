@@ -157,7 +157,9 @@ __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed)
 
 // NW warps cooperate on one pair.  NW == 1: a CTA holds WPB independent warps (each with its own
 // pair) that only share the replicated cost table.
-template <int D, int NW, int WPB, bool GFK>
+// DIR = false is the "probe" fill: same states, gap counters and stale-row side effects, but no direction bytes
+// (the whole byte assembly is dead code then).  The host uses it for fills it expects not to be the last one.
+template <int D, int NW, int WPB, bool GFK, bool DIR>
 __global__ void __launch_bounds__(WPB * 32)
 k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
         const int *__restrict__ h0v, const int *__restrict__ g0v, const unsigned *__restrict__ rowpk,
@@ -306,7 +308,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         }
                     }
                 });
-                if (warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, packed);
+                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, packed);
                 if (NW > 1) {
                     if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
                     if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
@@ -342,7 +344,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         }
                     }
                 });
-                if (warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, packed);
+                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, packed);
                 if (NW > 1) {
                     if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
                     if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
@@ -386,7 +388,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
 
 template <int D, int NW>
 static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
-                              bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+                              bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
     cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
     if (e != cudaSuccess) return e;
     constexpr int WPB = NW == 1 ? 8 : NW;
@@ -394,12 +396,11 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
     int blocks = (njobs + groups_per_block - 1) / groups_per_block;
     const int cap = ctx->sm_count * 6;   // more CTAs than can be resident just queue behind the persistent ones
     if (blocks > cap) blocks = cap;
-    if (gapfree)
-        k_band2<D, NW, WPB, true><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, pool->d_g0, pool->d_rowpk, d_jobs, njobs,
-                                                                         d_counter, d_state, d_ebrow, d_dir);
-    else
-        k_band2<D, NW, WPB, false><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, pool->d_h0, pool->d_g0, pool->d_rowpk, d_jobs, njobs,
-                                                                          d_counter, d_state, d_ebrow, d_dir);
+#define LAUNCH(GFV, DIRV) k_band2<D, NW, WPB, GFV, DIRV><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, \
+        pool->d_h0, pool->d_g0, pool->d_rowpk, d_jobs, njobs, d_counter, d_state, d_ebrow, d_dir)
+    if (gapfree) { if (probe) LAUNCH(true, false); else LAUNCH(true, true); }
+    else { if (probe) LAUNCH(false, false); else LAUNCH(false, true); }
+#undef LAUNCH
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -419,9 +420,9 @@ int band2_stride_for(int cls, long long B) {
 }
 
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
-                         bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
     if (njobs <= 0) return cudaSuccess;
-#define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, d_counter, d_state, d_ebrow, d_dir)
+#define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir)
     switch (cls) {
         case 64: L1(2, 1);
         case 128: L1(4, 1);

@@ -209,7 +209,7 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
     const int t = blockIdx.x * 4 + w;
     if (t >= njobs) return;
     const BandJob J = jobs[t];
-    if (done && !done[J.pair]) return;  // this pair's band is not final yet
+    if (done && done[J.pair] != 1) return;  // this pair's band is not final yet (or was only probed)
     const uint8_t *si = data + J.off_i, *sj = data + J.off_j;
     const int k = J.k;
     const int B = (J.lastj - J.lasti) + 2 * k + 1;

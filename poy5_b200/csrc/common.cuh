@@ -96,7 +96,8 @@ struct BandJob {          // one band fill of one pair
     int lasti, lastj;
     int k;                // half band (already clamped, src/algn.c:2195-2196)
     int pair;             // index into the per-pair state arrays
-    int swaped;
+    int swaped;           // bit 0 operands were exchanged by the caller, bit 1 full plane (linear), bit 2 gap-free pair,
+                          // bit 3 probe fill (no direction bytes), bit 4 no traceback wanted (a probe's verdict is final)
     int stride;           // bytes per anti-diagonal in the direction arena
     int64_t dir_off;      // byte offset of this pair's direction block in the arena
     int64_t eb_off;       // int offset of this pair's stale-EB row in the state arena
@@ -119,7 +120,7 @@ cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, co
 cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
                                int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost, int wide);
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
-                         bool gapfree, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
+                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
 int band2_class_for(long long B);
 int band2_stride_for(int cls, long long B);
 cudaError_t launch_band_lin(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,

@@ -499,7 +499,10 @@ extern "C" poy_status poy_batch_cost_affine(poy_ctx *ctx, const poy_cm *cm, cons
 namespace {
 struct HostPair {
     int lasti, lastj, T, k, dclass, stride, gapfree, fullplane;
-    int64_t off_i, off_j, eb_off, dir_bytes;
+    int probe;      // this round's fill writes no direction bytes (see the round loop of align_impl)
+    int want_dirs;  // the previous verdict asked for a fill with direction bytes
+    int repeat;     // ... at the same threshold (not a new iteration of the reference's loop)
+    int64_t off_i, off_j, eb_off, dir_bytes, work;
     int iterations;
     int64_t cells;
     bool done;
@@ -550,7 +553,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         h.T = (h.lastj - h.lasti + 1) * cm->min_non0;  // algn_fill_plane_3_aff, src/algn.c:2348-2349
         h.eb_off = eb_total;
         eb_total += h.lastj + 1;
-        h.iterations = 0; h.cells = 0; h.done = false; h.fullplane = 0;
+        h.iterations = 0; h.cells = 0; h.done = false; h.fullplane = 0; h.probe = 0; h.want_dirs = 0; h.repeat = 0;
         if (linear) {   // algn_nw_limit / algn_fill_plane_2: full plane or Ukkonen band (src/algn.c:2963, 1141-1176)
             const int lenX = h.lasti + 1, lenY = h.lastj + 1;
             int height = (lenX - lenY) + 50 + h_deltawh[p];
@@ -619,6 +622,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const char *tr = getenv("POY_TRACE");
     const bool trace = tr && tr[0] == '1';
     double t_prep = 0, t_wait = 0; int rounds = 0, waves = 0;
+    long long n_repeat = 0, n_probe = 0, n_full = 0;
+    const char *pe = getenv("POY_PROBE");   // POY_PROBE=0 turns the probe fills off (tuning / test hook)
+    const bool use_probes = !(pe && pe[0] == '0');
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
     while (!active.empty()) {
@@ -635,8 +641,23 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             // the packed 16x2 gap counters of k_band2 are exact while len_i + len_j < 65535
             h.dclass = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2 >= 65535 || force_generic) ? 0 : band2_class_for(B);
             h.stride = h.dclass ? band2_stride_for(h.dclass, B) : (int)(((B + 1) / 2 + 31) & ~31ll);
-            h.dir_bytes = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2) * h.stride;
-            h.iterations++;
+            h.work = h.lasti == 0 ? 64 : ((int64_t)h.lasti + h.lastj + 2) * h.stride;
+            // Probe fills.  A fill that will not be the last one needs no direction bytes, and without them a cell
+            // costs less than half.  Gap-free pairs are therefore filled without directions until a verdict says
+            // "the stop rule fired" (2: repeat this threshold with directions) or "the next fill should stop" (3).
+            // Pairs with gap-bit symbols always write directions: a repeated fill would start from the stale EB
+            // row the probe left behind.  Without traceback outputs nobody needs directions at all.
+            h.probe = 0;
+            if (!linear && h.dclass != 0 && h.lasti != 0 && use_probes) {
+                if (!want_trace) h.probe = 1;
+                else if (h.gapfree && !h.want_dirs) {
+                    const int newp = (2 * h.T - delta) / 2;
+                    h.probe = !(newp - h.lastj + 1 >= 0);   // a band that spans the matrix always stops
+                }
+            }
+            h.dir_bytes = h.probe ? 0 : h.work;
+            if (h.probe) ++n_probe; else ++n_full;
+            if (!h.repeat) h.iterations++;
             h.cells += h.fullplane ? (int64_t)h.lasti * (h.lastj + 1) : band_cells(h.lasti, h.lastj, h.k);
         }
         // order: by kernel class, 4-state pairs before gap-free ones, then by size (largest first, in 1 KiB steps) for
@@ -644,9 +665,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         keys.resize(active.size());
         for (size_t q = 0; q < active.size(); ++q) {
             const HostPair &h = hp[active[q]];
-            const uint64_t size_q = (uint64_t)std::min<int64_t>(h.dir_bytes >> 10, (1 << 18) - 1);
-            keys[q] = ((uint64_t)(4096 - h.dclass) << 51) | ((uint64_t)(h.gapfree ? 1 : 0) << 50) |
-                      ((((uint64_t)1 << 18) - 1 - size_q) << 32) | (uint32_t)active[q];
+            const uint64_t size_q = (uint64_t)std::min<int64_t>(h.work >> 10, (1 << 17) - 1);
+            keys[q] = ((uint64_t)(4096 - h.dclass) << 51) | ((uint64_t)(h.gapfree ? 1 : 0) << 50) | ((uint64_t)(h.probe ? 1 : 0) << 49) |
+                      ((((uint64_t)1 << 17) - 1 - size_q) << 32) | (uint32_t)active[q];
         }
         std::sort(keys.begin(), keys.end());
         order.resize(active.size());
@@ -674,7 +695,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 const HostPair &h = hp[p];
                 BandJob &j = hj[q];
                 j.off_i = h.off_i; j.off_j = h.off_j; j.lasti = h.lasti; j.lastj = h.lastj; j.k = h.k; j.pair = p;
-                j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0) | ((!linear && h.gapfree) ? 4 : 0);
+                j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0) | ((!linear && h.gapfree) ? 4 : 0) |
+                           (h.probe ? 8 : 0) | (want_trace ? 0 : 16);
                 j.stride = h.stride; j.dir_off = doff; j.eb_off = h.eb_off;
                 doff += (h.dir_bytes + 255) & ~255ll;
                 if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
@@ -690,14 +712,15 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 const int ax = nlaunch & 3;
                 ctx->stream = ctx->aux[ax];
                 if (!(used_aux & (1u << ax))) { cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0); used_aux |= 1u << ax; }
-                const int cls = hp[order[pos + q0]].dclass, gf = hp[order[pos + q0]].gapfree;
+                const int cls = hp[order[pos + q0]].dclass, gf = hp[order[pos + q0]].gapfree, pr = hp[order[pos + q0]].probe;
                 int q1 = q0;
                 // (the fallback kernels take both kinds of pair in one launch: they share one work buffer)
-                while (q1 < nj && hp[order[pos + q1]].dclass == cls && (linear || cls == 0 || hp[order[pos + q1]].gapfree == gf)) ++q1;
+                while (q1 < nj && hp[order[pos + q1]].dclass == cls &&
+                       (linear || cls == 0 || (hp[order[pos + q1]].gapfree == gf && hp[order[pos + q1]].probe == pr))) ++q1;
                 if (cls != 0) {
                     cudaError_t le;
                     if (linear) le = launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch & 15), d_state, d_dir);
-                    else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir);
+                    else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, pr != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir);
                     if (le != cudaSuccess) { ctx->stream = main_stream; return cuda_fail(ctx, le, "band fill launch"); }
                 } else {
                     void *v_work;
@@ -739,15 +762,19 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         std::vector<int> next;
         next.reserve(active.size());
         for (int p : active) {
-            if (h_done[p]) hp[p].done = true;
-            else { hp[p].T *= 2; next.push_back(p); }
+            const int verdict = h_done[p];   // k_band_finish / k_lin_finish
+            if (verdict == 1) { hp[p].done = true; continue; }
+            if (verdict == 2) { hp[p].want_dirs = 1; hp[p].repeat = 1; ++n_repeat; }   // same threshold again, with directions
+            else { hp[p].T *= 2; hp[p].want_dirs = (verdict == 3); hp[p].repeat = 0; }
+            next.push_back(p);
         }
         active.swap(next);
     }
     if (d_cost) {
         CK(launch_gather_cost(ctx, d_state, n, d_cost));
     }
-    if (trace) fprintf(stderr, "[poy5_b200] align n=%d rounds=%d waves=%d host prep %.1f ms, device wait %.1f ms\n", n, rounds, waves, t_prep * 1e3, t_wait * 1e3);
+    if (trace) fprintf(stderr, "[poy5_b200] align n=%d rounds=%d waves=%d host prep %.1f ms, device wait %.1f ms; fills: %lld probe, %lld full, %lld repeated\n",
+                       n, rounds, waves, t_prep * 1e3, t_wait * 1e3, n_probe, n_full, n_repeat);
     if (h_stats)
         for (int p = 0; p < n; ++p) {
             h_stats[4 * p + 0] = hp[p].iterations; h_stats[4 * p + 1] = hp[p].T; h_stats[4 * p + 2] = hp[p].k;

@@ -49,9 +49,19 @@ __global__ void k_band_finish(const BandJob *__restrict__ jobs, int njobs, PairS
         fin = (st->gapnum < p) || (newp - J.lastj + 1 >= 0);
     }
     st->iterations++;
-    if (!fin) st->T *= 2;
-    st->done = fin;
-    done[J.pair] = (uint8_t)fin;
+    // verdict for the host: 1 = final, 2 = the stop rule fired on a probe fill (repeat this threshold with
+    // direction bytes), 0 / 3 = double the threshold; 3 predicts that the next fill stops (gap_num already below its p)
+    int verdict;
+    if (fin) {
+        verdict = ((J.swaped & 8) && !(J.swaped & 16) && J.lasti != 0) ? 2 : 1;
+    } else {
+        st->T *= 2;
+        const int delta = J.lastj - J.lasti, T = st->T;
+        const int p = (T - delta) / 2, newp = (2 * T - delta) / 2;
+        verdict = ((st->gapnum < p) || (newp - J.lastj + 1 >= 0)) ? 3 : 0;
+    }
+    st->done = (verdict == 1);
+    done[J.pair] = (uint8_t)verdict;
 }
 
 cudaError_t launch_band_finish(poy_ctx *ctx, const BandJob *d_jobs, int njobs, PairState *d_state, uint8_t *d_done,
