@@ -97,7 +97,8 @@ struct BandJob {          // one band fill of one pair
     int k;                // half band (already clamped, src/algn.c:2195-2196)
     int pair;             // index into the per-pair state arrays
     int swaped;           // bit 0 operands were exchanged by the caller, bit 1 full plane (linear), bit 2 gap-free pair,
-                          // bit 3 probe fill (no direction bytes), bit 4 no traceback wanted (a probe's verdict is final)
+                          // bit 3 probe fill (no direction bytes), bit 4 no traceback wanted (a probe's verdict is final),
+                          // bit 5 repeat of a probed threshold: restore the stale state the probe started from
     int stride;           // bytes per anti-diagonal in the direction arena
     int64_t dir_off;      // byte offset of this pair's direction block in the arena
     int64_t eb_off;       // int offset of this pair's stale-EB row in the state arena
@@ -106,6 +107,7 @@ struct BandJob {          // one band fill of one pair
 struct PairState {        // survives across band fills of the same pair
     int T;                // current threshold
     int eh00;             // EH[0][0] as left behind by the previous fill
+    int eh00_snap;        // ... and as it was before the latest probe fill
     int cost;             // result of the latest fill
     int gapnum;           // max gap-count of the latest fill
     int iterations;
@@ -138,6 +140,7 @@ cudaError_t launch_band_finish(poy_ctx *ctx, const BandJob *d_jobs, int njobs, P
 cudaError_t launch_traceback(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                              const uint8_t *d_done, const uint8_t *d_dir, const int64_t *d_out_off, uint8_t *d_median,
                              uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj, int *d_out_len);
+cudaError_t launch_stale_snapshot(poy_ctx *ctx, const BandJob *d_jobs, int njobs, PairState *d_state, int *d_eb, int *d_eb_snap);
 cudaError_t launch_gather_cost(poy_ctx *ctx, const PairState *d_state, int n, int *d_cost);
 cudaError_t launch_fill_int(poy_ctx *ctx, int *d, int64_t n, int v);
 cudaError_t launch_microbench(poy_ctx *ctx, int kind, int iters, unsigned long long *d_cycles, int *d_sink,

@@ -551,8 +551,6 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         h.lastj = (int)(pool->h_off[b + 1] - h.off_j) - 1;
         if (h.lastj < h.lasti) return fail(ctx, POY_ERR_ORDER, "pass the shorter one as first");
         h.T = (h.lastj - h.lasti + 1) * cm->min_non0;  // algn_fill_plane_3_aff, src/algn.c:2348-2349
-        h.eb_off = eb_total;
-        eb_total += h.lastj + 1;
         h.iterations = 0; h.cells = 0; h.done = false; h.fullplane = 0; h.probe = 0; h.want_dirs = 0; h.repeat = 0;
         if (linear) {   // algn_nw_limit / algn_fill_plane_2: full plane or Ukkonen band (src/algn.c:2963, 1141-1176)
             const int lenX = h.lasti + 1, lenY = h.lastj + 1;
@@ -566,7 +564,17 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     poy_status s = domain_check(ctx, cm, maxsum);
     if (s != POY_OK) return s;
     if ((s = ensure_params(ctx, cm, pool)) != POY_OK) return s;
-    for (int p = 0; p < n; ++p) hp[p].gapfree = linear ? 1 : (pool->h_gapfree[h_si[p]] && pool->h_gapfree[h_sj[p]]);
+    // POY_FORCE_GENERIC=1 routes every pair through the any-width fallback kernels (test hook)
+    const char *fg = getenv("POY_FORCE_GENERIC");
+    const bool force_generic = fg && fg[0] == '1';
+    for (int p = 0; p < n; ++p) {
+        hp[p].gapfree = linear ? 1 : (pool->h_gapfree[h_si[p]] && pool->h_gapfree[h_sj[p]]);
+        // the stale EB row exists only for pairs with gap-bit symbols (and for the fallback kernel, which runs
+        // every pair through the 4-state code)
+        const bool generic = force_generic || (int64_t)hp[p].lasti + hp[p].lastj + 2 >= 65535;
+        hp[p].eb_off = eb_total;
+        if (!linear && (!hp[p].gapfree || generic)) eb_total += hp[p].lastj + 1;
+    }
     // Threshold doublings that provably cannot stop are skipped.  Every path from (0,0) to (leni,lenj) has
     // (#insertions - #deletions) = delta, and the gap counters are maxima over tie paths, so gap_num >= delta;
     // the stop rule (affine: gap_num < p, linear: gap_num + 1 < p) therefore fails while p <= delta (+1), and
@@ -589,14 +597,14 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
 
     void *v_state, *v_eb, *v_jobs, *v_misc, *v_pin, *v_pin2;
     if ((s = scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
-    if ((s = scratch(ctx, SL_EBROW, sizeof(int) * (size_t)eb_total, &v_eb)) != POY_OK) return s;
+    if ((s = scratch(ctx, SL_EBROW, sizeof(int) * 2 * (size_t)eb_total + 16, &v_eb)) != POY_OK) return s;   // rows + their snapshots
     if ((s = scratch(ctx, SL_JOBS, sizeof(BandJob) * (size_t)n, &v_jobs)) != POY_OK) return s;
     if ((s = scratch(ctx, SL_MISC, 256, &v_misc)) != POY_OK) return s;
     if ((s = pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (size_t)n, &v_pin)) != POY_OK) return s;
     if ((s = pinned(ctx, 1, (size_t)n + sizeof(int32_t) * (size_t)n, &v_pin2)) != POY_OK) return s;
     PairState *d_state = (PairState *)v_state;
     uint8_t *d_done = (uint8_t *)(d_state + n);
-    int *d_eb = (int *)v_eb;
+    int *d_eb = (int *)v_eb, *d_eb_snap = d_eb + eb_total;
     BandJob *d_jobs = (BandJob *)v_jobs;
     int *d_counter = (int *)v_misc;
     uint8_t *h_done = (uint8_t *)v_pin2;
@@ -610,9 +618,6 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     CK(launch_fill_int(ctx, d_eb, eb_total, POY_INF));
     CK(cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
 
-    // POY_FORCE_GENERIC=1 routes every pair through the any-width fallback kernels (test hook)
-    const char *fg = getenv("POY_FORCE_GENERIC");
-    const bool force_generic = fg && fg[0] == '1';
     std::vector<int> active((size_t)n);
     for (int p = 0; p < n; ++p) active[p] = p;
     std::vector<int> order;
@@ -645,12 +650,13 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             // Probe fills.  A fill that will not be the last one needs no direction bytes, and without them a cell
             // costs less than half.  Gap-free pairs are therefore filled without directions until a verdict says
             // "the stop rule fired" (2: repeat this threshold with directions) or "the next fill should stop" (3).
-            // Pairs with gap-bit symbols always write directions: a repeated fill would start from the stale EB
-            // row the probe left behind.  Without traceback outputs nobody needs directions at all.
+            // For pairs with gap-bit symbols a probe first snapshots the stale EB row / EH[0][0] it is about to
+            // change, and the repeated fill starts from the snapshot.  Without traceback outputs nobody needs
+            // directions at all.
             h.probe = 0;
             if (!linear && h.dclass != 0 && h.lasti != 0 && use_probes) {
                 if (!want_trace) h.probe = 1;
-                else if (h.gapfree && !h.want_dirs) {
+                else if (!h.want_dirs) {
                     const int newp = (2 * h.T - delta) / 2;
                     h.probe = !(newp - h.lastj + 1 >= 0);   // a band that spans the matrix always stops
                 }
@@ -696,12 +702,13 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 BandJob &j = hj[q];
                 j.off_i = h.off_i; j.off_j = h.off_j; j.lasti = h.lasti; j.lastj = h.lastj; j.k = h.k; j.pair = p;
                 j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0) | ((!linear && h.gapfree) ? 4 : 0) |
-                           (h.probe ? 8 : 0) | (want_trace ? 0 : 16);
+                           (h.probe ? 8 : 0) | (want_trace ? 0 : 16) | (h.repeat ? 32 : 0);
                 j.stride = h.stride; j.dir_off = doff; j.eb_off = h.eb_off;
                 doff += (h.dir_bytes + 255) & ~255ll;
                 if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
             }
             CK(cudaMemcpyAsync(d_jobs, hj, sizeof(BandJob) * (size_t)nj, cudaMemcpyHostToDevice, ctx->stream));
+            if (!linear && eb_total > 0 && want_trace && use_probes) CK(launch_stale_snapshot(ctx, d_jobs, nj, d_state, d_eb, d_eb_snap));
             // launch per band class (contiguous after the sort).  The launches of a wave are independent: they go to
             // round-robin auxiliary streams (fork / join with events) and each gets its own work counter.
             int q0 = 0, nlaunch = 0;

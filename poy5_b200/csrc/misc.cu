@@ -72,6 +72,34 @@ cudaError_t launch_band_finish(poy_ctx *ctx, const BandJob *d_jobs, int njobs, P
     return cudaGetLastError();
 }
 
+// ---- stale state across threshold doublings (pairs with gap-bit symbols) -----------------------------------
+// A probe fill changes the EB row / EH[0][0] the next fill inherits; if its threshold has to be repeated with
+// direction bytes, the repeat must start from what the probe started from.  One warp per job: probe jobs save,
+// repeat jobs restore, everything else returns.
+__global__ void __launch_bounds__(256) k_stale_snapshot(const BandJob *__restrict__ jobs, int njobs, PairState *state, int *eb, int *snap) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= njobs) return;
+    const BandJob J = jobs[t];
+    if (J.swaped & 4) return;                       // gap-free pairs have no stale state
+    const bool save = (J.swaped & 8) && !(J.swaped & 16), restore = (J.swaped & 32) != 0;
+    if (!save && !restore) return;
+    int *a = eb + J.eb_off, *b = snap + J.eb_off;
+    PairState *st = state + J.pair;
+    if (save) {
+        for (int j = lane; j <= J.lastj; j += 32) b[j] = a[j];
+        if (lane == 0) st->eh00_snap = st->eh00;
+    } else {
+        for (int j = lane; j <= J.lastj; j += 32) a[j] = b[j];
+        if (lane == 0) st->eh00 = st->eh00_snap;
+    }
+}
+cudaError_t launch_stale_snapshot(poy_ctx *ctx, const BandJob *d_jobs, int njobs, PairState *d_state, int *d_eb, int *d_eb_snap) {
+    if (njobs <= 0) return cudaSuccess;
+    k_stale_snapshot<<<(njobs + 7) / 8, 256, 0, ctx->stream>>>(d_jobs, njobs, d_state, d_eb, d_eb_snap);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
 __global__ void k_gather_cost(const PairState *__restrict__ state, int n, int *cost) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n) cost[p] = state[p].cost;
