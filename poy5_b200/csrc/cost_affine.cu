@@ -300,15 +300,21 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
         }
         int dM = jb >= 1 ? GO : M0;                       // M'(0, jb): diagonal predecessor of slot 0 in row 1
         int oCB = POY_INF, oEH = POY_INF, oM = POY_INF;
-        unsigned rk = 0, win = 0;
-        int4 bnext = make_int4(0, 0, 0, 0);
-        if (b > 0 && lane == 0) bnext = bin[1];
+        // Row codes and the boundary column of the previous block are consumed by lane 0 one row per step; both are
+        // fetched 32 rows at a time with one coalesced load per lane, a whole window (32 steps) ahead of their
+        // use, and handed to lane 0 by shuffle -- no load sits on the critical path of a step.
+        unsigned rk = 0;
+        auto load_win = [&](int w) { const int r = 32 * w + lane + 1; return rp[r <= lasti ? r : lasti] >> 28; };
+        auto load_bnd = [&](int w) { const int r = 32 * w + lane + 1; return b > 0 ? bin[r <= lasti ? r : lasti] : make_int4(0, 0, 0, 0); };
+        unsigned win = 0, win_next = load_win(0);
+        int4 bw = make_int4(0, 0, 0, 0), bw_next = load_bnd(0);
 
         const int nsteps = lasti + 31;
         for (int s = 0; s < nsteps; ++s) {
-            if ((s & 31) == 0) {                          // next 32 packed rows, one coalesced load
-                const int r = s + lane + 1;
-                win = rp[r <= lasti ? r : lasti] >> 28;
+            if ((s & 31) == 0) {
+                win = win_next; bw = bw_next;
+                win_next = load_win((s >> 5) + 1);
+                bw_next = load_bnd((s >> 5) + 1);
             }
             const int i = s - lane + 1;
             int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
@@ -317,16 +323,17 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
             unsigned rprev = __shfl_up_sync(0xffffffffu, rk, 1);
             const unsigned rfirst = __shfl_sync(0xffffffffu, win, s & 31);
             rk = lane == 0 ? rfirst : rprev;              // row i's table row travels down the lanes
+            if (b > 0) {                                  // (uniform) boundary column of row s + 1 for lane 0
+                const int bx = __shfl_sync(0xffffffffu, bw.x, s & 31);
+                const int by = __shfl_sync(0xffffffffu, bw.y, s & 31);
+                const int bz = __shfl_sync(0xffffffffu, bw.z, s & 31);
+                if (lane == 0) { lCB = bx; lEH = by; lM = bz; }
+            } else if (lane == 0) {                       // column 0: CB = EH = INF, EV'[i][0] = M'[i][0] = GO
+                lCB = POY_INF; lEH = POY_INF; lM = GO;
+            }
             if (i >= 1) {
                 const unsigned irow = rk;
-                if (lane == 0) {
-                    if (b == 0) {                         // column 0: CB = EH = INF, EV'[i][0] = M'[i][0] = GO
-                        lCB = POY_INF; lEH = POY_INF; lM = GO;
-                    } else {
-                        lCB = bnext.x; lEH = bnext.y; lM = bnext.z;
-                        bnext = bin[i < lasti ? i + 1 : lasti];
-                    }
-                }
+                int mD = dM;
                 // Three passes, each of which overwrites its state array in place (no register copies at the loop
                 // back edge): EV from the old CB, then CB from the old M, then the EH chain and the new M.
 #pragma unroll
@@ -339,7 +346,7 @@ __device__ __forceinline__ void cost_pair_gf(const int *s_tab_i, const CostJob &
                     int diag;
                     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(irow), "r"(GF_ROW_BYTES_U), "r"(c_off[c]));
                     asm("ld.shared.s32 %0, [%1];" : "=r"(diag) : "r"(addr));
-                    CBu[c] = (c == 0 ? dM : Mu[c > 0 ? c - 1 : 0]) + diag;
+                    CBu[c] = (c == 0 ? mD : Mu[c > 0 ? c - 1 : 0]) + diag;
                 }
                 int cbL = lCB, ehL = lEH;
 #pragma unroll
@@ -402,8 +409,11 @@ cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *p
     // overheads) pays off once the sequences span more than one such block; 16 wastes fewer lanes on short pairs.
     // POY_COST_C=16|32 overrides (tuning knob).
     int cg = wide ? 32 : 16;
-    { const char *e = getenv("POY_COST_C"); if (e && (atoi(e) == 16 || atoi(e) == 32)) cg = atoi(e); }
-    if (cg == 32)
+    { const char *e = getenv("POY_COST_C"); if (e && (atoi(e) == 16 || atoi(e) == 24 || atoi(e) == 32)) cg = atoi(e); }
+    if (cg == 24)
+        k_cost_affine<24, 3><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
+                                                               d_counter, d_bound, bound_stride, d_cost);
+    else if (cg == 32)
         k_cost_affine<32, 2><<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_rowpk, pool->d_colp, pool->d_g0, d_jobs, njobs,
                                                                d_counter, d_bound, bound_stride, d_cost);
     else
