@@ -18,6 +18,7 @@ inside the timed region).
 import argparse
 import ctypes
 import json
+from concurrent.futures import ThreadPoolExecutor
 import os
 import subprocess
 import sys
@@ -247,7 +248,17 @@ def main():
             d2h += 2 * 4 * n + 16 * n + 4 * out_total
     max_out = max(w["out_total"] for w in work)
     d_outs = [torch.empty(max_out + 256, dtype=torch.uint8, device=dev) for _ in range(4)]
-    h_outs = [torch.empty(max_out + 256, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+    # e2e: two host threads, each with its own context (stream, arenas) and pinned result buffers, take
+    # alternate chunks, so that one chunk's copies and host-side scheduling overlap the other's kernels
+    E2E_THREADS = 1 if args.no_e2e else 2
+    lanes = []
+    free_b, _total_b = torch.cuda.mem_get_info(dev)
+    arena = int(min(48 << 30, 0.30 * free_b))      # direction-byte arena per context (two contexts share the HBM)
+    for t in range(E2E_THREADS):
+        c = ctx if t == 0 else pb.Context(local_rank)
+        c.set_arena_limit(arena)
+        lanes.append(dict(ctx=c, cm=cm if t == 0 else pb.CostModel(c, t2d.full),
+                          h_outs=[torch.empty(max_out + 256, dtype=torch.uint8, pin_memory=True) for _ in range(4)]))
     best = torch.zeros(1, dtype=torch.int64, device=dev)
 
     seg_events = {}
@@ -278,21 +289,29 @@ def main():
                 seg_events[wi] = (e0, e1, e2)
             pool.close()
 
-    def step_e2e():
-        res = 0
-        for w in work:
-            pool = pb.Pool(ctx, data=w["data"], offsets=w["off"])
-            cost0 = sequence.Align.cost_2(ctx, cm, pool, w["ia"], w["ib"])
+    def e2e_lane(lane, items):
+        c, m, h_outs = lane["ctx"], lane["cm"], lane["h_outs"]
+        res = 1 << 60
+        for w in items:
+            pool = pb.Pool(c, data=w["data"], offsets=w["off"])
+            cost0 = sequence.Align.cost_2(c, m, pool, w["ia"], w["ib"])
             n = w["n"]
             cost1 = np.empty(n, np.int32); out_len = np.empty(4 * n, np.int32)
-            ctx.check(ctx.L.poy_batch_align_affine(ctx.h, cm.h, pool.h, n, _ptr(w["si"]), _ptr(w["sj"]), _ptr(w["swaped"]),
-                                                   _ptr(w["out_off"]), _ptr(cost1),
-                                                   ctypes.c_void_p(h_outs[0].data_ptr()), ctypes.c_void_p(h_outs[1].data_ptr()),
-                                                   ctypes.c_void_p(h_outs[2].data_ptr()), ctypes.c_void_p(h_outs[3].data_ptr()),
-                                                   _ptr(out_len), None))
-            res = min(int(cost0.min()), int(cost1.min()))
+            c.check(c.L.poy_batch_align_affine(c.h, m.h, pool.h, n, _ptr(w["si"]), _ptr(w["sj"]), _ptr(w["swaped"]),
+                                               _ptr(w["out_off"]), _ptr(cost1),
+                                               ctypes.c_void_p(h_outs[0].data_ptr()), ctypes.c_void_p(h_outs[1].data_ptr()),
+                                               ctypes.c_void_p(h_outs[2].data_ptr()), ctypes.c_void_p(h_outs[3].data_ptr()),
+                                               _ptr(out_len), None))
+            res = min(res, int(cost0.min()), int(cost1.min()))
             pool.close()
         return res
+
+    def step_e2e():
+        # longest chunks first, dealt alternately (the ctypes calls release the GIL)
+        order = sorted(work, key=lambda w: -w["cells"])
+        with ThreadPoolExecutor(len(lanes)) as ex:
+            futs = [ex.submit(e2e_lane, lanes[t], order[t::len(lanes)]) for t in range(len(lanes))]
+            return min(f.result() for f in futs)
 
     def barrier():
         if world > 1:

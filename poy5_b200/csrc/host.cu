@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <vector>
 #include <chrono>
+#include <atomic>
 #include "common.cuh"
 
 // ---- error plumbing ---------------------------------------------------------------------
@@ -21,6 +22,10 @@ static poy_status cuda_fail(poy_ctx *ctx, cudaError_t e, const char *where) {
     return fail(ctx, e == cudaErrorMemoryAllocation ? POY_ERR_NOMEM : POY_ERR_CUDA, buf);
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+// Every entry point binds the calling thread to the context's device first: host threads other than the one that
+// created the context start out on device 0.
+static inline void bind_device(const poy_ctx *ctx) { if (ctx) cudaSetDevice(ctx->device); }
 
 extern "C" const char *poy_status_string(poy_status s) {
     switch (s) {
@@ -74,6 +79,7 @@ extern "C" poy_status poy_ctx_create(int device, void *stream, poy_ctx **out) {
 }
 
 extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
+    bind_device(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -86,11 +92,13 @@ extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
     free(ctx);
 }
 extern "C" poy_status poy_ctx_set_arena_limit(poy_ctx *ctx, uint64_t bytes) {
+    bind_device(ctx);
     if (!ctx || bytes < (1u << 20)) return POY_ERR_ARG;
     ctx->arena_limit = bytes;
     return POY_OK;
 }
 extern "C" poy_status poy_ctx_synchronize(poy_ctx *ctx) {
+    bind_device(ctx);
     if (!ctx) return POY_ERR_ARG;
     CK(cudaStreamSynchronize(ctx->stream));
     return POY_OK;
@@ -309,6 +317,7 @@ extern "C" int32_t poy_cm_get_closest(const poy_cm_host *cm, int32_t a, int32_t 
 }
 
 extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm **out) {
+    bind_device(ctx);
     if (!ctx || !h || !out) return POY_ERR_ARG;
     *out = nullptr;
     int max_entry = 0;
@@ -322,7 +331,7 @@ extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm *
     }
     if (h->gap_open < 0 || max_entry >= POY_INF || h->gap_open >= POY_INF)
         return fail(ctx, POY_ERR_COST_RANGE, "cost entry or gap opening >= HIGH_NUM");
-    static uint64_t next_uid = 0;
+    static std::atomic<uint64_t> next_uid{0};   // contexts may be driven from different host threads
     poy_cm *cm = new poy_cm;
     cm->uid = ++next_uid;
     cm->h = *h;
@@ -350,6 +359,7 @@ extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm *
     return POY_OK;
 }
 extern "C" void poy_cm_free(poy_ctx *ctx, poy_cm *cm) {
+    bind_device(ctx);
     if (!cm) return;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     cudaFree(cm->d);
@@ -369,6 +379,7 @@ static poy_status pool_alloc(poy_ctx *ctx, poy_pool *p) {
 }
 
 extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
+    bind_device(ctx);
     if (!p) return;
     // no device sync: the blocks go back to the context's cache and are only reused in stream order
     if (p->owns_data) { cached_free(ctx, p->d_data, p->caps[6]); cached_free(ctx, p->d_off, p->caps[7]); }
@@ -395,6 +406,7 @@ static poy_status pool_new(poy_ctx *ctx, const int64_t *h_off, int32_t nseq, poy
 }
 
 extern "C" poy_status poy_pool_upload(poy_ctx *ctx, const uint8_t *data, const int64_t *offsets, int32_t nseq, poy_pool **out) {
+    bind_device(ctx);
     if (!ctx || !data || !offsets || !out) return POY_ERR_ARG;
     *out = nullptr;
     poy_pool *p;
@@ -414,6 +426,7 @@ extern "C" poy_status poy_pool_upload(poy_ctx *ctx, const uint8_t *data, const i
 
 extern "C" poy_status poy_pool_from_device(poy_ctx *ctx, const uint8_t *d_data, const int64_t *d_offsets,
                                            const int64_t *h_offsets, int32_t nseq, poy_pool **out) {
+    bind_device(ctx);
     if (!ctx || !d_data || !d_offsets || !h_offsets || !out) return POY_ERR_ARG;
     *out = nullptr;
     poy_pool *p;
@@ -455,6 +468,7 @@ static poy_status domain_check(poy_ctx *ctx, const poy_cm *cm, int64_t len_sum) 
 // ---- batch cost-only affine --------------------------------------------------------------------------
 extern "C" poy_status poy_batch_cost_affine_dev(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
                                                 const int32_t *d_a, const int32_t *d_b, int32_t *d_cost) {
+    bind_device(ctx);
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!d_a || !d_b || !d_cost))) return POY_ERR_ARG;
     if (cm->h.cost_model_type != 1) return fail(ctx, POY_ERR_MODEL, "cost_affine needs an affine cost model");
     if (n == 0) return POY_OK;
@@ -478,6 +492,7 @@ extern "C" poy_status poy_batch_cost_affine_dev(poy_ctx *ctx, const poy_cm *cm, 
 
 extern "C" poy_status poy_batch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
                                             const int32_t *a, const int32_t *b, int32_t *cost) {
+    bind_device(ctx);
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!a || !b || !cost))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     for (int p = 0; p < n; ++p)
@@ -795,6 +810,7 @@ extern "C" poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm,
                                                  const int32_t *h_si, const int32_t *h_sj, const int64_t *d_out_off,
                                                  int32_t *d_cost, uint8_t *d_median, uint8_t *d_medianwg,
                                                  uint8_t *d_resi, uint8_t *d_resj, int32_t *d_out_len, int32_t *d_stats) {
+    bind_device(ctx);
     (void)d_si; (void)d_sj;
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!h_si || !h_sj))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
@@ -821,6 +837,7 @@ extern "C" poy_status poy_batch_align_affine(poy_ctx *ctx, const poy_cm *cm, con
                                              const int32_t *si, const int32_t *sj, const uint8_t *swaped,
                                              const int64_t *out_off, int32_t *cost, uint8_t *median, uint8_t *medianwg,
                                              uint8_t *resi, uint8_t *resj, int32_t *out_len, int32_t *stats) {
+    bind_device(ctx);
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!si || !sj))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     const bool want_trace = median || medianwg || resi || resj || out_len;
@@ -868,6 +885,7 @@ extern "C" poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, con
                                              const int32_t *s1, const int32_t *s2, const int32_t *deltawh,
                                              const uint8_t *swaped, const int64_t *out_off, int32_t *cost, uint8_t *r1,
                                              uint8_t *r2, int32_t *out_len, int32_t *stats) {
+    bind_device(ctx);
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!s1 || !s2 || !deltawh))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     const bool want_trace = r1 || r2 || out_len;
@@ -907,6 +925,7 @@ extern "C" poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, con
 
 extern "C" poy_status poy_batch_cost_linear(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
                                             const int32_t *s1, const int32_t *s2, const int32_t *deltawh, int32_t *cost) {
+    bind_device(ctx);
     return poy_batch_align_linear(ctx, cm, pool, n, s1, s2, deltawh, nullptr, nullptr, cost, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -944,6 +963,7 @@ poy_status stage_rows(poy_ctx *ctx, int n, const uint8_t *rows_a, const uint8_t 
 extern "C" poy_status poy_batch_median_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
                                          const int64_t *off, const int32_t *len, int32_t with_gaps, const int64_t *out_off,
                                          uint8_t *out, int32_t *out_len) {
+    bind_device(ctx);
     if (!ctx || !cm || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !out_off || !out || !out_len))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     RowsOnDevice r;
@@ -958,6 +978,7 @@ extern "C" poy_status poy_batch_median_2(poy_ctx *ctx, const poy_cm *cm, int32_t
 
 extern "C" poy_status poy_batch_union(poy_ctx *ctx, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b, const int64_t *off,
                                       const int32_t *len, uint8_t *out) {
+    bind_device(ctx);
     if (!ctx || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !out))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     RowsOnDevice r;
@@ -971,6 +992,7 @@ extern "C" poy_status poy_batch_union(poy_ctx *ctx, int32_t n, const uint8_t *ro
 
 extern "C" poy_status poy_batch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
                                              const int64_t *off, const int32_t *len, int32_t use_worst, int32_t *cost) {
+    bind_device(ctx);
     if (!ctx || !cm || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !cost))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     RowsOnDevice r;
@@ -985,6 +1007,7 @@ extern "C" poy_status poy_batch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int
 extern "C" poy_status poy_batch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
                                            const int64_t *off, const int32_t *len, const int64_t *out_off, uint8_t *out,
                                            int32_t *out_len) {
+    bind_device(ctx);
     if (!ctx || !cm || n < 0 || (n > 0 && (!rows_a || !rows_b || !off || !len || !out_off || !out || !out_len))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     RowsOnDevice r;
@@ -1000,6 +1023,7 @@ extern "C" poy_status poy_batch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int32
 
 // ---- micro-benchmark ---------------------------------------------------------------------------------------
 extern "C" poy_status poy_microbench_int(poy_ctx *ctx, int32_t kind, double *ops_per_second, double *sm_clock_mhz) {
+    bind_device(ctx);
     if (!ctx || !ops_per_second) return POY_ERR_ARG;
     void *v;
     poy_status s = scratch(ctx, SL_MISC, 1 << 20, &v);
