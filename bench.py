@@ -191,6 +191,8 @@ def main():
         print(json.dumps(line))
         return 0
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
     import torch
     import torch.distributed as dist
     import poy5_b200 as pb
