@@ -159,8 +159,12 @@ __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed)
 // pair) that only share the replicated cost table.
 // DIR = false is the "probe" fill: same states, gap counters and stale-row side effects, but no direction bytes
 // (the whole byte assembly is dead code then).  The host uses it for fills it expects not to be the last one.
+// resident CTAs the register allocation aims at: the replicated table (32 KB) allows 6 per SM; the 4-warp class of
+// gap-free pairs is the one where a few registers decide between 4 and 5
+template <int NW, bool GFK> struct MinBlocks { static constexpr int v = (GFK && NW == 4) ? 5 : 1; };
+
 template <int D, int NW, int WPB, bool GFK, bool DIR>
-__global__ void __launch_bounds__(WPB * 32)
+__global__ void __launch_bounds__(WPB * 32, MinBlocks<NW, GFK>::v)
 k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
         const int *__restrict__ h0v, const int *__restrict__ g0v, const unsigned *__restrict__ rowpk,
         const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state, int *ebrow, uint8_t *dir) {
