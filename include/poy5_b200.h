@@ -162,7 +162,10 @@ POY_API poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, const 
  *  poy_batch_union        algn_CAML_union (src/algn.c:3657-3678): out has the layout of the inputs
  *  poy_batch_aligned_cost algn_CAML_verify_2 (use_worst = 0) / algn_CAML_worst_2 (use_worst = 1)
  *                         (src/algn.c:3003-3130) = Sequence.Align.max_cost_2 / verify
- *  poy_batch_ancestor_2   algn_CAML_ancestor_2 (src/algn.c:3603-3626,3742): capacity len[p] + 1 */
+ *  poy_batch_ancestor_2   algn_CAML_ancestor_2 (src/algn.c:3603-3626,3742): capacity len[p] + 1
+ *  poy_batch_closest      the column map of Sequence.Align.closest (src/sequence.ml:1180-1237): column i becomes
+ *                         Cost_matrix.Two_D.get_closest cm parent.(i) mine.(i) (src/cost_matrix.ml:1387-1428), then
+ *                         remove_gaps2 (src/sequence.ml:209-222); capacity len[p] + 1 */
 POY_API poy_status poy_batch_median_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
                                       const int64_t *off, const int32_t *len, int32_t with_gaps, const int64_t *out_off,
                                       uint8_t *out, int32_t *out_len);
@@ -173,6 +176,8 @@ POY_API poy_status poy_batch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int32_
 POY_API poy_status poy_batch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
                                         const int64_t *off, const int32_t *len, const int64_t *out_off, uint8_t *out,
                                         int32_t *out_len);
+POY_API poy_status poy_batch_closest(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_parent, const uint8_t *rows_mine,
+                                     const int64_t *off, const int32_t *len, const int64_t *out_off, uint8_t *out, int32_t *out_len);
 
 /* ---- INT32 / DPX issue-rate micro-benchmark (roofline denominator) ---------
  * Runs independent chains of one instruction class at full occupancy and

@@ -8,13 +8,14 @@
 #include "common.cuh"
 
 // warp per pair: medians of all columns; without gaps the pure-gap medians are squeezed out and the
-// leading gap restored (ballot compaction keeps the order)
+// leading gap restored (ballot compaction keeps the order).  with_gaps == 2 maps the columns through the
+// get_closest table instead (a = parent row, b = own row) and squeezes the gaps out the same way.
 __global__ void __launch_bounds__(128)
 k_median_2(const DevCM *__restrict__ cm, int n, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
            const int64_t *__restrict__ off, const int *__restrict__ len, int with_gaps, const int64_t *__restrict__ out_off,
            uint8_t *out, int *out_len) {
     __shared__ uint8_t s_med[1024];
-    for (int x = threadIdx.x; x < 1024; x += blockDim.x) s_med[x] = cm->median32[x];
+    for (int x = threadIdx.x; x < 1024; x += blockDim.x) s_med[x] = with_gaps == 2 ? cm->closest32[x] : cm->median32[x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -23,11 +24,11 @@ k_median_2(const DevCM *__restrict__ cm, int n, const uint8_t *__restrict__ a, c
     uint8_t *o = out + out_off[p];
     const int L = len[p];
     int w = 0;
-    if (!with_gaps) { if (lane == 0) o[0] = POY_GAP; w = 1; }
+    if (with_gaps != 1) { if (lane == 0) o[0] = POY_GAP; w = 1; }
     for (int x0 = 0; x0 < L; x0 += 32) {
         const int x = x0 + lane;
         int m = 0; bool keep = false;
-        if (x < L) { m = s_med[((ra[x] & 31) << 5) + (rb[x] & 31)]; keep = with_gaps || m != POY_GAP; }
+        if (x < L) { m = s_med[((ra[x] & 31) << 5) + (rb[x] & 31)]; keep = with_gaps == 1 || m != POY_GAP; }
         const unsigned mask = __ballot_sync(0xffffffffu, keep);
         if (keep) o[w + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)m;
         w += __popc(mask);

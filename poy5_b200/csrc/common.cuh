@@ -15,6 +15,7 @@ struct DevCM {
     int cost32[1024];    // full table (linear-gap kernels, worst/verify)
     int worst32[1024];
     uint8_t median32[1024];
+    uint8_t closest32[1024]; // Cost_matrix.Two_D.get_closest a b at [(a << 5) + b] (src/cost_matrix.ml:1387-1428)
     int prepend[32];
     int tail[32];
     int gapext[32];      // cost[a][gap]  (HAS_GAP_EXTENSION, src/algn.c:1220)

@@ -343,6 +343,7 @@ extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm *
     memcpy(img->cost32, h->cost, sizeof img->cost32);
     memcpy(img->worst32, h->worst, sizeof img->worst32);
     memcpy(img->median32, h->median, sizeof img->median32);
+    for (int a = 1; a < 32; ++a) for (int b = 1; b < 32; ++b) img->closest32[(a << 5) + b] = (uint8_t)poy_cm_get_closest(h, a, b);
     memcpy(img->prepend, h->prepend, sizeof img->prepend);
     memcpy(img->tail, h->tail, sizeof img->tail);
     for (int a = 0; a < 32; ++a) img->gapext[a] = h->cost[(a << 5) + GAPC];
@@ -970,6 +971,24 @@ extern "C" poy_status poy_batch_median_2(poy_ctx *ctx, const poy_cm *cm, int32_t
     poy_status s = stage_rows(ctx, n, rows_a, rows_b, off, len, out_off, 1, &r);
     if (s != POY_OK) return s;
     CK(launch_median_2(ctx, cm, n, r.a, r.b, r.off, r.len, with_gaps, r.out_off, r.out, r.res));
+    CK(cudaMemcpyAsync(out, r.out, (size_t)r.out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_len, r.res, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return POY_OK;
+}
+
+// Sequence.Align.closest, the column-wise half (src/sequence.ml:1217-1228): rows_parent / rows_mine are the two
+// aligned rows, every column becomes get_closest cm parent.(i) mine.(i), gaps are squeezed out and the leading gap
+// is put back (remove_gaps2, src/sequence.ml:209-222).
+extern "C" poy_status poy_batch_closest(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_parent, const uint8_t *rows_mine,
+                                        const int64_t *off, const int32_t *len, const int64_t *out_off, uint8_t *out, int32_t *out_len) {
+    bind_device(ctx);
+    if (!ctx || !cm || n < 0 || (n > 0 && (!rows_parent || !rows_mine || !off || !len || !out_off || !out || !out_len))) return POY_ERR_ARG;
+    if (n == 0) return POY_OK;
+    RowsOnDevice r;
+    poy_status s = stage_rows(ctx, n, rows_parent, rows_mine, off, len, out_off, 1, &r);
+    if (s != POY_OK) return s;
+    CK(launch_median_2(ctx, cm, n, r.a, r.b, r.off, r.len, 2, r.out_off, r.out, r.res));
     CK(cudaMemcpyAsync(out, r.out, (size_t)r.out_total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(out_len, r.res, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

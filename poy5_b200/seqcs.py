@@ -105,3 +105,13 @@ def median_3_union(ctx, cm2, pool, parent, aligned_a, aligned_b):
     tmp.close()
     return dict(sequence=med, cost=np.asarray(r["cost"], np.int64), cost_max=mx.astype(np.int64),
                 aligned_parent=r["res_a"], aligned_union=r["res_b"])
+
+
+def to_single(ctx, h, pool, parent, mine):
+    """DOS.to_single (src/seqCS.ml:950-982): the single-assignment sequence of `mine` given its parent's.  An empty
+    `mine` stays empty (cost 0); an empty parent is replaced by `mine` itself; otherwise
+    Sequence.Align.closest parent mine c2_FULL.  Returns (list of sequences, int64 costs)."""
+    parent = np.ascontiguousarray(parent, np.int32).copy(); mine = np.ascontiguousarray(mine, np.int32)
+    empty = _is_empty(pool)
+    parent[empty[parent]] = mine[empty[parent]]
+    return sequence.closest(ctx, h.c2_full, pool, parent, mine)

@@ -216,3 +216,58 @@ def ancestor_2(ctx, cm, rows_a, rows_b):
     out_len = np.zeros(n, np.int32)
     ctx.check(ctx.L.poy_batch_ancestor_2(ctx.h, cm.h, n, _ptr(a), _ptr(b), _ptr(off), _ptr(lens), _ptr(out_off), _ptr(out), _ptr(out_len)))
     return [out[out_off[p]:out_off[p] + out_len[p]] for p in range(n)]
+
+
+def closest_columns(ctx, cm, rows_parent, rows_mine):
+    """The column map of Sequence.Align.closest: get_closest cm parent.(i) mine.(i) for every column of the two
+    aligned rows, gaps squeezed out, leading gap restored (src/sequence.ml:1217-1228, 209-222)."""
+    a, b, off, lens = _pack_rows(rows_parent, rows_mine)
+    n = len(lens)
+    out_off = off + np.arange(n, dtype=np.int64)
+    out = np.zeros(int(lens.sum()) + n + 1, np.uint8)
+    out_len = np.zeros(n, np.int32)
+    ctx.check(ctx.L.poy_batch_closest(ctx.h, cm.h, n, _ptr(a), _ptr(b), _ptr(off), _ptr(lens), _ptr(out_off), _ptr(out), _ptr(out_len)))
+    return [out[out_off[p]:out_off[p] + out_len[p]] for p in range(n)]
+
+
+def closest(ctx, cm, pool, parent, mine):
+    """Batch Sequence.Align.closest parent mine cm (src/sequence.ml:1180-1237), bitset alphabets with combinations
+    (DNA): the single-assignment of `mine` closest to `parent`.  Per pair: empty `mine` -> (mine, 0); identical
+    sequences -> gap bits stripped, columns mapped, cost 0; otherwise align_2, map the columns through
+    get_closest, squeeze the gaps out and RE-COST the result against the parent with cost_2 ("the set distance
+    calculation is an upper bound in the affine gap cost model").  Returns (list of sequences, int64 costs)."""
+    from .api import Pool
+    parent = np.ascontiguousarray(parent, np.int32); mine = np.ascontiguousarray(mine, np.int32)
+    n = len(parent)
+    seqs = [pool.data[pool.offsets[s]:pool.offsets[s + 1]] for s in range(pool.nseq)]
+    out = [None] * n
+    cost = np.zeros(n, np.int64)
+    same, diff = [], []
+    for p in range(n):
+        m = seqs[mine[p]]
+        if len(m) == 0 or np.all(m == 16):                      # Sequence.is_empty
+            out[p] = m.copy()
+        elif len(seqs[parent[p]]) == len(m) and np.array_equal(seqs[parent[p]], m):
+            same.append(p)
+        else:
+            diff.append(p)
+    if same:
+        strip = lambda s: np.concatenate([s[:1], s[1:] & 15]).astype(np.uint8)
+        rows = [strip(seqs[mine[p]]) for p in same]
+        for p, r in zip(same, closest_columns(ctx, cm, rows, rows)):
+            out[p] = r
+    if diff:
+        d = np.asarray(diff)
+        r = Align.align_2(ctx, cm, pool, parent[d], mine[d])
+        res = closest_columns(ctx, cm, r["res_a"], r["res_b"])
+        for p, s in zip(diff, res):
+            out[p] = s
+        # re-cost: a pool holding the parents and the new single-assignment sequences
+        both = [seqs[parent[p]] for p in diff] + res
+        lens = np.fromiter((len(s) for s in both), np.int64, len(both))
+        off = np.zeros(len(both) + 1, np.int64); np.cumsum(lens, out=off[1:])
+        p2 = Pool(ctx, data=np.concatenate(both).astype(np.uint8), offsets=off)
+        k = len(diff)
+        cost[d] = Align.cost_2(ctx, cm, p2, np.arange(k, dtype=np.int32), np.arange(k, 2 * k, dtype=np.int32))
+        p2.close()
+    return out, cost

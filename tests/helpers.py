@@ -43,3 +43,28 @@ def oracle_align(P, pc, a, b):
     si, sj = (b, a) if sw else (a, b)
     c, m, w, ri, rj = P.align_affine(pc, si, sj, sw)
     return (c, m, w, rj, ri) if sw else (c, m, w, ri, rj)
+
+
+def oracle_closest(P, cmo, pc, m, parent, mine, linear_align=None):
+    """Sequence.Align.closest parent mine (src/sequence.ml:1180-1237) restated on top of the oracle: align_2,
+    get_closest per column, remove_gaps2, re-cost with cost_2.  `m` is the python cost-matrix object of
+    oracle.cost_matrix_oracle, `pc` its handle in the C oracle, `linear_align(a, b) -> (cost, ra, rb)` the
+    Align.align_2 of the linear-gap model.  -> (sequence, cost)"""
+    parent = np.asarray(parent, np.uint8); mine = np.asarray(mine, np.uint8)
+    if len(mine) == 0 or bool((mine == 16).all()):
+        return mine.copy(), 0
+    same = len(parent) == len(mine) and bool((parent == mine).all())
+    if same:
+        ra = np.concatenate([parent[:1], parent[1:] & 15]).astype(np.uint8)
+        rb = ra.copy()
+    elif m.cost_model_type == 1:
+        _, _, _, ra, rb = oracle_align(P, pc, parent, mine)
+    else:
+        _, ra, rb = linear_align(parent, mine)
+    col = [cmo.get_closest(m, int(a), int(b)) for a, b in zip(ra, rb)]
+    res = np.array([16] + [c for c in col if c != 16], np.uint8)
+    if same:
+        return res, 0
+    if m.cost_model_type == 1:
+        return res, int(P.cost_affine(pc, parent, res))
+    return res, int(linear_align(parent, res)[0])

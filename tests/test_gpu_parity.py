@@ -274,6 +274,48 @@ def test_dos_median_and_distance(ctx, port, go):
 
 
 @pytest.mark.parametrize("go", [None, 3])
+def test_closest_and_to_single(ctx, port, go):
+    """Sequence.Align.closest / DOS.to_single (src/sequence.ml:1180-1237, src/seqCS.ml:950-982): single assignment of
+    an ambiguous node sequence given its parent; identical sequences, empty sequences and gap-bit symbols included"""
+    import poy5_b200 as pb
+    from poy5_b200 import sequence
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.seqcs import Heuristic, to_single
+    from tests.helpers import oracle_closest
+    t2d = Two_D.of_transformations_and_gaps(1, 2, go)
+    full, orig = cmo.dna_matrices(1, 2, go)
+    h = Heuristic(pb.CostModel(ctx, t2d.full), pb.CostModel(ctx, t2d.original))
+    pf = port.cm(full)
+    rng = np.random.default_rng(77)
+    seqs = []
+    n = 120
+    for t in range(n):
+        anc = synth.random_seq(rng, int(rng.integers(1, 150)))
+        par = synth.evolve(rng, anc, 0.08, 0.03)
+        mine = synth.decorate(rng, synth.evolve(rng, anc, 0.1, 0.04), 0.25, 0.1)   # ambiguity codes + gap bits
+        if t % 9 == 0:
+            par = mine.copy()                                   # identical sequences: the `comp` branch
+        if t % 10 == 3:
+            mine = np.zeros(0, np.uint8)                        # empty `mine`
+        if t % 10 == 6:
+            par = np.zeros(0, np.uint8)                         # empty parent: to_single aligns mine with itself
+        seqs += [synth.with_gap(par), synth.with_gap(mine)]
+    pool = pb.Pool(ctx, seqs)
+    ip = np.arange(0, 2 * n, 2, dtype=np.int32); im = ip + 1
+    lin = lambda a, b: _oracle_linear(port, pf, a, b)
+    got, cost = sequence.closest(ctx, h.c2_full, pool, ip, im)
+    for t in range(n):
+        es, ec = oracle_closest(port, cmo, pf, full, seqs[ip[t]], seqs[im[t]], lin)
+        assert np.array_equal(got[t], es) and cost[t] == ec, ("closest", t)
+    got, cost = to_single(ctx, h, pool, ip, im)
+    for t in range(n):
+        par = seqs[ip[t]] if not bool((seqs[ip[t]] == 16).all()) else seqs[im[t]]
+        es, ec = oracle_closest(port, cmo, pf, full, par, seqs[im[t]], lin)
+        assert np.array_equal(got[t], es) and cost[t] == ec, ("to_single", t)
+    pool.close()
+
+
+@pytest.mark.parametrize("go", [None, 3])
 def test_median_3_union(ctx, port, go):
     """config #3's live path: parent x union(children) alignment + median_2"""
     import poy5_b200 as pb
