@@ -271,3 +271,59 @@ def closest(ctx, cm, pool, parent, mine):
         cost[d] = Align.cost_2(ctx, cm, p2, np.arange(k, dtype=np.int32), np.arange(k, 2 * k, dtype=np.int32))
         p2.close()
     return out, cost
+
+
+def _algn_median(ctx, cm, seqs, ia, ib):
+    """`algn s1 s2` of Sequence.readjust (src/sequence.ml:2099-2120): cost and median of one alignment; affine ->
+    align_affine_3's median, otherwise align_2 + median_2.  One batch over a temporary pool of `seqs`."""
+    from .api import Pool
+    pool = Pool(ctx, seqs)
+    try:
+        if cm.host.cost_model_type == 1:
+            r = Align.align_affine_3(ctx, cm, pool, ia, ib, want=("median",))
+            return r["cost"].astype(np.int64), r["median"]
+        r = Align.align_2(ctx, cm, pool, ia, ib)
+        return r["cost"].astype(np.int64), median_2(ctx, cm, r["res_a"], r["res_b"], False)
+    finally:
+        pool.close()
+
+
+def readjust(ctx, cm, pool, a, b, parent):
+    """Batch Sequence.readjust a b _ cm parent (src/sequence.ml:2097-2156, the `Algn_Normal` branch): the
+    approximate three-way re-optimisation of an interior node.  Per node: the medians ab, bc, ac (c = parent), each
+    re-aligned with the third sequence; the cheapest composition decides which pair of (sequence, median) goes
+    through Align.closest; the new sequence is then aligned with both children and the parent.
+    Returns dict(cost3, cost2, sequence, aligned_mp) like the reference's tuple (its last three members are the
+    same aligned row)."""
+    from .api import Pool
+    a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32); c = np.ascontiguousarray(parent, np.int32)
+    n = len(a)
+    sq = lambda idx: [pool.seq(int(x)) for x in idx]
+    A, B, Cc = sq(a), sq(b), sq(c)
+    ar = np.arange(n, dtype=np.int32)
+    # stage 1: ab, bc, ac in one batch over [A | B | C]
+    c1, m1 = _algn_median(ctx, cm, A + B + Cc, np.concatenate([ar, ar + n, ar]), np.concatenate([ar + n, ar + 2 * n, ar + 2 * n]))
+    cab, cbc, cac = c1[:n], c1[n:2 * n], c1[2 * n:]
+    ab, bc, ac = m1[:n], m1[n:2 * n], m1[2 * n:]
+    # stage 2: (ab, c), (bc, a), (ac, b) over [ab | bc | ac | C | A | B]
+    c2, _ = _algn_median(ctx, cm, list(ab) + list(bc) + list(ac) + Cc + A + B, np.arange(3 * n, dtype=np.int32),
+                         np.arange(3 * n, 6 * n, dtype=np.int32))
+    cabc, cbca, cacb = c2[:n] + cab, c2[n:2 * n] + cbc, c2[2 * n:] + cac
+    # make_center's choice: closest c ab | closest b ac | closest a bc
+    first, second = [], []
+    for p in range(n):
+        if cabc[p] <= cbca[p]:
+            pick = (Cc[p], ab[p]) if cabc[p] <= cacb[p] else (B[p], ac[p])
+        else:
+            pick = (A[p], bc[p]) if cbca[p] < cacb[p] else (B[p], ac[p])
+        first.append(pick[0]); second.append(pick[1])
+    p3 = Pool(ctx, first + second)
+    new, _ = closest(ctx, cm, p3, ar, ar + n)
+    p3.close()
+    # stage 3: align_2 of the new sequence with both children and the parent over [A | B | C | new]
+    p4 = Pool(ctx, A + B + Cc + list(new))
+    r = Align.align_2(ctx, cm, p4, np.arange(3 * n, dtype=np.int32), np.concatenate([ar, ar, ar]) + 3 * n)
+    p4.close()
+    cost = r["cost"].astype(np.int64)
+    cost2 = cost[:n] + cost[n:2 * n]
+    return {"cost3": cost2 + cost[2 * n:], "cost2": cost2, "sequence": list(new), "aligned_mp": r["res_b"][2 * n:]}

@@ -68,3 +68,33 @@ def oracle_closest(P, cmo, pc, m, parent, mine, linear_align=None):
     if m.cost_model_type == 1:
         return res, int(P.cost_affine(pc, parent, res))
     return res, int(linear_align(parent, res)[0])
+
+
+def oracle_readjust(P, cmo, pc, m, a, b, parent, linear_align=None):
+    """Sequence.readjust (src/sequence.ml:2097-2156, Algn_Normal) restated on top of the oracle.
+    -> (cost3, cost2, new sequence, aligned row of the new sequence against the parent)"""
+    def algn(s1, s2):
+        if m.cost_model_type == 1:
+            c, med, _, _, _ = oracle_align(P, pc, s1, s2)
+            return int(c), med
+        c, r1, r2 = linear_align(s1, s2)
+        return int(c), P.median_2(pc, r1, r2, False)
+
+    def align_2(s1, s2):
+        if m.cost_model_type == 1:
+            c, _, _, r1, r2 = oracle_align(P, pc, s1, s2)
+            return r1, r2, int(c)
+        c, r1, r2 = linear_align(s1, s2)
+        return r1, r2, int(c)
+    c = parent
+    cab, ab = algn(a, b); cbc, bc = algn(b, c); cac, ac = algn(a, c)
+    cabc = algn(ab, c)[0] + cab; cbca = algn(bc, a)[0] + cbc; cacb = algn(ac, b)[0] + cac
+    if cabc <= cbca:
+        x, y = (c, ab) if cabc <= cacb else (b, ac)
+    else:
+        x, y = (a, bc) if cbca < cacb else (b, ac)
+    new, _ = oracle_closest(P, cmo, pc, m, x, y, linear_align)
+    _, _, c1 = align_2(a, new)
+    _, _, c2 = align_2(b, new)
+    _, amp, c3 = align_2(parent, new)
+    return c1 + c2 + c3, c1 + c2, new, amp

@@ -316,6 +316,38 @@ def test_closest_and_to_single(ctx, port, go):
 
 
 @pytest.mark.parametrize("go", [None, 3])
+def test_readjust(ctx, port, go):
+    """Sequence.readjust (src/sequence.ml:2097-2156): approximate three-way re-optimisation of an interior node,
+    a batched composition of 9 alignments + closest per node"""
+    import poy5_b200 as pb
+    from poy5_b200 import sequence
+    from poy5_b200.cost_matrix import Two_D
+    from tests.helpers import oracle_readjust
+    t2d = Two_D.of_transformations_and_gaps(1, 1, go)
+    full, _ = cmo.dna_matrices(1, 1, go)
+    cm = pb.CostModel(ctx, t2d.full)
+    pf = port.cm(full)
+    rng = np.random.default_rng(5)
+    seqs = []
+    n = 40
+    for t in range(n):
+        anc = synth.random_seq(rng, int(rng.integers(5, 120)))
+        tri = [synth.evolve(rng, anc, 0.1, 0.04) for _ in range(3)]
+        if t % 3 == 0:
+            tri[2] = synth.decorate(rng, tri[2], 0.1, 0.1)
+        seqs += [synth.with_gap(x) for x in tri]
+    pool = pb.Pool(ctx, seqs)
+    ia = np.arange(0, 3 * n, 3, dtype=np.int32)
+    got = sequence.readjust(ctx, cm, pool, ia, ia + 1, ia + 2)
+    lin = lambda x, y: _oracle_linear(port, pf, x, y)
+    for t in range(n):
+        c3, c2, new, amp = oracle_readjust(port, cmo, pf, full, seqs[ia[t]], seqs[ia[t] + 1], seqs[ia[t] + 2], lin)
+        assert got["cost3"][t] == c3 and got["cost2"][t] == c2, ("readjust cost", t)
+        assert np.array_equal(got["sequence"][t], new) and np.array_equal(got["aligned_mp"][t], amp), ("readjust seq", t)
+    pool.close(); cm.close()
+
+
+@pytest.mark.parametrize("go", [None, 3])
 def test_median_3_union(ctx, port, go):
     """config #3's live path: parent x union(children) alignment + median_2"""
     import poy5_b200 as pb
