@@ -58,6 +58,7 @@ value algn_CAML_ancestor_2(value sa, value sb, value cm, value sab);
 value algn_CAML_union(value s1, value s2, value su);
 value algn_CAML_worst_2(value s1, value s2, value c);
 value algn_CAML_verify_2(value s1, value s2, value c);
+value algn_CAML_myers(value sa, value sb);
 value algn_CAML_align_3d(value s1, value s2, value s3, value c, value a, value s1p, value s2p,
                          value s3p, value uk);
 value seq_CAML_median_2_no_gaps(value s1, value s2, value m, value sm);
@@ -253,6 +254,14 @@ int ref_worst_2(void *cm, const unsigned char *a, const unsigned char *b, int le
 int ref_verify_2(void *cm, const unsigned char *a, const unsigned char *b, int len) {
     value va = make_seq(a, len, len), vb = make_seq(b, len, len);
     int r = Int_val(algn_CAML_verify_2(va, vb, (value)cm));
+    free_val(va); free_val(vb);
+    return r;
+}
+
+/* algn_CAML_myers (src/algn.c:3697-3743); keeps static state between calls, see scripts/ref_myers_probe.py */
+int ref_myers(const unsigned char *a, int la, const unsigned char *b, int lb) {
+    value va = make_seq(a, la, la), vb = make_seq(b, lb, lb);
+    int r = Int_val(algn_CAML_myers(va, vb));
     free_val(va); free_val(vb);
     return r;
 }
