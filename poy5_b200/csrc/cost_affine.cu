@@ -1,15 +1,10 @@
 // Batched cost-only affine DO alignment: the batch twin of algn_CAML_cost_affine_3 ->
 // algn_fill_plane_3_aff_nobt (src/algn.c:2457-2515, 1822-1863, 1987-2110).
 //
-// One WARP per pair.  The full leni x lenj plane is swept in column blocks of
-// W = 32*C columns; inside a block lane t owns the C columns [t*C, (t+1)*C) and
-// the warp runs a skewed wavefront: at step s lane t computes row s - t + 1 of
-// its strip, so the value a lane needs from its left neighbour (same row, one
-// column to the left) was produced exactly one step earlier and arrives through
-// __shfl_up_sync.  All DP state (the previous row of CB/EV/EH/EB for the C
-// owned columns) lives in registers; the only memory traffic per step is one
-// 16-byte row-parameter load per lane, and -- for sequences wider than W -- one
-// 16-byte boundary-column store/load per step per warp.
+// One WARP per pair, persistent kernel, jobs pulled from one list.  The full leni x lenj plane is swept in
+// column blocks of W = 32*C columns; inside a block lane t owns C adjacent columns and keeps the previous row of
+// its states in registers.  Sequences wider than W hand one boundary column (16 bytes per row) from block to
+// block through a per-warp scratch in global memory.
 //
 // Recurrences per cell (i,j), ' = cell (i-1,j-1)   (src/algn.c:1260-1433):
 //   EH = min(EH[i][j-1] + hext_j, CB[i][j-1] + go_j + ge_j)
@@ -18,13 +13,14 @@
 //   CB = diag + min(CB', EV' + [ic has gap]go_j, EH' + [jc has gap]go_i, EB' + max(go_i,go_j))
 // evaluated with the DPX fused add-min instructions (__viaddmin_s32, __vimin3_s32).
 //
-// Two code paths inside one persistent kernel: gap-free pairs (neither sequence
-// contains a gap-bit symbol, the case of all leaf/observed DNA) drop the EB state
-// -- provably EB >= CB in every cell when every table entry is <= INF, so it can
-// never win a minimum -- and fold min3(CB,EV,EH) of the diagonal cell into one
-// carried value M:  CB = M' + diag, EH = min(EH[j-1], CB[j-1]+GO) + ge_j,
-// EV = min(EV[i-1], CB[i-1]+GO) + ge_i, M = min3(CB,EH,EV): 3 DPX instructions, 3
-// adds and one table lookup per cell.  General pairs keep all four states.
+// Two code paths:
+//  * gap-free pairs (neither sequence contains a gap-bit symbol: all leaf / observed DNA) run a SKEWED wavefront
+//    (at step s lane t computes row s - t + 1, the left neighbour's value arrives one step later by __shfl_up),
+//    drop the EB state -- provably EB >= CB in every cell, so it never wins a minimum -- fold min3(CB,EV,EH) of
+//    the diagonal cell into one carried value M and work in a shifted domain that moves both gap extensions
+//    into the cost table: 3 DPX instructions, 1 add and one table lookup per cell (cost_pair_gf);
+//  * pairs with gap-bit symbols keep all four states and go ROW BY ROW, all lanes on the same row, so that the
+//    rows without a gap bit (most of them) can skip EB and the flag logic warp-uniformly (cost_pair_rows).
 //
 // The reference's row-buffer aliasing is reproduced in closed
 // form: for lenj >= 3 its only observable effect is that on every even row i>=2
@@ -99,17 +95,19 @@ __device__ int cost_affine_tiny(const DevCM *cm, const int *s_cost16, const int4
 }
 
 
-// ---- general pairs: 4 states, C columns per lane ------------------------------------------------------------
-// Right-aligned columns like the gap-free path: column lastj is slot C-1 of lane 31 of the last block and the
-// padding on the left of block 0 replicates column 0 (CB = EH = EB = INF, EV[i][0] = GO + sum vext, table entry
-// INF).  Everything a cell needs from the column's flags is decoded once per block into per-column constants,
-// and the state arrays are updated in place (right to left for the states that read the diagonal neighbour,
-// then left to right for the EH chain), so the loop carries no register copies.
+// ---- general pairs: 4 states, one row at a time --------------------------------------------------------------
+// All 32 lanes work on the SAME row, so everything that depends on the row symbol is warp uniform -- in
+// particular "this row and the one above carry no gap bit", which holds for most rows of an interior-node
+// sequence and removes the EB state and all flag logic from the cell (fast rows below).  The price is that the
+// in-row EH dependency crosses lanes: with E = EH - S_j (S_j = prefix sum of the column extensions) it becomes a
+// running minimum,  E_c = min(E_{c-1}, CB_{c-1} + opn_c - S_c),  which is a per-lane chain plus one 5-step warp
+// min-scan per row.  Columns are right-aligned as in the other paths; boundary columns between blocks travel
+// through the same per-warp scratch, fetched a 32-row window ahead.
 template <int C>
-__device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_cost16, const CostJob &J,
-                                                  const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
-                                                  const int *__restrict__ g0v, int4 *bnd0, int4 *bnd1, int GO, int lane,
-                                                  int *__restrict__ cost_out) {
+__device__ __forceinline__ void cost_pair_rows(const DevCM *cm, const int *s_cost16, const CostJob &J,
+                                               const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
+                                               const int *__restrict__ g0v, int4 *bnd0, int4 *bnd1, int GO, int lane,
+                                               int *__restrict__ cost_out) {
     constexpr int W = 32 * C;
     const int lasti = J.lasti, lastj = J.lastj;
     const int4 *rp = rowp + J.off_i;
@@ -125,121 +123,154 @@ __device__ __forceinline__ void cost_pair_general(const DevCM *cm, const int *s_
     }
     const int nb = (lastj + W - 1) / W;
     const int pad = nb * W - lastj;
+    int s_carry = 0;                         // S of the last column of the previous block
     for (int b = 0; b < nb; ++b) {
         const int jb = b * W + lane * C - pad;  // slot c <-> column jb + c + 1 (<= 0: replica of column 0)
         const int4 *bin = (b & 1) ? bnd0 : bnd1;
         int4 *bout = (b & 1) ? bnd1 : bnd0;
         const bool last_block = (b == nb - 1);
-        const bool owns_last = last_block && lane == 31;
-        // per-column constants:
-        //   c_odc = 2GO if the previous column symbol has the gap bit, else 0  (EB opening when the row side is clean)
-        //   c_lim = -INF if the column symbol has the gap bit, else INF         (EB is alive only where both have it)
-        //   c_cap = INF if the column symbol has the gap bit, else 0            (go_i is charged on CB <- EH there)
-        //   c_tab = byte offset of the column inside a row of the cost table
-        int c_ext[C], c_opn[C], c_go[C], c_odc[C], c_lim[C], c_cap[C], c_tab[C];
-        int CBu[C], EVu[C], EHu[C], EBu[C];
+        // per-column constants: K = opn - S_j, Q = S_{j-1} + (column symbol has the gap bit ? GO : 0),
+        // byte offset into a table row, flags (bit 4 gap bit, bit 5 previous symbol has it, bit 6 go_j == 0)
+        int c_K[C], c_Q[C], c_tab[C], c_fl[C];
+        int CBu[C], EVu[C], Eu[C], EBu[C];
+        int s_prev_lane;                     // S of the column left of slot 0
+        {
+            int ext[C], opn[C];
+            int run = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int j = jb + c + 1;
-            if (j >= 1) {
-                const int4 v = cp[j];
-                c_ext[c] = v.x; c_opn[c] = v.y; c_go[c] = v.z;
-                c_odc[c] = (v.w & PF_PREVGAP) ? 2 * GO : 0;
-                c_lim[c] = (v.w & PF_HASGAP) ? -POY_INF : POY_INF;
-                c_cap[c] = (v.w & PF_HASGAP) ? POY_INF : 0;
-                c_tab[c] = (v.w & 15) * 4;
-                CBu[c] = POY_INF; EVu[c] = POY_INF; EHu[c] = GO + g0[j];
-            } else {
-                c_ext[c] = 0; c_opn[c] = 0; c_go[c] = GO; c_odc[c] = 0; c_lim[c] = POY_INF; c_cap[c] = 0;
-                c_tab[c] = 16 * 4;                            // the INF column of the table
-                CBu[c] = 0; EVu[c] = GO; EHu[c] = GO;         // CB[0][0], EV[0][0], EH[0][0]
-            }
-            EBu[c] = POY_INF;
-        }
-        int dCB, dEV, dEH, dEB;   // cell (i-1, jb): diagonal predecessor of slot 0
-        if (jb <= 0) { dCB = 0; dEV = GO; dEH = GO; dEB = POY_INF; }
-        else { dCB = POY_INF; dEV = POY_INF; dEH = GO + g0[jb]; dEB = POY_INF; }
-        int ev_col0 = GO;  // EV[i][0] running sum (lane 0 of block 0), src/algn.c:2066-2070
-        int oCB = POY_INF, oEH = POY_INF, oEV = POY_INF, oEB = POY_INF;
-        int4 rnext = rp[1];
-        int4 bnext = make_int4(0, 0, 0, 0);
-        if (b > 0 && lane == 0) bnext = bin[1];
-        const int nsteps = lasti + 31;
-        // one wavefront step; ROW1 = some lane may be on row 1 (the first 32 steps), see the column-0 note below
-        auto step = [&](auto row1_c, int s) {
-            constexpr bool ROW1 = decltype(row1_c)::value;
-            const int i = s - lane + 1;
-            int lCB = __shfl_up_sync(0xffffffffu, oCB, 1);
-            int lEH = __shfl_up_sync(0xffffffffu, oEH, 1);
-            int lEV = __shfl_up_sync(0xffffffffu, oEV, 1);
-            int lEB = __shfl_up_sync(0xffffffffu, oEB, 1);
-            if (i >= 1 && i <= lasti) {
-                const int4 r = rnext;
-                if (i < lasti) rnext = rp[i + 1];
-                if (lane == 0) {
-                    if (b == 0) {
-                        ev_col0 += r.x;
-                        lCB = POY_INF; lEH = POY_INF; lEV = ev_col0; lEB = POY_INF;
-                    } else {
-                        lCB = bnext.x; lEH = bnext.y; lEV = bnext.z; lEB = bnext.w;
-                        if (i < lasti) bnext = bin[i + 1];
-                    }
+            for (int c = 0; c < C; ++c) {
+                const int j = jb + c + 1;
+                if (j >= 1) {
+                    const int4 v = cp[j];
+                    ext[c] = v.x; opn[c] = v.y;
+                    c_fl[c] = (v.w & (PF_HASGAP | PF_PREVGAP)) | (v.z == 0 ? 64 : 0);
+                    c_tab[c] = (v.w & 15) * 4;
+                } else {
+                    ext[c] = 0; opn[c] = 0; c_fl[c] = 0; c_tab[c] = 16 * 4;
                 }
-                const char *rowbase = (const char *)(s_cost16 + (r.w & 15) * GF_TAB_COLS);
-                const int vext = r.x, opnV = r.y, go_i = r.z;
-                const bool rH = (r.w & PF_HASGAP) != 0, rP = (r.w & PF_PREVGAP) != 0;
+                run += ext[c];
+            }
+            int incl = run;                  // inclusive warp scan of the per-lane sums
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            s_prev_lane = s_carry + incl - run;
+            int sj = s_prev_lane;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int j = jb + c + 1;
+                c_Q[c] = sj + ((c_fl[c] & PF_HASGAP) ? GO : 0);
+                sj += ext[c];
+                c_K[c] = opn[c] - sj;
+                if (j >= 1) { CBu[c] = POY_INF; EVu[c] = POY_INF; Eu[c] = GO + g0[j] - sj; }
+                else { CBu[c] = 0; EVu[c] = GO; Eu[c] = GO; }          // CB[0][0], EV[0][0], EH[0][0]
+                EBu[c] = POY_INF;
+            }
+            s_carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        const int s_last = s_carry;          // S of the block's last column (lane 31 un-shifts EH with it)
+        // left neighbour of lane 0 at row 0: column jb of row 0
+        int4 bprev;                          // (CB, E, EV, EB) of the column left of the block, previous row
+        if (b == 0) bprev = make_int4(0, GO, GO, POY_INF);
+        else bprev = make_int4(POY_INF, GO + g0[b * W - pad] - s_prev_lane, POY_INF, POY_INF);
+        int ev_col0 = GO;                    // EV[i][0] running sum (block 0), src/algn.c:2066-2070
+        auto load_bnd = [&](int w) { const int r = 32 * w + lane + 1; return b > 0 ? bin[r <= lasti ? r : lasti] : make_int4(0, 0, 0, 0); };
+        int4 bw = make_int4(0, 0, 0, 0), bw_next = load_bnd(0);
+        int4 rnext = rp[1];
+        bool prevH = false;                  // row 0 leaves EB = INF everywhere
+        for (int i = 1; i <= lasti; ++i) {
+            if (((i - 1) & 31) == 0) { bw = bw_next; bw_next = load_bnd(((i - 1) >> 5) + 1); }
+            const int4 r = rnext;
+            rnext = rp[i < lasti ? i + 1 : lasti];
+            // values of the column to the left: previous row (diagonal) ...
+            int xCB0 = __shfl_up_sync(0xffffffffu, CBu[C - 1], 1);
+            int xEV0 = __shfl_up_sync(0xffffffffu, EVu[C - 1], 1);
+            int xE0 = __shfl_up_sync(0xffffffffu, Eu[C - 1], 1);
+            int xEB0 = __shfl_up_sync(0xffffffffu, EBu[C - 1], 1);
+            int4 bcur = make_int4(POY_INF, POY_INF, 0, POY_INF);   // ... and this row (CB, E) for the EH chain
+            if (b > 0) {
+                bcur.x = __shfl_sync(0xffffffffu, bw.x, (i - 1) & 31);
+                bcur.y = __shfl_sync(0xffffffffu, bw.y, (i - 1) & 31);
+                bcur.z = __shfl_sync(0xffffffffu, bw.z, (i - 1) & 31);
+                bcur.w = __shfl_sync(0xffffffffu, bw.w, (i - 1) & 31);
+            }
+            if (lane == 0) { xCB0 = bprev.x; xE0 = bprev.y; xEV0 = bprev.z; xEB0 = bprev.w; }
+            const int vext = r.x, opnV = r.y, go_i = r.z;
+            const bool rH = (r.w & PF_HASGAP) != 0, rP = (r.w & PF_PREVGAP) != 0;
+            const char *rowbase = (const char *)(s_cost16 + (r.w & 15) * GF_TAB_COLS);
+            if (!rH && !prevH) {
+                // fast row: no cell of this row or the one above has both gap bits, so EB >= INF throughout,
+                // go_i = GO, nothing is charged on CB <- EV, and CB <- EH is charged GO where the column has the bit
+                sfor_down<C>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    int xCB, xEV, xE;
+                    if constexpr (c == 0) { xCB = xCB0; xEV = xEV0; xE = xE0; }
+                    else { xCB = CBu[c - 1]; xEV = EVu[c - 1]; xE = Eu[c - 1]; }
+                    const int m = __vimin3_s32(xCB, xEV, xE + c_Q[c]);
+                    EVu[c] = __viaddmin_s32(EVu[c], vext, CBu[c] + opnV);
+                    CBu[c] = m + *(const int *)(rowbase + c_tab[c]);
+                });
+            } else {
                 const int mask_i = rH ? -1 : 0;
                 const int rowlim = rH ? -POY_INF : POY_INF;
                 const int rowod = rP ? 2 * GO : 0;
-                // pass 1, right to left: column c reads the old states of column c-1 and of itself, writes itself
                 sfor_down<C>([&](auto cc) {
                     constexpr int c = decltype(cc)::value;
-                    int xCB, xEV, xEH, xEB;
-                    if constexpr (c == 0) { xCB = dCB; xEV = dEV; xEH = dEH; xEB = dEB; }
-                    else { xCB = CBu[c - 1]; xEV = EVu[c - 1]; xEH = EHu[c - 1]; xEB = EBu[c - 1]; }
-                    const int go_j = c_go[c];
-                    // EB = min(EB' + dg, CB' + od) where both symbols carry the gap bit, >= INF elsewhere (values
-                    // >= INF never win a minimum against the finite states, so any such value will do)
-                    const int od = max(rowod, c_odc[c]);
-                    const int lim = max(rowlim, c_lim[c]);
+                    int xCB, xEV, xE, xEB;
+                    if constexpr (c == 0) { xCB = xCB0; xEV = xEV0; xE = xE0; xEB = xEB0; }
+                    else { xCB = CBu[c - 1]; xEV = EVu[c - 1]; xE = Eu[c - 1]; xEB = EBu[c - 1]; }
+                    const int fl = c_fl[c];
+                    const bool cH = (fl & PF_HASGAP) != 0;
+                    const int go_j = (fl & 64) ? 0 : GO;
+                    const int od = max(rowod, (fl & PF_PREVGAP) ? 2 * GO : 0);
+                    const int lim = max(rowlim, cH ? -POY_INF : POY_INF);
                     const int eb = max(__viaddmin_s32(xCB, od, xEB), lim);
-                    const int diag = *(const int *)(rowbase + c_tab[c]);
-                    const int gv = go_j & mask_i;
-                    const int gh = min(go_i, c_cap[c]);
-                    const int xgo = max(go_i, go_j);
-                    int m = __viaddmin_s32(xEV, gv, xCB);
-                    m = __viaddmin_s32(xEH, gh, m);
-                    m = __viaddmin_s32(xEB, xgo, m);
+                    const int xEH = xE + c_Q[c] - (cH ? GO : 0);            // un-shift: Q = S_{j-1} + [cH] GO
+                    int m = __viaddmin_s32(xEV, go_j & mask_i, xCB);
+                    m = __viaddmin_s32(xEH, cH ? go_i : 0, m);
+                    m = __viaddmin_s32(xEB, max(go_i, go_j), m);
                     EVu[c] = __viaddmin_s32(EVu[c], vext, CBu[c] + opnV);
-                    CBu[c] = m + diag;
+                    CBu[c] = m + *(const int *)(rowbase + c_tab[c]);
                     EBu[c] = eb;
                 });
-                // column 0 has no opening alternative (EV[i][0] = EV[i-1][0] + vext, src/algn.c:2066-2070); its replicas
-                // could only find one in row 1, from CB[0][0] = 0 when the first row symbol opens for free
-                if (ROW1 && i == 1 && b == 0) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        if (c_tab[c] == 16 * 4) EVu[c] = GO + vext;
-                }
-                // pass 2, left to right: the EH chain over the new CB
-                int cbL = lCB, ehL = lEH;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    ehL = __viaddmin_s32(ehL, c_ext[c], cbL + c_opn[c]);
-                    EHu[c] = ehL;
-                    cbL = CBu[c];
-                }
-                // F5: EV at the last column of an even row comes from clobbered predecessors
-                if (owns_last && !(i & 1)) EVu[C - 1] = POY_INF + imin(r.x, r.y);
-                dCB = lCB; dEV = lEV; dEH = lEH; dEB = lEB;
-                oCB = CBu[C - 1]; oEH = EHu[C - 1]; oEV = EVu[C - 1]; oEB = EBu[C - 1];
-                if (lane == 31 && !last_block) bout[i] = make_int4(oCB, oEH, oEV, oEB);
             }
-        };
-        int s = 0;
-        for (; s < 32 && s < nsteps; ++s) step(std::true_type{}, s);
-        for (; s < nsteps; ++s) step(std::false_type{}, s);
-        if (owns_last) cost_out[J.out] = imin(imin(EHu[C - 1], EVu[C - 1]), imin(CBu[C - 1], EBu[C - 1]));
+            prevH = rH;
+            // column 0 has no opening alternative (EV[i][0] = EV[i-1][0] + vext, src/algn.c:2066-2070); its replicas
+            // could only find one in row 1, from CB[0][0] = 0 when the first row symbol opens for free
+            if (i == 1 && b == 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (c_tab[c] == 16 * 4) EVu[c] = GO + vext;
+            }
+            // EH chain: E_c = min(E_{c-1}, CB_{c-1} + K_c); per-lane running minimum, then a warp scan of the lane totals
+            int cbleft = __shfl_up_sync(0xffffffffu, CBu[C - 1], 1);
+            if (lane == 0) cbleft = bcur.x;
+            int P[C];
+            P[0] = cbleft + c_K[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) P[c] = __viaddmin_s32(CBu[c - 1], c_K[c], P[c - 1]);
+            int incl = P[C - 1];
+            if (lane == 0) incl = min(incl, bcur.y);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl = min(incl, t);
+            }
+            int X = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) X = bcur.y;
+#pragma unroll
+            for (int c = 0; c < C; ++c) Eu[c] = min(P[c], X);
+            // F5: EV at the last column of an even row comes from clobbered predecessors
+            if (last_block && !(i & 1) && lane == 31) EVu[C - 1] = POY_INF + imin(r.x, r.y);
+            if (lane == 31 && !last_block) bout[i] = make_int4(CBu[C - 1], Eu[C - 1], EVu[C - 1], EBu[C - 1]);
+            // the column left of the block, as the next row's diagonal neighbour
+            if (b == 0) { ev_col0 += vext; bprev = make_int4(POY_INF, POY_INF, ev_col0, POY_INF); }
+            else bprev = bcur;
+        }
+        if (last_block && lane == 31)
+            cost_out[J.out] = imin(imin(Eu[C - 1] + s_last, EVu[C - 1]), imin(CBu[C - 1], EBu[C - 1]));
         __syncwarp();
     }
 }
@@ -399,7 +430,7 @@ k_cost_affine(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const
         if (job >= njobs) break;
         const CostJob J = jobs[job];
         if (J.gapfree) cost_pair_gf<CG>(s_tab, J, rowpk, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
-        else cost_pair_general<(CG >= 32 ? 16 : 8)>(cm, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
+        else cost_pair_rows<(CG >= 32 ? 16 : 8)>(cm, s_cost16, J, rowp, colp, g0v, bnd0, bnd1, GO, lane, cost_out);
     }
 }
 
