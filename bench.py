@@ -56,7 +56,10 @@ def make_config(pairs, lengths, world, total_bytes=None):
                regime="subst %d indel %d gap_open %d" % REGIME,
                l2="inputs larger than L2 (%.1f GB of sequences per step)" % ((total_bytes or sum(2.0 * pairs * (L + 1) for L in lengths)) / 1e9),
                pairs_per_length=pairs, lengths=list(lengths),
-               parallelism="pairs sharded over %d GPU(s), NCCL min-reduce of candidate costs" % world)
+               parallelism="pairs sharded over %d GPU(s), NCCL min-reduce of candidate costs" % world,
+               streams="value: one context (stream) per GPU, the batches of a step back to back; e2e: two host threads with "
+                       "one context each take alternate batches, so copies, host-side scheduling and kernel tails of one "
+                       "batch overlap the kernels of the other (which is why e2e can exceed value)")
     return cfg
 
 
