@@ -82,6 +82,12 @@ struct poy_ctx {
     void *cache_ptr[64];
     size_t cache_cap[64];
     int cache_n;
+    // second lane for large banded batches: the batch is cut in two halves whose threshold-doubling rounds run as
+    // independent pipelines (own stream set, arenas and host thread), so that the tail of one half's round is
+    // filled by the other half's kernels
+    poy_ctx *twin;
+    bool is_twin;
+    cudaEvent_t ev_twin_start, ev_twin_done;
 };
 
 // ---- work descriptors ----------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include <vector>
 #include <chrono>
 #include <atomic>
+#include <thread>
 #include "common.cuh"
 
 // ---- error plumbing ---------------------------------------------------------------------
@@ -65,6 +66,8 @@ extern "C" poy_status poy_ctx_create(int device, void *stream, poy_ctx **out) {
         cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_twin_start, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_twin_done, cudaEventDisableTiming);
     {   // direction arena: up to 40% of the free HBM, at most 64 GiB
         size_t fr = 0, tot = 0;
         ctx->arena_limit = 8ull << 30;
@@ -83,6 +86,8 @@ extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->twin) { poy_ctx_destroy(ctx->twin); ctx->twin = nullptr; }
+    cudaEventDestroy(ctx->ev_twin_start); cudaEventDestroy(ctx->ev_twin_done);
     for (int s = 0; s < 8; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
     for (int i = 0; i < ctx->cache_n; ++i) cudaFree(ctx->cache_ptr[i]);
     for (int s = 0; s < 4; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
@@ -806,6 +811,55 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     return POY_OK;
 }
 
+// Large batches are cut in two halves that run align_impl concurrently, the second one on the context's twin
+// (own streams, scratch and host thread).  Every per-pair array is indexed by the pair's position in the batch, so
+// the second half simply gets the pointers advanced by n0.  POY_SPLIT=0 turns this off.
+static poy_status align_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n, const int32_t *h_si,
+                              const int32_t *h_sj, const uint8_t *h_swaped, const int64_t *d_out_off, int32_t *d_cost,
+                              uint8_t *d_median, uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
+                              int32_t *d_out_len, int32_t *h_stats, const int32_t *h_deltawh = nullptr) {
+    const bool linear = h_deltawh != nullptr;
+    const char *se = getenv("POY_SPLIT"), *sm = getenv("POY_SPLIT_MIN");   // POY_SPLIT_MIN: smallest batch that is split (test hook)
+    const int split_min = sm ? std::max(2, atoi(sm)) : 4096;
+    const bool model_ok = linear ? cm->h.cost_model_type != 1 : cm->h.cost_model_type == 1;
+    if (n < split_min || ctx->is_twin || !model_ok || (se && se[0] == '0'))
+        return align_impl(ctx, cm, pool, n, h_si, h_sj, h_swaped, d_out_off, d_cost, d_median, d_medianwg, d_resi, d_resj,
+                          d_out_len, h_stats, h_deltawh);
+    if (!ctx->twin) {
+        poy_status cs = poy_ctx_create(ctx->device, nullptr, &ctx->twin);
+        if (cs != POY_OK) return fail(ctx, cs, "second lane: context creation failed");
+        ctx->twin->is_twin = true;
+    }
+    poy_ctx *tw = ctx->twin;
+    poy_status s = ensure_params(ctx, cm, pool);     // once, before the lanes diverge
+    if (s != POY_OK) return s;
+    const uint64_t full_arena = ctx->arena_limit;
+    ctx->arena_limit = tw->arena_limit = std::max<uint64_t>(full_arena / 2, 1ull << 20);
+    CK(cudaEventRecord(ctx->ev_twin_start, ctx->stream));
+    CK(cudaStreamWaitEvent(tw->stream, ctx->ev_twin_start, 0));
+    const int32_t n0 = n / 2, n1 = n - n0;
+    const int per = linear ? 2 : 4;
+    poy_status s1 = POY_OK;
+    const uint64_t tw_launches0 = tw->launches;
+    std::thread lane([&] {
+        cudaSetDevice(ctx->device);
+        s1 = align_impl(tw, cm, pool, n1, h_si + n0, h_sj + n0, h_swaped ? h_swaped + n0 : nullptr,
+                        d_out_off ? d_out_off + n0 : nullptr, d_cost ? d_cost + n0 : nullptr, d_median, d_medianwg, d_resi, d_resj,
+                        d_out_len ? d_out_len + (size_t)per * n0 : nullptr, h_stats ? h_stats + 4 * (size_t)n0 : nullptr,
+                        h_deltawh ? h_deltawh + n0 : nullptr);
+    });
+    const poy_status s0 = align_impl(ctx, cm, pool, n0, h_si, h_sj, h_swaped, d_out_off, d_cost, d_median, d_medianwg, d_resi,
+                                     d_resj, d_out_len, h_stats, h_deltawh);
+    lane.join();
+    ctx->arena_limit = full_arena;
+    ctx->launches += tw->launches - tw_launches0;
+    cudaEventRecord(ctx->ev_twin_done, tw->stream);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_twin_done, 0);
+    if (s0 != POY_OK) return s0;
+    if (s1 != POY_OK) { snprintf(ctx->err, sizeof ctx->err, "%s", tw->err); return s1; }
+    return POY_OK;
+}
+
 extern "C" poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n,
                                                  const int32_t *d_si, const int32_t *d_sj, const uint8_t *d_swaped,
                                                  const int32_t *h_si, const int32_t *h_sj, const int64_t *d_out_off,
@@ -824,7 +878,7 @@ extern "C" poy_status poy_batch_align_affine_dev(poy_ctx *ctx, const poy_cm *cm,
     }
     std::vector<int32_t> stats;
     if (d_stats) stats.resize(4 * (size_t)n);
-    poy_status s = align_impl(ctx, cm, pool, n, h_si, h_sj, d_swaped ? sw.data() : nullptr, d_out_off, d_cost, d_median,
+    poy_status s = align_split(ctx, cm, pool, n, h_si, h_sj, d_swaped ? sw.data() : nullptr, d_out_off, d_cost, d_median,
                               d_medianwg, d_resi, d_resj, d_out_len, d_stats ? stats.data() : nullptr);
     if (s != POY_OK) return s;
     if (d_stats) {
@@ -868,7 +922,7 @@ extern "C" poy_status poy_batch_align_affine(poy_ctx *ctx, const poy_cm *cm, con
     if (resi) { d_i = cur; cur += al_total; }
     if (resj) { d_j = cur; cur += al_total; }
     if (want_trace) CK(cudaMemcpyAsync(d_out_off, out_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    s = align_impl(ctx, cm, pool, n, si, sj, swaped, want_trace ? d_out_off : nullptr, d_cost, d_m, d_w, d_i, d_j,
+    s = align_split(ctx, cm, pool, n, si, sj, swaped, want_trace ? d_out_off : nullptr, d_cost, d_m, d_w, d_i, d_j,
                    want_trace ? d_len : nullptr, stats);
     if (s != POY_OK) return s;
     if (cost) CK(cudaMemcpyAsync(cost, d_cost, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -913,7 +967,7 @@ extern "C" poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, con
     if (r1) { d_1 = cur; cur += al_total; }
     if (r2) { d_2 = cur; cur += al_total; }
     if (want_trace) CK(cudaMemcpyAsync(d_out_off, out_off, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    s = align_impl(ctx, cm, pool, n, s1, s2, swaped, want_trace ? d_out_off : nullptr, d_cost, nullptr, nullptr, d_1, d_2,
+    s = align_split(ctx, cm, pool, n, s1, s2, swaped, want_trace ? d_out_off : nullptr, d_cost, nullptr, nullptr, d_1, d_2,
                    want_trace ? d_len : nullptr, stats, deltawh);
     if (s != POY_OK) return s;
     if (cost) CK(cudaMemcpyAsync(cost, d_cost, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));

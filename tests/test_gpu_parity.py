@@ -150,6 +150,36 @@ def test_arena_waves_do_not_change_results(ctx, port):
     cm.close(); pool.close()
 
 
+def test_two_lane_split_does_not_change_results(ctx, port, monkeypatch):
+    """large batches are cut in two halves that run on two stream sets / host threads; same results, also against
+    the oracle, for the affine and the linear entry point"""
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES["R1"])
+    pc = port.cm(full)
+    seqs, ia, ib = synth.pair_batch(9, 257, 300, frac_decorated=0.3, jitter=0.2)
+    pool = pb.Pool(ctx, seqs)
+    monkeypatch.setenv("POY_SPLIT", "0")
+    r1 = Align.align_affine_3(ctx, cm, pool, ia, ib)
+    monkeypatch.setenv("POY_SPLIT", "1"); monkeypatch.setenv("POY_SPLIT_MIN", "16")
+    r2 = Align.align_affine_3(ctx, cm, pool, ia, ib)
+    assert np.array_equal(r1["cost"], r2["cost"])
+    for p in range(len(ia)):
+        for k in ("median", "medianwg", "res_a", "res_b"):
+            assert np.array_equal(r1[k][p], r2[k][p]), (k, p)
+    for p in range(0, len(ia), 7):
+        oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r2["cost"][p] and np.array_equal(om, r2["median"][p]) and np.array_equal(rb, r2["res_b"][p])
+    lin = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 2, None).full)
+    pl = port.cm(cmo.dna_matrices(1, 2, None)[0])
+    r3 = Align.align_2(ctx, lin, pool, ia, ib)
+    for p in range(0, len(ia), 5):
+        oc, ra, rb = _oracle_linear(port, pl, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r3["cost"][p] and np.array_equal(ra, r3["res_a"][p]) and np.array_equal(rb, r3["res_b"][p]), p
+    cm.close(); lin.close(); pool.close()
+
+
 # ---- linear-gap path (algn_CAML_simple_2 / backtrace_2d) -------------------------------------------------
 def _oracle_linear(port, pc, pool_seq_a, pool_seq_b, deltaw=None):
     """Sequence.Align.cost_2 / align_2 semantics (linear) on top of the oracle."""
