@@ -649,8 +649,10 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const bool trace = tr && tr[0] == '1';
     double t_prep = 0, t_wait = 0; int rounds = 0, waves = 0;
     long long n_repeat = 0, n_probe = 0, n_full = 0;
-    const char *pe = getenv("POY_PROBE");   // POY_PROBE=0 turns the probe fills off (tuning / test hook)
-    const bool use_probes = !(pe && pe[0] == '0');
+    const char *pe = getenv("POY_PROBE");   // POY_PROBE=0 turns the probe fills off, 2 forces them on small batches too (test hook)
+    // small batches are latency bound (a repeated threshold is one more round trip), probes only pay when the
+    // fills saturate the GPU
+    const bool use_probes = !(pe && pe[0] == '0') && (n >= 1024 || (pe && pe[0] == '2'));
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
     while (!active.empty()) {

@@ -104,9 +104,10 @@ class Align:
         cost = np.zeros(n, np.int32)
         out_len = np.zeros(4 * n, np.int32)
         st = np.zeros(4 * n, np.int32) if stats else None
+        any_out = any(v is not None for v in bufs.values())     # cost only: no traceback, no direction bytes
         ctx.check(ctx.L.poy_batch_align_affine(ctx.h, cm.h, pool.h, n, _ptr(si), _ptr(sj), _ptr(swaped), _ptr(out_off),
                                                _ptr(cost), _ptr(bufs["median"]), _ptr(bufs["medianwg"]),
-                                               _ptr(bufs["resi"]), _ptr(bufs["resj"]), _ptr(out_len), _ptr(st)))
+                                               _ptr(bufs["resi"]), _ptr(bufs["resj"]), _ptr(out_len) if any_out else None, _ptr(st)))
         out_len = out_len.reshape(n, 4)
         res = {"cost": cost, "swaped": swaped, "out_len": out_len}
         ends = out_off + caps

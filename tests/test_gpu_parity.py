@@ -150,6 +150,38 @@ def test_arena_waves_do_not_change_results(ctx, port):
     cm.close(); pool.close()
 
 
+@pytest.mark.parametrize("rname", ["R1", "R2", "R3"])
+def test_probe_fills_do_not_change_results(ctx, port, monkeypatch, rname):
+    """fills without direction bytes until the stop rule fires (then the threshold is repeated with directions, from
+    the snapshot of the stale EB row for pairs with gap-bit symbols): forced on for a small batch, compared with
+    probes off and with the oracle"""
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES[rname])
+    pc = port.cm(full)
+    seqs, ia, ib = synth.pair_batch(21, 200, 260, frac_decorated=0.5, jitter=0.3)
+    e_seqs, e_ia, e_ib = edge_pairs(31, n=120, maxlen=50)
+    base = len(seqs)
+    seqs = seqs + e_seqs
+    keep = [p for p in range(len(e_ia)) if len(e_seqs[e_ia[p]]) <= len(e_seqs[e_ib[p]])]
+    ia = np.concatenate([ia, e_ia[keep] + base]).astype(np.int32); ib = np.concatenate([ib, e_ib[keep] + base]).astype(np.int32)
+    pool = pb.Pool(ctx, seqs)
+    monkeypatch.setenv("POY_PROBE", "0")
+    r0 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    monkeypatch.setenv("POY_PROBE", "2")
+    r1 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    c1 = Align.align_affine_3(ctx, cm, pool, ia, ib, want=())["cost"]          # no traceback: every fill is a probe
+    assert np.array_equal(r0["cost"], r1["cost"]) and np.array_equal(r0["cost"], c1)
+    assert np.array_equal(r0["stats"][:, :3], r1["stats"][:, :3])                 # same iterations, T and k
+    for p in range(len(ia)):
+        for k in ("median", "medianwg", "res_a", "res_b"):
+            assert np.array_equal(r0[k][p], r1[k][p]), (k, p)
+    for p in range(0, len(ia), 3):
+        oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r1["cost"][p] and np.array_equal(om, r1["median"][p]) and np.array_equal(ra, r1["res_a"][p]), p
+    cm.close(); pool.close()
+
+
 def test_two_lane_split_does_not_change_results(ctx, port, monkeypatch):
     """large batches are cut in two halves that run on two stream sets / host threads; same results, also against
     the oracle, for the affine and the linear entry point"""
