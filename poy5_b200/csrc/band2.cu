@@ -140,6 +140,44 @@ __device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, uns
     return b;
 }
 
+// One band cell of a gap-free pair.  All DP values are carried times 256 (so a finite value stays below 2^28 and
+// an "infinite" one below 2^30), which leaves the low byte free for tags that turn tie-breaking into plain minima:
+//   * EH = min(EH_left + 32, CB_left + GO): ties take the opening, so bit 5 of the winner says "the extension won
+//     strictly" = no END_HORIZONTAL; likewise bit 4 for EV;
+//   * the final choice is min3 of (EV + tagV, EH + tagH, CB + 3): its low two bits ARE the todo code, with the
+//     V-before-H (or, for swapped operands, H-before-V) priority built in (tagV, tagH = 0, 1 or 1, 0); "X is in
+//     the tie set" is X <= that minimum;
+//   * ALIGN_TO_* of cell (i,j) are the DO_* flags of cell (i-1,j-1) (same three values, no gap-bit surcharges), so
+//     nothing is stored for them: after an align step the traceback reads the next cell's todo code, and CB needs
+//     only the carried minimum K of the diagonal predecessor.
+// Byte (gap-free format, k_traceback decodes it when bit 6 of BandJob::swaped is set): bits 0-1 todo code (0/1 =
+// the two gap directions in priority order, 3 = align), bit 4 / 5 = NOT END_VERTICAL / END_HORIZONTAL, bit 7 =
+// HORIZONTAL_EQ_VERTICAL.
+#define INF256 (POY_INF << 8)
+template <bool EDGE>
+__device__ __forceinline__ unsigned cell_gf(int &CB, int &EV, int &EH, int &K, unsigned &G, int lCB, int lEH, unsigned lG,
+                                            int uCB, int uEV, unsigned uG, int diag, int GO256, bool lb, bool rb, bool jpos,
+                                            int tagV, int tagH) {
+    int eH = min(lEH + 32, lCB + GO256);
+    int eV = min(uEV + 16, uCB + GO256);
+    if (lb) eH = INF256 + 32;
+    if (rb) eV = INF256 + 16;
+    const int nEH = eH & ~255, nEV = eV & ~255;
+    int nCB = (K & ~255) + diag;
+    if (EDGE && !jpos) nCB = INF256;
+    const int k = __vimin3_s32(nEV + tagV, nEH + tagH, nCB + 3);
+    const bool fV = nEV <= k, fH = nEH <= k, fA = nCB <= k;
+    // gap counters: component-wise max over the chosen predecessors (+1 on the side that gaps)
+    const unsigned cD = fA ? G : 0u;
+    const unsigned cL = fH ? lG + 1u : 0u;
+    const unsigned cU = fV ? uG + 0x10000u : 0u;
+    G = __vimax3_u16x2(cD, cL, cU);
+    unsigned w = (unsigned)(k | eH | eV);
+    if (fH && fV) w |= 128u;
+    CB = nCB; EV = nEV; EH = nEH; K = k;
+    return w & 0xFFu;
+}
+
 // Named-barrier producer / consumer pair (the PTX manual's bar.arrive / bar.sync idiom): the producing warp
 // arrives without waiting, the consuming warp waits until both have reached the barrier.
 __device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
@@ -182,11 +220,12 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     // the direction bytes and gap counters do not change; the cost is shifted back when it is stored.
     for (int x = threadIdx.x; x < 256 * 32; x += WPB * 32) {
         const int e = x >> 5;
-        s_tab_i[x] = cm->cost16[e] - (GFK ? cm->prepend[e & 15] + cm->gapext[e >> 4] : 0);
+        s_tab_i[x] = GFK ? (cm->cost16[e] - cm->prepend[e & 15] - cm->gapext[e >> 4]) * 256 : cm->cost16[e];   // x256: see cell_gf
     }
     __syncthreads();
     const char *s_tab = (const char *)s_tab_i;
     const int GO = cm->gap_open;
+    const int GO256 = GO << 8;
 
     for (;;) {
         int job;
@@ -222,18 +261,27 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         const int rbslot = (B - 1) - d0;  // slot holding the right border, if 0 <= rbslot < D
 
         int CB[D], EV[D], EH[D], EB[D];
+        int K[D];                         // gap-free pairs: tagged minimum of the diagonal predecessor (cell_gf)
         unsigned G[D];
+        const int tagV = swaped ? 1 : 0, tagH = swaped ? 0 : 1;
         sfor<D>([&](auto uc) {
             constexpr int u = decltype(uc)::value;
             const int d = d0 + u, j0 = d - k;
             if (d < B && j0 >= 0 && j0 <= lastj) {  // row 0 (src/algn.c:2222-2247)
-                CB[u] = h0[j0] - (GF ? g0[j0] : 0);
-                EH[u] = j0 == 0 ? eh00 : CB[u];
-                EV[u] = POY_INF;
+                if (GF) {
+                    CB[u] = (h0[j0] - g0[j0]) << 8;
+                    EH[u] = j0 == 0 ? (eh00 << 8) : CB[u];
+                    EV[u] = INF256;
+                    K[u] = min(CB[u], EH[u]);
+                } else {
+                    CB[u] = h0[j0];
+                    EH[u] = j0 == 0 ? eh00 : CB[u];
+                    EV[u] = POY_INF;
+                }
                 EB[u] = GF ? POY_INF : eb[j0];
                 G[u] = (unsigned)j0 & 0xFFFFu;
             } else {
-                CB[u] = EV[u] = EH[u] = EB[u] = POY_INF; G[u] = 0u;
+                CB[u] = EV[u] = EH[u] = EB[u] = K[u] = GF ? INF256 : POY_INF; G[u] = 0u;
             }
         });
 
@@ -304,8 +352,13 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         bool lb = false;
                         if constexpr (u == 0) lb = (tid == 0);
                         if (EDGE) lb = lb || (j == 0);
-                        const unsigned b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
-                                                          R[h], C[h], s_tab, GO, lb, u == rbslot, j > 0, swaped);
+                        unsigned b;
+                        if constexpr (GF)
+                            b = cell_gf<EDGE>(CB[u], EV[u], EH[u], K[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
+                                              *(const int *)(s_tab + R[h].meta + C[h].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
+                        else
+                            b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
+                                               R[h], C[h], s_tab, GO, lb, u == rbslot, j > 0, swaped);
                         packed |= (unsigned long long)b << (8 * h);
                         if (!GF) {
                             if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
@@ -340,8 +393,13 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         else { constexpr int uu = u < D - 1 ? u + 1 : u; uCB = CB[uu]; uEV = EV[uu]; uG = G[uu]; }
                         bool lb = false;
                         if (EDGE) lb = (j == 0);
-                        const unsigned b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
-                                                          R[h], C[h + 1], s_tab, GO, lb, u == rbslot, j > 0, swaped);
+                        unsigned b;
+                        if constexpr (GF)
+                            b = cell_gf<EDGE>(CB[u], EV[u], EH[u], K[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
+                                              *(const int *)(s_tab + R[h].meta + C[h + 1].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
+                        else
+                            b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
+                                               R[h], C[h + 1], s_tab, GO, lb, u == rbslot, j > 0, swaped);
                         packed |= (unsigned long long)b << (8 * h);
                         if (!GF) {
                             if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
@@ -377,7 +435,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 if (u == dstar % D) {
                     int fin = __vimin3_s32(EH[u], EV[u], CB[u]);
                     if (!GF) fin = min(fin, EB[u]);
-                    if (GF) fin += g0[lastj] + (int)(rowpk[J.off_i + lasti] & 0x0FFFFFFFu);
+                    if (GF) fin = (fin >> 8) + g0[lastj] + (int)(rowpk[J.off_i + lasti] & 0x0FFFFFFFu);
                     st->cost = fin;
                     st->gapnum = max((int)(G[u] & 0xFFFFu), (int)(G[u] >> 16));
                 }
