@@ -154,18 +154,19 @@ __device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, uns
 // the two gap directions in priority order, 3 = align), bit 4 / 5 = NOT END_VERTICAL / END_HORIZONTAL, bit 7 =
 // HORIZONTAL_EQ_VERTICAL.
 #define INF256 (POY_INF << 8)
-template <bool EDGE>
+template <bool EDGE, bool DIR>
 __device__ __forceinline__ unsigned cell_gf(int &CB, int &EV, int &EH, int &K, unsigned &G, int lCB, int lEH, unsigned lG,
                                             int uCB, int uEV, unsigned uG, int diag, int GO256, bool lb, bool rb, bool jpos,
                                             int tagV, int tagH) {
-    int eH = min(lEH + 32, lCB + GO256);
-    int eV = min(uEV + 16, uCB + GO256);
-    if (lb) eH = INF256 + 32;
-    if (rb) eV = INF256 + 16;
-    const int nEH = eH & ~255, nEV = eV & ~255;
-    int nCB = (K & ~255) + diag;
+    // (a probe fill writes no byte: no END_* tags, nothing to clear)
+    int eH = min(lEH + (DIR ? 32 : 0), lCB + GO256);
+    int eV = min(uEV + (DIR ? 16 : 0), uCB + GO256);
+    if (lb) eH = INF256 + (DIR ? 32 : 0);
+    if (rb) eV = INF256 + (DIR ? 16 : 0);
+    const int nEH = DIR ? (eH & ~255) : eH, nEV = DIR ? (eV & ~255) : eV;
+    int nCB = (DIR ? (K & ~255) : K) + diag;
     if (EDGE && !jpos) nCB = INF256;
-    const int k = __vimin3_s32(nEV + tagV, nEH + tagH, nCB + 3);
+    const int k = DIR ? __vimin3_s32(nEV + tagV, nEH + tagH, nCB + 3) : __vimin3_s32(nEV, nEH, nCB);
     const bool fV = nEV <= k, fH = nEH <= k, fA = nCB <= k;
     // gap counters: component-wise max over the chosen predecessors (+1 on the side that gaps)
     const unsigned cD = fA ? G : 0u;
@@ -175,13 +176,21 @@ __device__ __forceinline__ unsigned cell_gf(int &CB, int &EV, int &EH, int &K, u
     unsigned w = (unsigned)(k | eH | eV);
     if (fH && fV) w |= 128u;
     CB = nCB; EV = nEV; EH = nEH; K = k;
-    return w & 0xFFu;
+    return w;      // only the low byte is meaningful: pack_dir picks it
 }
 
 // Named-barrier producer / consumer pair (the PTX manual's bar.arrive / bar.sync idiom): the producing warp
 // arrives without waiting, the consuming warp waits until both have reached the barrier.
 __device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void pair_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// low bytes of H words -> one little-endian word (PRMT: three byte permutes for four cells)
+template <int H>
+__device__ __forceinline__ unsigned pack_dir(const unsigned (&b)[H]) {
+    if constexpr (H == 1) return b[0] & 0xFFu;
+    else if constexpr (H == 2) return __byte_perm(b[0], b[1], 0x0040) & 0xFFFFu;
+    else return __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+}
 
 template <int H>
 __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed) {
@@ -337,7 +346,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
                 unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
                 if (NW > 1 && lane == 0 && warp > 0) { sCB = s_xo[warp - 1][0]; sEH = s_xo[warp - 1][1]; sG = (unsigned)s_xo[warp - 1][2]; }
-                unsigned long long packed = 0;
+                unsigned bw[H];
+                sfor<H>([&](auto hc) { bw[decltype(hc)::value] = 0u; });
                 if (warp_in_band)
                 sfor<H>([&](auto hc) {
                     constexpr int h = decltype(hc)::value;
@@ -354,18 +364,18 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         if (EDGE) lb = lb || (j == 0);
                         unsigned b;
                         if constexpr (GF)
-                            b = cell_gf<EDGE>(CB[u], EV[u], EH[u], K[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
+                            b = cell_gf<EDGE, DIR>(CB[u], EV[u], EH[u], K[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
                                               *(const int *)(s_tab + R[h].meta + C[h].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         else
                             b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
                                                R[h], C[h], s_tab, GO, lb, u == rbslot, j > 0, swaped);
-                        packed |= (unsigned long long)b << (8 * h);
+                        bw[h] = b;
                         if (!GF) {
                             if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
                         }
                     }
                 });
-                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, packed);
+                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, pack_dir<H>(bw));
                 if (NW > 1) {
                     if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
                     if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
@@ -379,7 +389,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
                 unsigned sG = __shfl_down_sync(0xffffffffu, G[0], 1);
                 if (NW > 1 && lane == 31 && warp < NW - 1) { sCB = s_xe[warp + 1][0]; sEV = s_xe[warp + 1][1]; sG = (unsigned)s_xe[warp + 1][2]; }
-                unsigned long long packed = 0;
+                unsigned bw[H];
+                sfor<H>([&](auto hc) { bw[decltype(hc)::value] = 0u; });
                 if (warp_in_band)
                 sfor<H>([&](auto hc) {
                     constexpr int h = decltype(hc)::value;
@@ -395,18 +406,18 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         if (EDGE) lb = (j == 0);
                         unsigned b;
                         if constexpr (GF)
-                            b = cell_gf<EDGE>(CB[u], EV[u], EH[u], K[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
+                            b = cell_gf<EDGE, DIR>(CB[u], EV[u], EH[u], K[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
                                               *(const int *)(s_tab + R[h].meta + C[h + 1].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         else
                             b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
                                                R[h], C[h + 1], s_tab, GO, lb, u == rbslot, j > 0, swaped);
-                        packed |= (unsigned long long)b << (8 * h);
+                        bw[h] = b;
                         if (!GF) {
                             if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
                         }
                     }
                 });
-                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, packed);
+                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, pack_dir<H>(bw));
                 if (NW > 1) {
                     if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
                     if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
