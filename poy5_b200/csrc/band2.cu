@@ -49,7 +49,7 @@ struct Ent { int ext, opn, meta; };
 template <bool GF>
 __device__ __forceinline__ Ent row_entry(const int4 v) {
     Ent e;
-    e.ext = v.x; e.opn = GF ? 0 : v.y;
+    e.ext = GF ? 0 : (v.x << 8); e.opn = GF ? 0 : (v.y << 8);     // x256: see cell_gf / cell_gen
     e.meta = ((v.w & 15) << 11);
     if (!GF) e.meta |= ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
     return e;
@@ -57,87 +57,60 @@ __device__ __forceinline__ Ent row_entry(const int4 v) {
 template <bool GF>
 __device__ __forceinline__ Ent col_entry(const int4 v, int lane) {
     Ent e;
-    e.ext = v.x; e.opn = GF ? 0 : v.y;
+    e.ext = GF ? 0 : (v.x << 8); e.opn = GF ? 0 : (v.y << 8);
     e.meta = (((v.w & 15) << 7) + (lane << 2));
     if (!GF) e.meta |= ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
     return e;
 }
 
-// One band cell.  On entry CB/EV/EH/EB/G hold the diagonal predecessor (i-1,j-1), on exit the new
-// cell.  l* = (i,j-1), u* = (i-1,j).  EDGE adds the j == 0 handling of the prologue.
-template <bool GF, bool EDGE>
-__device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, unsigned &G, int lCB, int lEH, unsigned lG,
-                                         int uCB, int uEV, unsigned uG, const Ent r, const Ent c, const char *s_tab,
-                                         int GO, bool lb, bool rb, bool jpos, bool swaped) {
+// One band cell of a pair with gap-bit symbols (4 states).  On entry CB/EV/EH/EB/G hold the diagonal predecessor
+// (i-1,j-1), on exit the new cell.  l* = (i,j-1), u* = (i-1,j).  EDGE adds the j == 0 handling of the prologue.
+// Same value-times-256 + tag scheme as cell_gf below (read that comment first); here the ALIGN_TO_* code cannot be
+// taken from the predecessor's todo code (the gap-bit surcharges differ), so it is a second tagged minimum, and
+// the block state EB brings its own END_BLOCK tag.  Byte (tagged format): bits 0-1 todo code, bits 2-3
+// ALIGN_TO code (both: 0/1 = the two gap directions in priority order, 2 = block, 3 = align), bits 4/5/6 = NOT
+// END_VERTICAL / END_HORIZONTAL / END_BLOCK, bit 7 = HORIZONTAL_EQ_VERTICAL.
+#define INF256 (POY_INF << 8)
+template <bool EDGE, bool DIR>
+__device__ __forceinline__ unsigned cell_gen(int &CB, int &EV, int &EH, int &EB, unsigned &G, int lCB, int lEH, unsigned lG,
+                                             int uCB, int uEV, unsigned uG, const Ent r, const Ent c, const char *s_tab,
+                                             int GO256, bool lb, bool rb, bool jpos, int tagV, int tagH) {
     // extend horizontal / vertical: ties take the opening (END_* flag)
-    bool stopH, stopV;
-    int nEH, nEV;
-    if (GF) {   // no gap bits: ext = ge, opn = GO + ge, and the common ge lives in the shifted table (see k_band2)
-        const int tH = lCB + GO, tV = uCB + GO;
-        stopH = !(lEH < tH); nEH = min(lEH, tH);
-        stopV = !(uEV < tV); nEV = min(uEV, tV);
-    } else {
-        const int tH = lCB + c.opn, xH = lEH + c.ext;
-        stopH = !(xH < tH); nEH = min(xH, tH);
-        const int tV = uCB + r.opn, xV = uEV + r.ext;
-        stopV = !(xV < tV); nEV = min(xV, tV);
-    }
-    if (lb) { nEH = POY_INF; stopH = false; }
-    if (rb) { nEV = POY_INF; stopV = false; }
-    int nCB, nEB = POY_INF;
-    bool eqV, eqH, eqD = false, stopB = false;
-    {
-        const int diag = GF ? *(const int *)(s_tab + r.meta + c.meta)
-                            : *(const int *)(s_tab + (r.meta & 0xFFFF) + (c.meta & 0xFFFF));
-        int m;
-        if (GF) {
-            m = __vimin3_s32(CB, EV, EH);
-            eqV = (EV == m); eqH = (EH == m);
-        } else {
-            const bool hg_i = (r.meta & M_HAS) != 0, hg_j = (c.meta & M_HAS) != 0;
-            // at the left border the reference's "previous column symbol" is the column symbol itself
-            const bool pg_j = lb ? hg_j : ((c.meta & M_PREV) != 0);
-            const bool both = hg_i && hg_j;
-            const bool clean = !(r.meta & M_PREV) && !pg_j;
-            const int dg = both ? 0 : POY_INF;
-            const int od = both ? (clean ? 0 : 2 * GO) : POY_INF;
-            const int xB = EB + dg, tB = CB + od;
-            stopB = !(xB < tB);
-            nEB = min(xB, tB);
-            const bool goz_i = (r.meta & M_GOZ) != 0, goz_j = (c.meta & M_GOZ) != 0;
-            const int v = EV + ((hg_i && !goz_j) ? GO : 0);
-            const int h = EH + ((hg_j && !goz_i) ? GO : 0);
-            const int dd = EB + ((goz_i && goz_j) ? 0 : GO);
-            m = min(__vimin3_s32(CB, v, h), dd);
-            eqV = (v == m); eqH = (h == m); eqD = (dd == m);
-        }
-        nCB = m + diag;
-    }
-    if (EDGE && !jpos) { nCB = POY_INF; nEB = POY_INF; eqV = eqH = eqD = false; stopB = false; }
-    // final minimum and its tie set
-    int fin = __vimin3_s32(nEH, nEV, nCB);
-    if (!GF) fin = min(fin, nEB);
-    const bool fH = (nEH == fin), fV = (nEV == fin), fA = (nCB == fin);
-    const bool fD = GF ? false : (nEB == fin);
-    const bool heqv = fH && fV;
+    int eH = min(lEH + c.ext + (DIR ? 32 : 0), lCB + c.opn);
+    int eV = min(uEV + r.ext + (DIR ? 16 : 0), uCB + r.opn);
+    if (lb) eH = INF256 + (DIR ? 32 : 0);
+    if (rb) eV = INF256 + (DIR ? 16 : 0);
+    const int nEH = DIR ? (eH & ~255) : eH, nEV = DIR ? (eV & ~255) : eV;
+    const int diag = *(const int *)(s_tab + (r.meta & 0xFFFF) + (c.meta & 0xFFFF));
+    const bool hg_i = (r.meta & M_HAS) != 0, hg_j = (c.meta & M_HAS) != 0;
+    // at the left border the reference's "previous column symbol" is the column symbol itself
+    const bool pg_j = lb ? hg_j : ((c.meta & M_PREV) != 0);
+    const bool both = hg_i && hg_j;
+    const bool clean = !(r.meta & M_PREV) && !pg_j;
+    const int dg = both ? 0 : INF256;
+    const int od = both ? (clean ? 0 : 2 * GO256) : INF256;
+    int eB = min(EB + dg + (DIR ? 64 : 0), CB + od);
+    const bool goz_i = (r.meta & M_GOZ) != 0, goz_j = (c.meta & M_GOZ) != 0;
+    const int v = EV + ((hg_i && !goz_j) ? GO256 : 0);
+    const int h = EH + ((hg_j && !goz_i) ? GO256 : 0);
+    const int dd = EB + ((goz_i && goz_j) ? 0 : GO256);
+    // ALIGN_TO_*: tagged minimum over the four ways into CB (tags in bits 2-3)
+    const int mk = DIR ? min(__vimin3_s32(CB + 12, v + 4 * tagV, h + 4 * tagH), dd + 8) : min(__vimin3_s32(CB, v, h), dd);
+    int nCB = (DIR ? (mk & ~255) : mk) + diag;
+    if (EDGE && !jpos) { nCB = INF256; eB = INF256 + (DIR ? 64 : 0); }
+    const int nEB = DIR ? (eB & ~255) : eB;
+    // final minimum, its todo code and its tie set
+    const int k = DIR ? min(__vimin3_s32(nEV + tagV, nEH + tagH, nCB + 3), nEB + 2) : min(__vimin3_s32(nEV, nEH, nCB), nEB);
+    const bool fV = nEV <= k, fH = nEH <= k, fA = nCB <= k, fD = nEB <= k;
     // gap counters: component-wise max over the chosen predecessors (+1 on the side that gaps)
     const unsigned cD = (fA || fD) ? G : 0u;
     const unsigned cL = fH ? lG + 1u : 0u;
     const unsigned cU = fV ? uG + 0x10000u : 0u;
     G = __vimax3_u16x2(cD, cL, cU);
-    // traceback byte
-    // priorities V > H > D > A, or H > V > D > A when the caller swapped the operands (choose_dir):
-    // the two orders differ only when V and H tie
-    unsigned todo = fV ? 0u : fH ? 1u : fD ? 2u : 3u;
-    unsigned nxt = eqV ? 0u : eqH ? 4u : eqD ? 8u : 12u;
-    if (swaped && heqv) todo = 1u;
-    if (swaped && eqV && eqH) nxt = 4u;
-    unsigned b = todo | nxt;
-    if (stopV || heqv) b |= 16u;
-    if (stopH || heqv) b |= 32u;
-    if (stopB) b |= 64u;
+    unsigned w = (unsigned)(k | mk | eH) | (unsigned)(eV | eB);
+    if (fH && fV) w |= 128u;
     CB = nCB; EV = nEV; EH = nEH; EB = nEB;
-    return b;
+    return w;      // only the low byte is meaningful: pack_dir picks it
 }
 
 // One band cell of a gap-free pair.  All DP values are carried times 256 (so a finite value stays below 2^28 and
@@ -153,7 +126,6 @@ __device__ __forceinline__ unsigned cell(int &CB, int &EV, int &EH, int &EB, uns
 // Byte (gap-free format, k_traceback decodes it when bit 6 of BandJob::swaped is set): bits 0-1 todo code (0/1 =
 // the two gap directions in priority order, 3 = align), bit 4 / 5 = NOT END_VERTICAL / END_HORIZONTAL, bit 7 =
 // HORIZONTAL_EQ_VERTICAL.
-#define INF256 (POY_INF << 8)
 template <bool EDGE, bool DIR>
 __device__ __forceinline__ unsigned cell_gf(int &CB, int &EV, int &EH, int &K, unsigned &G, int lCB, int lEH, unsigned lG,
                                             int uCB, int uEV, unsigned uG, int diag, int GO256, bool lb, bool rb, bool jpos,
@@ -229,7 +201,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     // the direction bytes and gap counters do not change; the cost is shifted back when it is stored.
     for (int x = threadIdx.x; x < 256 * 32; x += WPB * 32) {
         const int e = x >> 5;
-        s_tab_i[x] = GFK ? (cm->cost16[e] - cm->prepend[e & 15] - cm->gapext[e >> 4]) * 256 : cm->cost16[e];   // x256: see cell_gf
+        s_tab_i[x] = (GFK ? cm->cost16[e] - cm->prepend[e & 15] - cm->gapext[e >> 4] : cm->cost16[e]) * 256;   // x256: see cell_gf
     }
     __syncthreads();
     const char *s_tab = (const char *)s_tab_i;
@@ -283,14 +255,14 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     EV[u] = INF256;
                     K[u] = min(CB[u], EH[u]);
                 } else {
-                    CB[u] = h0[j0];
-                    EH[u] = j0 == 0 ? eh00 : CB[u];
-                    EV[u] = POY_INF;
+                    CB[u] = h0[j0] << 8;
+                    EH[u] = j0 == 0 ? (eh00 << 8) : CB[u];
+                    EV[u] = INF256;
                 }
-                EB[u] = GF ? POY_INF : eb[j0];
+                EB[u] = GF ? INF256 : (eb[j0] << 8);          // the stale EB row is kept unscaled in memory
                 G[u] = (unsigned)j0 & 0xFFFFu;
             } else {
-                CB[u] = EV[u] = EH[u] = EB[u] = K[u] = GF ? INF256 : POY_INF; G[u] = 0u;
+                CB[u] = EV[u] = EH[u] = EB[u] = K[u] = INF256; G[u] = 0u;
             }
         });
 
@@ -367,11 +339,11 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                             b = cell_gf<EDGE, DIR>(CB[u], EV[u], EH[u], K[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
                                               *(const int *)(s_tab + R[h].meta + C[h].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         else
-                            b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
-                                               R[h], C[h], s_tab, GO, lb, u == rbslot, j > 0, swaped);
+                            b = cell_gen<EDGE, DIR>(CB[u], EV[u], EH[u], EB[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
+                                                    R[h], C[h], s_tab, GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         bw[h] = b;
                         if (!GF) {
-                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
+                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u] >> 8;
                         }
                     }
                 });
@@ -409,11 +381,11 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                             b = cell_gf<EDGE, DIR>(CB[u], EV[u], EH[u], K[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
                                               *(const int *)(s_tab + R[h].meta + C[h + 1].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         else
-                            b = cell<GF, EDGE>(CB[u], EV[u], EH[u], EB[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
-                                               R[h], C[h + 1], s_tab, GO, lb, u == rbslot, j > 0, swaped);
+                            b = cell_gen<EDGE, DIR>(CB[u], EV[u], EH[u], EB[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
+                                                    R[h], C[h + 1], s_tab, GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         bw[h] = b;
                         if (!GF) {
-                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u];
+                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u] >> 8;
                         }
                     }
                 });
@@ -446,7 +418,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 if (u == dstar % D) {
                     int fin = __vimin3_s32(EH[u], EV[u], CB[u]);
                     if (!GF) fin = min(fin, EB[u]);
-                    if (GF) fin = (fin >> 8) + g0[lastj] + (int)(rowpk[J.off_i + lasti] & 0x0FFFFFFFu);
+                    fin >>= 8;
+                    if (GF) fin += g0[lastj] + (int)(rowpk[J.off_i + lasti] & 0x0FFFFFFFu);
                     st->cost = fin;
                     st->gapnum = max((int)(G[u] & 0xFFFFu), (int)(G[u] >> 16));
                 }

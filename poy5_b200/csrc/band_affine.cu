@@ -212,7 +212,7 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
     if (done && done[J.pair] != 1) return;  // this pair's band is not final yet (or was only probed)
     const uint8_t *si = data + J.off_i, *sj = data + J.off_j;
     const int k = J.k;
-    const bool gf_fmt = (J.swaped & 64) != 0, swaped = (J.swaped & 1) != 0;
+    const bool tagged = (J.swaped & 64) != 0, swaped = (J.swaped & 1) != 0, gf_todo = tagged && (J.swaped & 4) != 0;
     const int B = (J.lastj - J.lasti) + 2 * k + 1;
     const uint8_t *db = dir + J.dir_off;
     const int stride = J.stride;
@@ -257,14 +257,15 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
                 const int cb = (d >> 1) - c0;
                 if (r >= TB_ROWS || cb < 0 || cb >= TB_COLS) break;  // left the tile
                 unsigned b = tile[r * TB_COLS + cb];
-                if (gf_fmt) {
-                    // gap-free format (cell_gf in band2.cu) -> the general one: todo codes 0/1 are the gap directions in
-                    // priority order (H first for swapped operands), bits 4/5 are inverted, bit 7 is
-                    // HORIZONTAL_EQ_VERTICAL, and the mode after an align step is the next cell's todo code
-                    unsigned t = b & 3u;
+                if (tagged) {
+                    // tagged format (cell_gf / cell_gen in band2.cu) -> the plain one: codes 0/1 are the two gap
+                    // directions in priority order (H first for swapped operands), the END_* bits are stored
+                    // inverted and bit 7 is HORIZONTAL_EQ_VERTICAL
+                    unsigned t = b & 3u, nx = (b >> 2) & 3u;
                     if (swaped && t < 2u) t ^= 1u;
+                    if (swaped && nx < 2u) nx ^= 1u;
                     const unsigned heqv = (b & 128u) ? 48u : 0u;
-                    b = t | ((b & 48u) ^ 48u) | heqv;
+                    b = t | (nx << 2) | ((b & 112u) ^ 112u) | heqv;
                 }
                 if (mode == 4) mode = b & 3;
                 if (mode == 0) {
@@ -282,7 +283,8 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
                     PUT(pi, ni, ic); PUT(pj, nj, jc); PUT(pw, nw, POY_GAP);
                     --i; --j; ic = si[i]; jc = sj[j];
                 } else {
-                    mode = gf_fmt ? 4 : (int)((b >> 2) & 3);
+                    // gap-free pairs store no ALIGN_TO code: it equals the todo code of the cell the walk moves to
+                    mode = gf_todo ? 4 : (int)((b >> 2) & 3);
                     const int prep = cm->median32[((ic & POY_NOGAP) << 5) + (jc & POY_NOGAP)];
                     PUT_M(prep); PUT(pw, nw, prep);
                     PUT(pi, ni, ic); PUT(pj, nj, jc);

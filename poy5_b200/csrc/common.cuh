@@ -106,7 +106,7 @@ struct BandJob {          // one band fill of one pair
     int swaped;           // bit 0 operands were exchanged by the caller, bit 1 full plane (linear), bit 2 gap-free pair,
                           // bit 3 probe fill (no direction bytes), bit 4 no traceback wanted (a probe's verdict is final),
                           // bit 5 repeat of a probed threshold: restore the stale state the probe started from,
-                          // bit 6 the direction bytes are in the gap-free format of k_band2 (cell_gf)
+                          // bit 6 the direction bytes are in the tagged format of k_band2 (cell_gf / cell_gen)
     int stride;           // bytes per anti-diagonal in the direction arena
     int64_t dir_off;      // byte offset of this pair's direction block in the arena
     int64_t eb_off;       // int offset of this pair's stale-EB row in the state arena

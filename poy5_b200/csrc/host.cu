@@ -726,7 +726,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 j.off_i = h.off_i; j.off_j = h.off_j; j.lasti = h.lasti; j.lastj = h.lastj; j.k = h.k; j.pair = p;
                 j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0) | ((!linear && h.gapfree) ? 4 : 0) |
                            (h.probe ? 8 : 0) | (want_trace ? 0 : 16) | (h.repeat ? 32 : 0) |
-                           ((!linear && h.gapfree && h.dclass != 0) ? 64 : 0);
+                           ((!linear && h.dclass != 0) ? 64 : 0);
                 j.stride = h.stride; j.dir_off = doff; j.eb_off = h.eb_off;
                 doff += (h.dir_bytes + 255) & ~255ll;
                 if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
