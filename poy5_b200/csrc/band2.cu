@@ -180,7 +180,9 @@ __device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed)
 // (the whole byte assembly is dead code then).  The host uses it for fills it expects not to be the last one.
 // resident CTAs the register allocation aims at: the replicated table (32 KB) allows 6 per SM; the 4-warp class of
 // gap-free pairs is the one where a few registers decide between 4 and 5
-template <int NW, bool GFK> struct MinBlocks { static constexpr int v = (GFK && NW == 4) ? 5 : 1; };
+template <int NW, bool GFK> struct MinBlocks {
+    static constexpr int v = GFK ? (NW == 4 ? 5 : 1) : (NW == 4 ? 3 : NW == 3 ? 4 : NW == 6 ? 2 : 1);
+};
 
 template <int D, int NW, int WPB, bool GFK, bool DIR>
 __global__ void __launch_bounds__(WPB * 32, MinBlocks<NW, GFK>::v)
