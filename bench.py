@@ -165,7 +165,20 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else that prints there (NCCL's version banner, ...) was
+    redirected to stderr at start-up"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     lengths = tuple(int(x) for x in args.lengths.split(","))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +204,7 @@ def main():
                     cpu_baseline=dict(value=val, unit="GCUPS", cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                     alignments_per_s=r["alignments_per_s"],
                     e2e=dict(value=val, unit="GCUPS", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -268,15 +281,13 @@ def main():
 
     seg_events = {}
 
-    def reduce_costs(costs):
-        # candidate min-reduction: (cost << 32 | index) packed int64, min over the batch and over ranks
+    def local_min(costs):
+        # candidate min-reduction inside the rank: (cost << 32 | index) packed int64, min over the batch
         packed = (costs.to(torch.int64) << 32) | torch.arange(costs.numel(), device=dev, dtype=torch.int64)
-        m = packed.min().reshape(1)
-        if world > 1:
-            dist.all_reduce(m, op=dist.ReduceOp.MIN)
-        return m
+        return packed.min().reshape(1)
 
     def step_resident(record=False):
+        best.fill_(torch.iinfo(torch.int64).max)
         for wi, w in enumerate(work):
             if record:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
@@ -288,11 +299,13 @@ def main():
             sequence.align_affine_3_dev(ctx, cm, pool, w["si"], w["sj"], w["d_sw"].data_ptr(), w["d_out_off"].data_ptr(),
                                         w["d_cost1"].data_ptr(), d_outs[0].data_ptr(), d_outs[1].data_ptr(),
                                         d_outs[2].data_ptr(), d_outs[3].data_ptr(), w["d_len"].data_ptr())
-            best.copy_(torch.minimum(reduce_costs(w["d_cost0"]), reduce_costs(w["d_cost1"])))
+            best.copy_(torch.minimum(best, torch.minimum(local_min(w["d_cost0"]), local_min(w["d_cost1"]))))
             if record:
                 e2.record(stream)
                 seg_events[wi] = (e0, e1, e2)
             pool.close()
+        if world > 1:      # one MIN all-reduce of the packed (cost, candidate) per round, not per batch
+            dist.all_reduce(best, op=dist.ReduceOp.MIN)
 
     def e2e_lane(lane, items):
         c, m, h_outs = lane["ctx"], lane["cm"], lane["h_outs"]
@@ -316,7 +329,12 @@ def main():
         order = sorted(work, key=lambda w: -w["cells"])
         with ThreadPoolExecutor(len(lanes)) as ex:
             futs = [ex.submit(e2e_lane, lanes[t], order[t::len(lanes)]) for t in range(len(lanes))]
-            return min(f.result() for f in futs)
+            res = min(f.result() for f in futs)
+        if world > 1:
+            t = torch.tensor([res], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            res = int(t.item())
+        return res
 
     def barrier():
         if world > 1:
@@ -418,7 +436,7 @@ def main():
                     config=make_config(args.pairs, lengths, world, sum(w["data"].nbytes for w in work)),
                     alignments_per_s=world * total_aln / (ms * 1e-3), breakdown=breakdown, clocks=clocks, e2e=e2e,
                     gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
