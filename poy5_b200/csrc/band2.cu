@@ -1,30 +1,31 @@
-// Register-resident Ukkonen-band fill, second generation: k_band2<D, NW, GF>.
+// Register-resident Ukkonen-band fill: k_band2<D, NW, WPB, GF, DIR>.
 //
-// Same algorithm and bit-exact semantics as band_affine.cu (which keeps the documentation of the
-// band geometry, the direction byte and the reference citations: algn_newkk_test_aff /
-// algn_newkk_fill_a_row_aff / ASSIGN_MINIMUM / algn_fill_gapnum, src/algn.c:2186-2306, 2113-2180,
-// 1936-1981, 126-176).  What changes is how the work is mapped to the machine:
+// Same algorithm and bit-exact results as the fallback in band_affine.cu (which keeps the documentation of the
+// band geometry and the reference citations: algn_newkk_test_aff / algn_newkk_fill_a_row_aff / ASSIGN_MINIMUM /
+// algn_fill_gapnum, src/algn.c:2186-2306, 2113-2180, 1936-1981, 126-176).  What changes is how the work is mapped
+// to the machine:
 //
-//  * one CTA of NW warps per pair; thread t owns the D diagonals [t*D, (t+1)*D) and keeps the
-//    latest cell of each in registers, so a CTA covers bands up to NW*32*D diagonals
-//    (D=16, NW=8: 4096).  Strip edges cross lanes by one __shfl per sub-step and cross warps through
-//    12 bytes of shared memory + one __syncthreads per sub-step;
-//  * the tie logic is branch free: every tie mask of the reference equals "candidate == minimum"
-//    (a strict improvement resets the mask, an equal candidate joins it), so a cell is a handful of
-//    VIMNMX/VIADDMNMX, ISETP and SEL instead of nested compare chains;
-//  * per-row / per-column gap parameters ride in sliding register windows (an anti-diagonal step
-//    moves every thread one row down and one column right), so a cell does no global loads;
-//  * the two unsigned-short gap counters travel packed in one register and are updated with the
-//    DPX 16x2 max (__vimax3_u16x2); exact while len_i + len_j < 65535 (longer pairs take the
-//    generic kernel);
-//  * the 16x16 cost table is replicated once per shared-memory bank (32 KB) so the per-cell lookup
-//    is conflict free whatever symbols the 32 lanes hold;
-//  * the anti-diagonals a < delta+k+2, where some cell of the band still lies outside the matrix,
-//    run a predicated prologue; afterwards every cell with d < B either is valid or lies beyond the
-//    last row/column, where garbage can no longer reach a valid cell (the right-border rule cuts the
-//    only path), so the steady-state loop carries no validity predicates at all;
-//  * GF = both sequences free of gap-bit symbols: the EB state and everything that depends on gap
-//    bits disappear (EB >= INF can neither win nor tie a minimum there).
+//  * one CTA of NW warps per pair; thread t owns the D diagonals [t*D, (t+1)*D) and keeps the latest cell of each
+//    in registers, so a CTA covers bands up to NW*32*D diagonals (D=8, NW=16: 4096).  Strip edges cross lanes by
+//    one __shfl per sub-step and cross warps through 12-byte shared-memory mailboxes guarded by pairwise named
+//    barriers (producer bar.arrive, consumer bar.sync); NW == 1 packs 8 independent warps into a CTA;
+//  * the tie logic is branch free and mostly compare free: all values are carried times 256 and the low byte
+//    holds tie-break tags, so the todo / ALIGN_TO codes and the END_* bits of the direction byte are the low bits
+//    of the minima themselves (cell_gf / cell_gen);
+//  * per-row / per-column gap parameters ride in sliding register windows (an anti-diagonal step moves every
+//    thread one row down and one column right), so a cell does no global loads;
+//  * the two unsigned-short gap counters travel packed in one register and are updated with the DPX 16x2 max
+//    (__vimax3_u16x2); exact while len_i + len_j < 65535 (longer pairs take the fallback kernel);
+//  * the 16x16 cost table is replicated once per shared-memory bank (32 KB) so the per-cell lookup is conflict
+//    free whatever symbols the 32 lanes hold;
+//  * the anti-diagonals a < delta+k+2, where some cell of the band still lies outside the matrix, run a
+//    predicated prologue; afterwards every cell with d < B either is valid or lies beyond the last row/column,
+//    where garbage can no longer reach a valid cell (the right-border rule cuts the only path), so the
+//    steady-state loop carries no validity predicates at all;
+//  * GF = both sequences free of gap-bit symbols: the EB state and everything that depends on gap bits
+//    disappear (EB >= INF can neither win nor tie a minimum there), and the gap extensions move into the table
+//    (shifted domain, see k_band2);
+//  * DIR = false is the probe fill: same states and gap counters, no direction bytes.
 #include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
@@ -165,11 +166,11 @@ __device__ __forceinline__ unsigned pack_dir(const unsigned (&b)[H]) {
 }
 
 template <int H>
-__device__ __forceinline__ void store_dir(uint8_t *p, unsigned long long packed) {
+__device__ __forceinline__ void store_dir(uint8_t *p, unsigned packed) {
+    static_assert(H == 1 || H == 2 || H == 4, "one to four direction bytes per thread and sub-step");
     if (H == 1) *p = (uint8_t)packed;
     else if (H == 2) *(uint16_t *)p = (uint16_t)packed;
-    else if (H == 4) *(uint32_t *)p = (uint32_t)packed;
-    else *(unsigned long long *)p = packed;
+    else *(uint32_t *)p = packed;
 }
 
 }  // namespace

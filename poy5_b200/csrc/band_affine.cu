@@ -29,6 +29,10 @@
 //   bit 4     vertical run stops here   (END_VERTICAL | HORIZONTAL_EQ_VERTICAL)
 //   bit 5     horizontal run stops here (END_HORIZONTAL | HORIZONTAL_EQ_VERTICAL)
 //   bit 6     block-diagonal run stops here (END_BLOCK)
+// This plain format is what the fallback kernel below writes.  The register-resident kernels of band2.cu write a
+// "tagged" variant (same fields; the two gap codes are stored in priority order instead of V/H order, the END_*
+// bits inverted, bit 7 = HORIZONTAL_EQ_VERTICAL, no ALIGN_TO field for gap-free pairs); BandJob::swaped bit 6
+// tells k_traceback which one it is reading.
 //
 // State that the reference leaves behind from one band fill to the next (its row
 // buffers are not re-initialised between threshold doublings): row 0 of EB and
