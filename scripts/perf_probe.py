@@ -13,11 +13,12 @@ ap.add_argument("--pairs", type=int, default=20000)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--mode", default="both")
 ap.add_argument("--decorated", type=float, default=0.10)
+ap.add_argument("--linear", action="store_true", help="linear-gap cost model (algn_CAML_simple_2 / align_2d) instead of affine")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
 ctx = pb.Context(0, stream.cuda_stream)
-cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 1, 3).full)
+cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(1, 1, None if a.linear else 3).full)
 data, off = synth.pair_pool(1234 + a.L, 0, a.pairs, a.L, decorated=a.decorated)
 n = a.pairs
 lens = np.diff(off)
@@ -32,6 +33,10 @@ def timed(fn):
 if a.mode in ("both", "cost"):
     t, cost = timed(lambda: sequence.Align.cost_2(ctx, cm, pool, ia, ib))
     print("cost-only  L=%d pairs=%d: %.1f ms  %.1f GCUPS  %.0f aln/s" % (a.L, n, t * 1e3, cells / t / 1e9, n / t))
+if a.linear:
+    t, r = timed(lambda: sequence.Align.align_2(ctx, cm, pool, ia, ib))
+    print("linear align_2 L=%d pairs=%d: %.1f ms  %.1f GCUPS-eq  %.0f aln/s" % (a.L, n, t * 1e3, cells / t / 1e9, n / t))
+    sys.exit(0)
 if a.mode in ("both", "align"):
     t, r = timed(lambda: sequence.Align.align_affine_3(ctx, cm, pool, ia, ib, want=("median",), stats=True))
     st = r["stats"]
