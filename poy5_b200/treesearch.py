@@ -287,17 +287,44 @@ def apply_tbr(tree, move):
 class ShardedBackend:
     """N>1: candidates are independent, so `distance` batches are dealt to the ranks by estimated cells (LPT),
     every rank evaluates its shard and the per-candidate costs are combined with ONE all-reduce (each rank
-    contributes its own entries, zeros elsewhere).  Medians (the downpass) are replicated: every rank needs
-    every node sequence for the next level anyway."""
+    contributes its own entries, zeros elsewhere).  Medians (the downpass) are replicated by default -- every rank
+    needs every node sequence for the next level anyway -- or, for wide levels, sharded and all-gathered
+    (`min_shard_medians`)."""
 
-    def __init__(self, backend, device=None):
+    def __init__(self, backend, device=None, min_shard_medians=1 << 30):
         import torch.distributed as dist
-        self.b, self.device = backend, device
+        self.b, self.device, self.min_shard_medians = backend, device, min_shard_medians
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
 
     def median(self, pairs):
-        return self.b.median(pairs)
+        """Batches of `min_shard_medians` pairs or more are dealt to the ranks like the candidates; the new medians
+        (sequence + cost2, padded rows) are exchanged with ONE all-gather per tree level."""
+        import torch
+        import torch.distributed as dist
+        from . import shard
+        if self.world == 1 or len(pairs) < self.min_shard_medians:
+            return self.b.median(pairs)
+        work = [(len(a) - 1) * (len(b) - 1) for a, b in pairs]
+        parts = shard.lpt_partition(work, self.world)
+        mine = parts[self.rank]
+        res = self.b.median([pairs[i] for i in mine])
+        cap = 16 + max(len(a) + len(b) for a, b in pairs)
+        rows = max(len(p) for p in parts)
+        buf = np.zeros((rows, cap), np.uint8)
+        for q, (seq, c2) in enumerate(res):
+            buf[q, :16].view(np.int64)[:] = (len(seq), c2)
+            buf[q, 16:16 + len(seq)] = seq
+        t = torch.from_numpy(buf).to(self.device) if self.device is not None else torch.from_numpy(buf)
+        got = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(got, t)
+        out = [None] * len(pairs)
+        for r, g in enumerate(got):
+            g = g.cpu().numpy()
+            for q, i in enumerate(parts[r]):
+                ln, c2 = g[q, :16].view(np.int64)
+                out[int(i)] = (g[q, 16:16 + int(ln)].copy(), int(c2))
+        return out
 
     def distance(self, pairs):
         import torch
@@ -313,3 +340,144 @@ class ShardedBackend:
             out[torch.as_tensor(mine, device=self.device)] = torch.as_tensor(vals, dtype=torch.int64, device=self.device)
         dist.all_reduce(out, op=dist.ReduceOp.SUM)
         return [int(x) for x in out.cpu().tolist()]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# SPR round over several loci with incremental medians (BASELINE configs #4 / #5)
+# ------------------------------------------------------------------------------------------------------------
+
+def all_directions(tree, loci, backend):
+    """All-direction medians of one tree for every locus (`loci[l][taxon]`), all loci in lockstep: one median
+    batch per tree level for the whole data set (the Array_ops.map over loci of src/seqCS.ml:2232-2345 turned
+    inside out)."""
+    return directional_medians_multi([(tree, dict(enumerate(ls)), None) for ls in loci], backend)
+
+
+def downpass(tree, loci, backend, root=None):
+    """Post-order pass towards the root edge only (n-2 medians + the root median per locus, level-synchronous;
+    src/allDirChar.ml:2033-2125).  Returns (total cost over loci, per-locus dict of towards-root medians)."""
+    root = tree.edges()[0] if root is None else root
+    parent, order = {root[0]: root[1], root[1]: root[0]}, [root[0], root[1]]
+    for x in order:
+        for y in tree.adj[x]:
+            if y not in parent:
+                parent[y] = x; order.append(y)
+    kids = {x: [y for y in tree.adj[x] if parent.get(y) == x and parent[x] != y] for x in order}
+    height = {}
+    for x in reversed(order):
+        height[x] = 1 + max((height[k] for k in kids[x]), default=-1)
+    dms = [{(x, parent[x]): (ls[x], 0) for x in order if not kids[x]} for ls in loci]
+    for h in range(1, max(height.values()) + 1):
+        lvl = [x for x in order if height[x] == h]
+        res = backend.median([(dm[(kids[x][0], x)][0], dm[(kids[x][1], x)][0]) for dm in dms for x in lvl])
+        for k, dm in enumerate(dms):
+            for q, x in enumerate(lvl):
+                seq, c2 = res[k * len(lvl) + q]
+                dm[(x, parent[x])] = (seq, c2 + dm[(kids[x][0], x)][1] + dm[(kids[x][1], x)][1])
+    a, b = root
+    res = backend.median([(dm[(a, b)][0], dm[(b, a)][0]) for dm in dms])
+    total = sum(c2 + dm[(a, b)][1] + dm[(b, a)][1] for (seq, c2), dm in zip(res, dms))
+    return int(total), dms
+
+
+def spr_prunings(tree, n_leaves):
+    """Every (u, v): cut edge u-v, prune the clade on v's side, rejoin it inside the rest (u's side).  Prunings whose
+    rest has fewer than three leaves have no alternative position and are left out."""
+    out = []
+    for (a, b) in tree.edges():
+        for (u, v) in ((a, b), (b, a)):
+            rest = tree.component(u, v)
+            if sum(1 for x in rest if x < n_leaves) >= 3:
+                out.append((u, v))
+    return out
+
+
+def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64):
+    """One SPR neighbourhood over several loci.  For the pruning (u, v) the rest tree is u's side with u suppressed
+    (its neighbours x1, x2 joined); only the medians that *see* the cut are recomputed, top-down from the cut:
+
+        up[x1] = dm[(x2, u)], up[x2] = dm[(x1, u)]                  (reused from the unbroken tree)
+        up[c]  = median(up[a], dm[(s, a)])    for the children c, s of a (away from the cut), level by level
+        join edge a-c:  em = median(up[c], dm[(c, a)]);  estimate = distance(dm[(v, u)], em) + both accumulated costs
+
+    which is what AllDirNode's lazy directional medians recompute after a break (src/allDirChar.ml:2132-2204) and
+    the Parmap candidate seam of src/ptree.ml:1356-1453 evaluates.  All prunings of a chunk and all loci advance
+    in lockstep: one median batch per level, one edge-median batch, ONE distance batch per chunk; the estimate of
+    a candidate is the sum over loci.  Returns (best estimate, (pruning, join edge), number of candidates,
+    number of alignments issued); ties resolve to the first candidate in enumeration order."""
+    n = len(loci[0])
+    dms = all_directions(tree, loci, backend) if dms is None else dms
+    prunings = spr_prunings(tree, n) if prunings is None else list(prunings)
+    nl = len(loci)
+    best, ncand, naln = None, 0, 0
+    for c0 in range(0, len(prunings), chunk):
+        part = prunings[c0:c0 + chunk]
+        ups, levels, joins = [], [], []       # per pruning: up[l][node]; nodes by depth; join edges (a, c)
+        for (u, v) in part:
+            x1, x2 = [w for w in tree.adj[u] if w != v]
+            up = [{x1: dm[(x2, u)], x2: dm[(x1, u)]} for dm in dms]
+            lv, frontier, par = [], [(x1, u), (x2, u)], {}
+            while frontier:
+                nxt = []
+                for a, pa in frontier:
+                    ch = [w for w in tree.adj[a] if w != pa]
+                    if ch:
+                        nxt += [(ch[0], a), (ch[1], a)]
+                        par[ch[0]] = (a, ch[1]); par[ch[1]] = (a, ch[0])
+                frontier = nxt
+                if nxt:
+                    lv.append([c for c, _ in nxt])
+            ups.append(up); levels.append((lv, par))
+            joins.append([(par[c][0], c) for l_ in lv for c in l_])
+        for d in range(max(len(lv) for lv, _ in levels)):
+            batch, own = [], []
+            for k, (lv, par) in enumerate(levels):
+                if d < len(lv):
+                    for c in lv[d]:
+                        a, s = par[c]
+                        for l in range(nl):
+                            batch.append((ups[k][l][a][0], dms[l][(s, a)][0])); own.append((k, l, c, a, s))
+            naln += len(batch)
+            for (k, l, c, a, s), (seq, c2) in zip(own, backend.median(batch)):
+                ups[k][l][c] = (seq, c2 + ups[k][l][a][1] + dms[l][(s, a)][1])
+        batch, own = [], []
+        for k, js in enumerate(joins):
+            for (a, c) in js:
+                for l in range(nl):
+                    batch.append((ups[k][l][c][0], dms[l][(c, a)][0])); own.append((k, l, a, c))
+        naln += len(batch)
+        ems = {}
+        for (k, l, a, c), (seq, c2) in zip(own, backend.median(batch)):
+            ems[(k, l, a, c)] = (seq, c2 + ups[k][l][c][1] + dms[l][(c, a)][1])
+        cand, meta = [], []
+        for k, ((u, v), js) in enumerate(zip(part, joins)):
+            for (a, c) in js:
+                base = 0
+                for l in range(nl):
+                    em = ems[(k, l, a, c)]
+                    cand.append((dms[l][(v, u)][0], em[0])); base += em[1] + dms[l][(v, u)][1]
+                meta.append(((u, v), (a, c), base))
+        naln += len(cand)
+        d = np.asarray(backend.distance(cand), np.int64).reshape(len(meta), nl).sum(axis=1)
+        est = d + np.array([m[2] for m in meta], np.int64)
+        if len(est):
+            q = int(np.argmin(est))
+            if best is None or int(est[q]) < best[0]:
+                best = (int(est[q]), meta[q][0], meta[q][1], ncand + q)
+        ncand += len(meta)
+    if best is None:
+        return None, None, 0, naln
+    return best[0], (best[1], best[2]), ncand, naln
+
+
+def apply_spr(tree, move):
+    """prune v's clade at (u, v), suppress u, split the join edge with u and hang the clade back on it"""
+    (u, v), (a, c) = move
+    t = tree.copy()
+    t.remove_edge(u, v)
+    x1, x2 = t.adj[u]
+    t.remove_edge(u, x1); t.remove_edge(u, x2)
+    t.add_edge(x1, x2)
+    t.remove_edge(a, c)
+    t.add_edge(a, u); t.add_edge(u, c); t.add_edge(u, v)
+    return t

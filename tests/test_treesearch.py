@@ -81,3 +81,84 @@ def test_sharded_candidates_gloo(port):
     single = run(OracleBackend(port, full, orig), taxa(5, 6, 50))
     for r in res:
         assert (r[1], r[2], r[3]) == (single[1], single[2], single[6])
+
+
+# ---- SPR round over several loci with incremental medians (BASELINE configs #4 / #5) ----
+
+def loci_taxa(seed, n, lengths):
+    return [taxa(seed + 17 * k, n, L) for k, L in enumerate(lengths)]
+
+
+def run_spr(backend, loci):
+    """Wagner tree of locus 0, downpass cost, one SPR round over all loci, exact cost of the rearranged tree"""
+    tree = treesearch.wagner_build(loci[0], backend)
+    c0, _ = treesearch.downpass(tree, loci, backend)
+    est, move, ncand, naln = treesearch.spr_round(tree, loci, backend, chunk=5)
+    t2 = treesearch.apply_spr(tree, move)
+    c1, _ = treesearch.downpass(t2, loci, backend)
+    return tree.edges(), c0, est, move, ncand, naln, t2.edges(), c1
+
+
+def test_spr_round_oracle(port):
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    loci = loci_taxa(7, 7, (50, 70))
+    b = OracleBackend(port, full, orig)
+    r = run_spr(b, loci)
+    n = 7
+    assert len(r[6]) == 2 * n - 3 and sorted(x for e in r[6] for x in e if x < n) == sorted(
+        x for e in r[0] for x in e if x < n)
+    assert r[4] > 20 and r[1] > 0 and r[7] > 0
+    # downpass == sum over loci of the single-locus tree cost rooted on the same edge
+    tree = treesearch.wagner_build(loci[0], b)
+    assert r[1] == sum(treesearch.tree_cost(tree, ls, b) for ls in loci)
+    # chunking does not change the neighbourhood or its best estimate
+    est2, move2, ncand2, _ = treesearch.spr_round(tree, loci, b, chunk=1000)
+    assert (est2, move2, ncand2) == (r[2], r[3], r[4])
+    # the estimate of the winning move is what the driver says it is: distance(clade, edge median) + both sides
+    dms = treesearch.all_directions(tree, loci, b)
+    est3, move3, _, _ = treesearch.spr_round(tree, loci, b, dms=dms, prunings=[r[3][0]])
+    assert (est3, move3) == (r[2], r[3])
+
+
+@pytest.mark.gpu
+def test_spr_gpu_matches_oracle_replay(ctx, port):
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.seqcs import Heuristic
+    t2d = Two_D.of_transformations_and_gaps(1, 1, 3)
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    h = Heuristic(pb.CostModel(ctx, t2d.full), pb.CostModel(ctx, t2d.original))
+    loci = loci_taxa(23, 8, (120, 90, 150))
+    got = run_spr(treesearch.GpuBackend(ctx, h), loci)
+    ref = run_spr(OracleBackend(port, full, orig), loci)
+    assert got == ref
+
+
+def _spr_worker(rank, world, port_no, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.port import Port
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    b = treesearch.ShardedBackend(OracleBackend(Port(), full, orig), min_shard_medians=4)
+    r = run_spr(b, loci_taxa(9, 6, (40, 55)))
+    q.put((rank, r[1:6], r[7]))
+    dist.destroy_process_group()
+
+
+def test_sharded_spr_and_medians_gloo(port):
+    world = 2
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    pn = 31700 + os.getpid() % 2000
+    procs = [ctxm.Process(target=_spr_worker, args=(r, world, pn, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    single = run_spr(OracleBackend(port, full, orig), loci_taxa(9, 6, (40, 55)))
+    for r in res:
+        assert (r[1], r[2]) == (single[1:6], single[7])
