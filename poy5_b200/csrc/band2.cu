@@ -468,10 +468,22 @@ int band2_stride_for(int cls, long long B) {
     return (int)((B + 255) / 256) * 128;
 }
 
+// lowlat: shapes for rounds with so few pairs that the GPU is mostly idle and the round's duration is the wavefront
+// latency of ONE pair (anti-diagonals x time per sub-step).  The same band is then spread over 2-4x as many warps
+// with 2 or 4 diagonals per thread: the per-sub-step dependency chain shrinks accordingly.  The direction-byte
+// layout (byte d/2 of anti-diagonal a) and the stride do not depend on the shape, so the traceback is unchanged.
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
-                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, bool lowlat) {
     if (njobs <= 0) return cudaSuccess;
 #define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir)
+    if (lowlat)
+        switch (cls) {
+            case 128: L1(2, 2);
+            case 256: L1(2, 4);
+            case 512: L1(2, 8);
+            case 768: L1(4, 6);
+            case 1024: L1(4, 8);
+        }
     switch (cls) {
         case 64: L1(2, 1);
         case 128: L1(4, 1);

@@ -130,7 +130,7 @@ cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, co
 cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
                                int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost, int wide);
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
-                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir);
+                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, bool lowlat = false);
 int band2_class_for(long long B);
 int band2_stride_for(int cls, long long B);
 cudaError_t launch_band_lin(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,

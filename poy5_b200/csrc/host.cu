@@ -646,7 +646,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const int gen_blocks = ctx->sm_count * 2;
 
     const char *tr = getenv("POY_TRACE");
-    const bool trace = tr && tr[0] == '1';
+    const bool trace = tr && (tr[0] == '1' || tr[0] == '2');
+    const bool trace_rounds = tr && tr[0] == '2';   // POY_TRACE=2: one line per threshold-doubling round
     double t_prep = 0, t_wait = 0; int rounds = 0, waves = 0;
     long long n_repeat = 0, n_probe = 0, n_full = 0;
     const char *pe = getenv("POY_PROBE");   // POY_PROBE=0 turns the probe fills off, 2 forces them on small batches too (test hook)
@@ -655,8 +656,12 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const bool use_probes = !(pe && pe[0] == '0') && (n >= 1024 || (pe && pe[0] == '2'));
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
+    // POY_LOWLAT=0 turns the low-latency kernel shapes off, 2 forces them (test hook); default: rounds with at most
+    // two pairs per SM, where the round lasts as long as one pair's wavefront (see launch_band2)
+    const char *ll = getenv("POY_LOWLAT");
     while (!active.empty()) {
         ++rounds;
+        const bool lowlat = !(ll && ll[0] == '0') && ((ll && ll[0] == '2') || (int64_t)active.size() <= 2 * (int64_t)ctx->sm_count);
         // band geometry of this round (algn_newkk_increaseT_aff / algn_newkk_test_aff, src/algn.c:2311-2336, 2195-2196)
         for (int p : active) {
             HostPair &h = hp[p];
@@ -751,7 +756,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 if (cls != 0) {
                     cudaError_t le;
                     if (linear) le = launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch & 15), d_state, d_dir);
-                    else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, pr != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir);
+                    else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, pr != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir, lowlat);
                     if (le != cudaSuccess) { ctx->stream = main_stream; return cuda_fail(ctx, le, "band fill launch"); }
                 } else {
                     void *v_work;
@@ -790,6 +795,14 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         }
         CK(cudaMemcpyAsync(h_done, d_done, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (trace_rounds) {
+            int hist[4097 / 64 + 1] = {0}, ngf = 0, npr = 0;
+            for (int p : active) { hist[hp[p].dclass / 64]++; ngf += hp[p].gapfree; npr += hp[p].probe; }
+            fprintf(stderr, "[poy5_b200]   round %d: %zu active (%d gap-free, %d probes), %.2f ms since batch start; classes:", rounds,
+                    active.size(), ngf, npr, (t_prep + t_wait) * 1e3);
+            for (int c = 0; c <= 4096 / 64; ++c) if (hist[c]) fprintf(stderr, " %d:%d", c * 64, hist[c]);
+            fprintf(stderr, "\n");
+        }
         std::vector<int> next;
         next.reserve(active.size());
         for (int p : active) {

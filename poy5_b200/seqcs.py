@@ -17,9 +17,14 @@ class Heuristic:
 def _is_empty(pool):
     """Sequence.is_empty (src/sequence.ml:241-251): every symbol equals the gap code."""
     if getattr(pool, "_empty", None) is None:
-        nongap = (pool.data != 16)
-        cs = np.concatenate([[0], np.cumsum(nongap, dtype=np.int64)])
-        pool._empty = (cs[pool.offsets[1:]] - cs[pool.offsets[:-1]]) == 0
+        if pool.nseq == 0:
+            pool._empty = np.zeros(0, bool)
+        elif (pool.lens > 0).all():
+            # per-sequence "any symbol differs from the gap code" (segments are non-empty: reduceat is exact)
+            pool._empty = np.maximum.reduceat((pool.data != 16).view(np.uint8), pool.offsets[:-1]) == 0
+        else:
+            cs = np.concatenate([[0], np.cumsum(pool.data != 16, dtype=np.int64)])
+            pool._empty = (cs[pool.offsets[1:]] - cs[pool.offsets[:-1]]) == 0
     return pool._empty
 
 
@@ -47,6 +52,26 @@ class DOS:
                     out[m] = Align.cost_2(ctx, cm, pool, a[idx][m], b[idx][m], deltaw=int(v))
                 res[idx] = out
         return res
+
+    @staticmethod
+    def median_cost(ctx, h, pool, a, b):
+        """The part of DOS.median a tree pass consumes -- the median sequence and cost2 (affine model; same
+        empty-child rule) -- without reading the aligned rows / median_wg back or computing cost2_max.
+        Returns (list of sequences, int64 costs)."""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        n = len(a)
+        empty = _is_empty(pool)
+        ea, eb = empty[a], empty[b]
+        seqs, cost = [None] * n, np.zeros(n, np.int64)
+        for p in np.flatnonzero(ea | eb):
+            seqs[p] = pool.seq(b[p] if ea[p] else a[p]).copy()
+        idx = np.flatnonzero(~(ea | eb))
+        if len(idx):
+            r = Align.align_affine_3(ctx, h.c2_full, pool, a[idx], b[idx], want=("median",))
+            for q, p in enumerate(idx):
+                seqs[p] = r["median"][q]
+            cost[idx] = r["cost"]
+        return seqs, cost
 
     @staticmethod
     def median(ctx, h, pool, a, b):

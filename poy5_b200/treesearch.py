@@ -22,8 +22,11 @@ import numpy as np
 class GpuBackend:
     """Batches go through libpoy5b200.so (seqcs.DOS.median / DOS.distance)."""
 
-    def __init__(self, ctx, h):
+    def __init__(self, ctx, h, lean=True):
+        """lean: medians read back only what a tree pass consumes (sequence + cost2, DOS.median_cost) instead of
+        the full DOS.median record (aligned children, median_wg, cost2_max); affine models only"""
         self.ctx, self.h = ctx, h
+        self.lean = lean and h.c2_full.host.cost_model_type == 1
         self.n_median = self.n_distance = 0
         self.cells_distance = 0
 
@@ -43,9 +46,13 @@ class GpuBackend:
         if not pairs:
             return []
         pool, ia, ib = self._pool(pairs)
+        self.n_median += len(pairs)
+        if self.lean:
+            seqs, cost = DOS.median_cost(self.ctx, self.h, pool, ia, ib)
+            pool.close()
+            return list(zip(seqs, cost.tolist()))
         r = DOS.median(self.ctx, self.h, pool, ia, ib)
         pool.close()
-        self.n_median += len(pairs)
         return [(np.array(r["sequence"][p], np.uint8), int(r["cost2"][p])) for p in range(len(pairs))]
 
     def distance(self, pairs):

@@ -71,6 +71,8 @@ def main():
     ap.add_argument("--prunings", type=int, default=0, help="sample size; 0 = the whole SPR neighbourhood")
     ap.add_argument("--chunk", type=int, default=32, help="prunings per candidate batch")
     ap.add_argument("--check", type=int, default=0, help="replay this many medians and candidates on the CPU checker")
+    ap.add_argument("--full-median", action="store_true", help="read back the whole DOS.median record per node")
+    ap.add_argument("--profile", action="store_true", help="cProfile of the SPR round to stderr")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -90,7 +92,7 @@ def main():
     lens = [int(rng.integers(a.lmin, a.lmax + 1)) for _ in range(a.loci)]
     loci = [make_taxa(a.seed + 17 * k, a.taxa, L) for k, L in enumerate(lens)]
     tree = random_tree(a.seed, a.taxa)
-    gb = treesearch.GpuBackend(ctx, h)
+    gb = treesearch.GpuBackend(ctx, h, lean=not a.full_median)
     back = treesearch.ShardedBackend(gb, device=torch.device("cuda", local), min_shard_medians=64 * world)
     rec = Recorder(back, 1) if a.check else back
     treesearch.downpass(random_tree(1, 6), [make_taxa(2, 6, 200)], back)         # warm-up
@@ -111,7 +113,13 @@ def main():
     m0, d0, c0 = gb.n_median, gb.n_distance, gb.cells_distance
     if a.check:
         rec.every = max(1, (len(pr) * 4 * a.taxa * a.loci) // max(1, a.check))
+    if a.profile:
+        import cProfile, pstats
+        prof = cProfile.Profile(); prof.enable()
     est, move, ncand, naln = treesearch.spr_round(tree, loci, rec, dms=dms, prunings=pr, chunk=a.chunk)
+    if a.profile:
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(28)
     sync(); t3 = time.perf_counter()
     if world > 1:
         tot = torch.tensor([gb.n_median - m0, gb.n_distance - d0, gb.cells_distance - c0], dtype=torch.int64, device="cuda")

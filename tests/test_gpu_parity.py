@@ -182,6 +182,42 @@ def test_probe_fills_do_not_change_results(ctx, port, monkeypatch, rname):
     cm.close(); pool.close()
 
 
+@pytest.mark.parametrize("rname", ["R1", "R2", "R3"])
+def test_low_latency_shapes_do_not_change_results(ctx, port, monkeypatch, rname):
+    """rounds with few pairs spread a band over more warps (2 / 4 diagonals per thread); forced on and off over
+    band classes 64 ... 2048, gap-free and gap-bit pairs, compared with each other and with the oracle"""
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES[rname])
+    pc = port.cm(full)
+    rng = np.random.default_rng(77)
+    seqs, ia, ib = synth.pair_batch(5, 60, 420, frac_decorated=0.5, jitter=0.3)
+    seqs = list(seqs)
+    extra_a, extra_b = [], []
+    for q in range(24):                      # unrelated pairs: the band grows until it spans the matrix
+        la, lb = 90 + 45 * q, 90 + 45 * q + int(rng.integers(0, 200))
+        a, b = synth.random_seq(rng, la), synth.random_seq(rng, lb)
+        if q % 2:
+            a = synth.decorate(rng, a)
+        extra_a.append(len(seqs)); seqs.append(synth.with_gap(a))
+        extra_b.append(len(seqs)); seqs.append(synth.with_gap(b))
+    ia = np.concatenate([ia, extra_a]).astype(np.int32); ib = np.concatenate([ib, extra_b]).astype(np.int32)
+    pool = pb.Pool(ctx, seqs)
+    monkeypatch.setenv("POY_LOWLAT", "0")
+    r0 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    monkeypatch.setenv("POY_LOWLAT", "2")
+    r1 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    assert np.array_equal(r0["cost"], r1["cost"]) and np.array_equal(r0["stats"], r1["stats"])
+    assert r0["stats"][:, 2].max() > 500             # the wide classes were exercised
+    for p in range(len(ia)):
+        for k in ("median", "medianwg", "res_a", "res_b"):
+            assert np.array_equal(r0[k][p], r1[k][p]), (k, p)
+    for p in list(range(0, 60, 4)) + list(range(60, len(ia))):
+        oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r1["cost"][p] and np.array_equal(om, r1["median"][p]) and np.array_equal(ra, r1["res_a"][p]), p
+    cm.close(); pool.close()
+
+
 def test_two_lane_split_does_not_change_results(ctx, port, monkeypatch):
     """large batches are cut in two halves that run on two stream sets / host threads; same results, also against
     the oracle, for the affine and the linear entry point"""
