@@ -201,6 +201,16 @@ def test_low_latency_shapes_do_not_change_results(ctx, port, monkeypatch, rname)
             a = synth.decorate(rng, a)
         extra_a.append(len(seqs)); seqs.append(synth.with_gap(a))
         extra_b.append(len(seqs)); seqs.append(synth.with_gap(b))
+    # the band of the third fill is 4 * delta + 5 diagonals wide (k = 1.5 delta + 2): length differences that land in
+    # the 1280 ... 4096 classes (16-warp shapes, mbarrier handshakes)
+    for q, delta in enumerate((300, 400, 500, 600, 800, 1000)):
+        la = int(1.6 * delta) + 200
+        a = synth.random_seq(rng, la)
+        b = np.concatenate([synth.evolve(rng, a, 0.1, 0.0), synth.random_seq(rng, delta)])
+        if q % 2:
+            b = synth.decorate(rng, b)
+        extra_a.append(len(seqs)); seqs.append(synth.with_gap(a))
+        extra_b.append(len(seqs)); seqs.append(synth.with_gap(b))
     ia = np.concatenate([ia, extra_a]).astype(np.int32); ib = np.concatenate([ib, extra_b]).astype(np.int32)
     pool = pb.Pool(ctx, seqs)
     monkeypatch.setenv("POY_LOWLAT", "0")
@@ -208,7 +218,7 @@ def test_low_latency_shapes_do_not_change_results(ctx, port, monkeypatch, rname)
     monkeypatch.setenv("POY_LOWLAT", "2")
     r1 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
     assert np.array_equal(r0["cost"], r1["cost"]) and np.array_equal(r0["stats"], r1["stats"])
-    assert r0["stats"][:, 2].max() > 500             # the wide classes were exercised
+    assert r0["stats"][:, 2].max() > 1200            # the wide classes were exercised
     for p in range(len(ia)):
         for k in ("median", "medianwg", "res_a", "res_b"):
             assert np.array_equal(r0[k][p], r1[k][p]), (k, p)
