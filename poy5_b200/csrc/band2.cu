@@ -157,26 +157,6 @@ __device__ __forceinline__ unsigned cell_gf(int &CB, int &EV, int &EH, int &K, u
 __device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void pair_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-// The 16-warp shapes would need 30 named-barrier ids (the hardware has 16), so their neighbour handshakes use
-// shared-memory mbarriers (count 1): the lane that wrote the mailbox arrives (release), every lane of the consuming
-// warp polls the phase parity (acquire).  The lockstep argument of DESIGN.md section 5 bounds the producer to one
-// phase ahead, so the parity test cannot alias.
-__device__ __forceinline__ void mb_init(unsigned long long *b) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
-__device__ __forceinline__ void mb_arrive(unsigned long long *b) {
-    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
-__device__ __forceinline__ void mb_wait(unsigned long long *b, unsigned &parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
-    unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-    parity ^= 1u;
-}
-
 // low bytes of H words -> one little-endian word (PRMT: three byte permutes for four cells)
 template <int H>
 __device__ __forceinline__ unsigned pack_dir(const unsigned (&b)[H]) {
@@ -215,7 +195,6 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     __shared__ int s_job;
     __shared__ int s_xe[NW][4];        // slot-0 state of lane 0 of every warp (read by the warp to its left)
     __shared__ int s_xo[NW][4];        // slot-(D-1) state of lane 31 of every warp (read by the warp to its right)
-    __shared__ unsigned long long s_mbE[NW > 8 ? NW : 1], s_mbO[NW > 8 ? NW : 1];   // 16-warp shapes: E(w) / O(w) as mbarriers
     static_assert(NW == 1 || WPB == NW, "cooperating warps fill the whole CTA");
     const int lane = threadIdx.x & 31, warp = (NW == 1) ? 0 : (threadIdx.x >> 5);
     const int tid = (NW == 1) ? lane : (int)threadIdx.x;   // thread index within the group that owns the pair
@@ -241,7 +220,6 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         } else {
             __syncthreads();
             if (tid == 0) s_job = atomicAdd(counter, 1);
-            if (NW > 8 && tid < NW) { mb_init(&s_mbE[tid]); mb_init(&s_mbO[tid]); }   // balanced per job: quiescent here
             __syncthreads();
             job = s_job;
         }
@@ -304,25 +282,18 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         // warp w-1 on barrier O(w-1) and for the even sub-step of warp w+1 on barrier E(w+1); the producer side only
         // arrives.  Program order makes every arrive / wait pair up and keeps the 12-byte mailboxes race free
         // (DESIGN.md section 5).  Warps wholly right of the band take no part.  16 warps would need 30 barrier
-        // ids, so those shapes do the same handshakes with shared-memory mbarriers (MB).
+        // ids, so that class keeps __syncthreads.
         constexpr bool P2P = (NW > 1 && NW <= 8);
-        constexpr bool MB = (NW > 8);
         const bool warp_in_band = (NW == 1) || (warp * 32 * D < B);
-        const bool has_left = (P2P || MB) && warp > 0;
-        const bool has_right = (P2P || MB) && warp + 1 < NW && (warp + 1) * 32 * D < B;
-        [[maybe_unused]] const int bar_E_mine = warp, bar_E_right = warp + 1;            // E(w) = id w, w = 1 .. NW-1
-        [[maybe_unused]] const int bar_O_mine = NW + warp, bar_O_left = NW + warp - 1;   // O(w) = id NW + w, w = 0 .. NW-2
-        [[maybe_unused]] unsigned par_O = 0u, par_E = 0u;                                // MB: phase parity of O(w-1) / E(w+1)
-        [[maybe_unused]] constexpr int MBN = NW > 8 ? NW : 1;
-        auto wait_O_left = [&] { if constexpr (MB) mb_wait(&s_mbO[(warp - 1) % MBN], par_O); else pair_wait(bar_O_left); };
-        auto wait_E_right = [&] { if constexpr (MB) mb_wait(&s_mbE[(warp + 1) % MBN], par_E); else pair_wait(bar_E_right); };
-        auto arrive_E = [&] { if constexpr (MB) { if (lane == 0) mb_arrive(&s_mbE[warp % MBN]); } else pair_arrive(bar_E_mine); };
-        auto arrive_O = [&] { if constexpr (MB) { if (lane == 31) mb_arrive(&s_mbO[warp % MBN]); } else pair_arrive(bar_O_mine); };
+        const bool has_left = P2P && warp > 0;
+        const bool has_right = P2P && warp + 1 < NW && (warp + 1) * 32 * D < B;
+        const int bar_E_mine = warp, bar_E_right = warp + 1;            // E(w) = id w, w = 1 .. NW-1
+        const int bar_O_mine = NW + warp, bar_O_left = NW + warp - 1;   // O(w) = id NW + w, w = 0 .. NW-2
         if (NW > 1) {
             if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
             if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
             __syncthreads();
-            if ((P2P || MB) && warp_in_band && has_right) arrive_O();   // row 0 stands in for "odd sub-step -1"
+            if (P2P && warp_in_band && has_right) pair_arrive(bar_O_mine);   // row 0 stands in for "odd sub-step -1"
         } else {
             __syncwarp();
         }
@@ -345,7 +316,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             }
             // ---- even diagonals ----
             {
-                if (has_left) wait_O_left();
+                if (has_left) pair_wait(bar_O_left);
                 int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
                 int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
                 unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
@@ -382,12 +353,13 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, pack_dir<H>(bw));
                 if (NW > 1) {
                     if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
-                    if (has_left) arrive_E();
+                    if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
+                    else __syncthreads();
                 }
             }
             // ---- odd diagonals ----
             {
-                if (has_right) wait_E_right();
+                if (has_right) pair_wait(bar_E_right);
                 int sCB = __shfl_down_sync(0xffffffffu, CB[0], 1);
                 int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
                 unsigned sG = __shfl_down_sync(0xffffffffu, G[0], 1);
@@ -423,7 +395,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, pack_dir<H>(bw));
                 if (NW > 1) {
                     if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
-                    if (has_right) arrive_O();
+                    if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
+                    else __syncthreads();
                 }
             }
             // ---- slide the windows one row down / one column right ----
@@ -434,10 +407,10 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             C[H] = col_entry<GF>(ncol, lane);
         };
 
-        if (warp_in_band) {
+        if (!P2P || warp_in_band) {
             for (; a <= a_end && a < a_main; a += 2) iteration(std::true_type{});
             for (; a <= a_end; a += 2) iteration(std::false_type{});
-            if (has_left) wait_O_left();   // drains the last arrive of the left neighbour
+            if (has_left) pair_wait(bar_O_left);   // drains the last arrive of the left neighbour
         }
 
         // result: the cell (lasti, lastj) is the latest cell of diagonal delta + k
@@ -510,7 +483,6 @@ cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, c
             case 512: L1(2, 8);
             case 768: L1(4, 6);
             case 1024: L1(4, 8);
-            case 1280: case 1536: case 2048: L1(4, 16);
         }
     switch (cls) {
         case 64: L1(2, 1);

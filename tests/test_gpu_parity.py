@@ -228,6 +228,40 @@ def test_low_latency_shapes_do_not_change_results(ctx, port, monkeypatch, rname)
     cm.close(); pool.close()
 
 
+def test_many_wide_pairs_per_cta(ctx, port, monkeypatch):
+    """more 4096-class pairs than resident CTAs: every CTA of the 16-warp shape processes several pairs in a row, with
+    and without probe fills; sampled against the oracle"""
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES["R1"])
+    pc = port.cm(full)
+    rng = np.random.default_rng(123)
+    seqs, ia, ib = [], [], []
+    for q in range(330):
+        delta = 600 + 40 * (q % 10)
+        a = synth.random_seq(rng, int(1.6 * delta) + 150)
+        b = np.concatenate([synth.evolve(rng, a, 0.1, 0.0), synth.random_seq(rng, delta)])
+        if q % 3 == 0:
+            a = synth.decorate(rng, a)
+        ia.append(len(seqs)); seqs.append(synth.with_gap(a))
+        ib.append(len(seqs)); seqs.append(synth.with_gap(b))
+    ia = np.asarray(ia, np.int32); ib = np.asarray(ib, np.int32)
+    pool = pb.Pool(ctx, seqs)
+    monkeypatch.setenv("POY_PROBE", "0")
+    r0 = Align.align_affine_3(ctx, cm, pool, ia, ib, want=("median",), stats=True)
+    monkeypatch.setenv("POY_PROBE", "2")
+    r1 = Align.align_affine_3(ctx, cm, pool, ia, ib, want=("median",), stats=True)
+    assert np.array_equal(r0["cost"], r1["cost"]) and np.array_equal(r0["stats"][:, :3], r1["stats"][:, :3])
+    band = (pool.lens[ib] - pool.lens[ia]) + 2 * r0["stats"][:, 2] + 1
+    assert ((band > 2048) & (band <= 4096)).sum() > 300
+    for p in range(len(ia)):
+        assert np.array_equal(r0["median"][p], r1["median"][p]), p
+    for p in range(0, len(ia), 47):
+        oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r1["cost"][p] and np.array_equal(om, r1["median"][p]), p
+    cm.close(); pool.close()
+
+
 def test_two_lane_split_does_not_change_results(ctx, port, monkeypatch):
     """large batches are cut in two halves that run on two stream sets / host threads; same results, also against
     the oracle, for the affine and the linear entry point"""
