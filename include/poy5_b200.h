@@ -179,6 +179,26 @@ POY_API poy_status poy_batch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int32_t 
 POY_API poy_status poy_batch_closest(poy_ctx *ctx, const poy_cm *cm, int32_t n, const uint8_t *rows_parent, const uint8_t *rows_mine,
                                      const int64_t *off, const int32_t *len, const int64_t *out_off, uint8_t *out, int32_t *out_len);
 
+/* ---- batch twins of SeqCS.DOS.distance / SeqCS.DOS.median (src/seqCS.ml:701-774, 985-1084) ----------------
+ * The per-locus policy the OCaml side applies around the alignment stubs, restated once above the batch entry
+ * points so that the candidate seam (src/ptree.ml:1356-1408) can hand over (a[p], b[p]) in ANY order:
+ *  poy_dos_distance  cost[p] = DOS.distance: missing_distance if either sequence is empty (Sequence.is_empty,
+ *                    src/seqCS.ml:705-709); else Sequence.Align.cost_2 under c2_ORIGINAL -- affine:
+ *                    algn_CAML_cost_affine_3; linear: shorter first, deltaw = max(|len a - len b|, 8) folded into
+ *                    deltawh = count_gaps + deltaw_calc (src/sequence.ml:868-925), algn_CAML_simple_2
+ *  poy_dos_median    DOS.median, affine model: an empty child yields the other child with cost 0
+ *                    (src/seqCS.ml:991-1039); else Sequence.Align.align_affine_3 under c2_FULL with the shorter
+ *                    sequence first and swaped = len a > len b (src/sequence.ml:633-649).  Pair p owns the slot
+ *                    [out_off[p], out_off[p] + len_a + len_b + 2) of `median`; its median sequence is
+ *                    RIGHT-justified there, out_len[p] bytes long; cost2[p] is the alignment cost.
+ *                    POY_ERR_MODEL for non-affine models (compose poy_batch_align_linear + poy_batch_ancestor_2).
+ * All array arguments are HOST pointers. */
+POY_API poy_status poy_dos_distance(poy_ctx *ctx, const poy_cm *c2_original, const poy_pool *pool, int32_t n,
+                                    const int32_t *a, const int32_t *b, int32_t missing_distance, int32_t *cost);
+POY_API poy_status poy_dos_median(poy_ctx *ctx, const poy_cm *c2_full, const poy_pool *pool, int32_t n, const int32_t *a,
+                                  const int32_t *b, const int64_t *out_off, int32_t *cost2, uint8_t *median,
+                                  int32_t *out_len);
+
 /* ---- INT32 / DPX issue-rate micro-benchmark (roofline denominator) ---------
  * Runs independent chains of one instruction class at full occupancy and
  * returns thread-level operations per second.  kind: 0 IADD3, 1 IMNMX (min),

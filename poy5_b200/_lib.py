@@ -73,6 +73,8 @@ def load():
     L.poy_batch_aligned_cost.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, vp]
     L.poy_batch_ancestor_2.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
     L.poy_batch_closest.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
+    L.poy_dos_distance.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp]
+    L.poy_dos_median.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.poy_microbench_int.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _LIB = L
     return L
@@ -83,4 +85,5 @@ EXPORTS = ["poy_ctx_create", "poy_ctx_destroy", "poy_last_error", "poy_status_st
            "poy_cm_upload", "poy_cm_free", "poy_pool_upload", "poy_pool_from_device", "poy_pool_free",
            "poy_batch_cost_affine", "poy_batch_cost_affine_dev", "poy_batch_align_affine",
            "poy_batch_align_affine_dev", "poy_batch_cost_linear", "poy_batch_align_linear", "poy_batch_median_2", "poy_batch_union",
-           "poy_batch_aligned_cost", "poy_batch_ancestor_2", "poy_batch_closest", "poy_microbench_int"]
+           "poy_batch_aligned_cost", "poy_batch_ancestor_2", "poy_batch_closest", "poy_dos_distance", "poy_dos_median",
+           "poy_microbench_int"]

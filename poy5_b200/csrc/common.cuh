@@ -53,6 +53,8 @@ struct poy_pool {
     uint8_t *d_gapfree;    // per sequence: 1 if no base at index >= 1 carries the gap bit
     int64_t *h_off;        // host copy of the offsets
     uint8_t *h_gapfree;    // host copy of d_gapfree (valid once the parameters have been computed)
+    uint8_t *h_empty;      // per sequence: every symbol is the gap code (Sequence.is_empty); filled on first use by dos.cu
+    int32_t *h_gapcnt;     // per sequence: symbols that carry the gap bit (Sequence.count_gaps); filled with h_empty
     int32_t nseq;
     int64_t nbytes;
     bool owns_data;

@@ -393,6 +393,8 @@ extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
     cached_free(ctx, p->d_h0, p->caps[3]); cached_free(ctx, p->d_g0, p->caps[4]); cached_free(ctx, p->d_gapfree, p->caps[5]);
     free(p->h_off);
     free(p->h_gapfree);
+    free(p->h_empty);
+    free(p->h_gapcnt);
     delete p;
 }
 

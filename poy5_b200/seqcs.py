@@ -3,6 +3,7 @@ character.  One call == the ``Array_ops.map`` over loci / the Parmap map over ca
 reference performs one alignment at a time (src/seqCS.ml:2232-2345, src/ptree.ml:1356-1408)."""
 import numpy as np
 from . import sequence
+from .api import _ptr
 from .sequence import Align
 
 
@@ -140,3 +141,28 @@ def to_single(ctx, h, pool, parent, mine):
     empty = _is_empty(pool)
     parent[empty[parent]] = mine[empty[parent]]
     return sequence.closest(ctx, h.c2_full, pool, parent, mine)
+
+
+# ---- the same policy inside the C ABI (poy5_b200/csrc/dos.cu) -------------------------------------------------------
+def dos_distance(ctx, h, pool, a, b, missing_distance=0):
+    """poy_dos_distance: DOS.distance with the empty-sequence / ordering / deltaw rules applied in C++.  int64[n]."""
+    a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+    cost = np.zeros(len(a), np.int32)
+    ctx.check(ctx.L.poy_dos_distance(ctx.h, h.c2_original.h, pool.h, len(a), _ptr(a), _ptr(b), int(missing_distance), _ptr(cost)))
+    return cost.astype(np.int64)
+
+
+def dos_median(ctx, h, pool, a, b):
+    """poy_dos_median (affine model): (list of median sequences, int64 cost2) with the empty-child / shorter-first /
+    swaped rules applied in C++."""
+    a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+    n = len(a)
+    caps = (pool.lens[a] + pool.lens[b] + 2).astype(np.int64)
+    out_off = np.zeros(n, np.int64)
+    if n > 1:
+        np.cumsum(caps[:-1], out=out_off[1:])
+    buf = np.zeros(max(1, int(caps.sum())), np.uint8)
+    cost = np.zeros(n, np.int32); out_len = np.zeros(n, np.int32)
+    ctx.check(ctx.L.poy_dos_median(ctx.h, h.c2_full.h, pool.h, n, _ptr(a), _ptr(b), _ptr(out_off), _ptr(cost), _ptr(buf), _ptr(out_len)))
+    ends = out_off + caps
+    return [buf[ends[p] - out_len[p]:ends[p]] for p in range(n)], cost.astype(np.int64)
