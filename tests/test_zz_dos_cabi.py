@@ -1,6 +1,6 @@
 """SeqCS.DOS policy inside the C ABI (poy_dos_distance / poy_dos_median, poy5_b200/csrc/dos.cu) against the Python
 mirror of the same policy and against the CPU checker: empty sequences, either argument order, affine and linear
-cost models.  (Sorted last on purpose: these entry points were added at the end of round 1.)"""
+cost models."""
 import numpy as np
 import pytest
 from oracle import cost_matrix_oracle as cmo
