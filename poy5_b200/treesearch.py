@@ -488,3 +488,126 @@ def apply_spr(tree, move):
     t.remove_edge(a, c)
     t.add_edge(a, u); t.add_edge(u, c); t.add_edge(u, v)
     return t
+
+
+# ------------------------------------------------------------------------------------------------------------
+# TBR round over several loci with incremental medians (BASELINE config #4)
+# ------------------------------------------------------------------------------------------------------------
+
+def _side_plan(tree, s, t):
+    """The component on s's side of the cut edge s-t with s suppressed (its neighbours x1, x2 joined), as BFS levels
+    from the cut: (x1, x2, levels of nodes, node -> (parent, sibling)); None when s is a leaf."""
+    nb = [w for w in tree.adj[s] if w != t]
+    if not nb:
+        return None
+    x1, x2 = nb
+    lv, frontier, par = [], [(x1, s), (x2, s)], {}
+    while frontier:
+        nxt = []
+        for a, pa in frontier:
+            ch = [w for w in tree.adj[a] if w != pa]
+            if ch:
+                nxt += [(ch[0], a), (ch[1], a)]
+                par[ch[0]] = (a, ch[1]); par[ch[1]] = (a, ch[0])
+        frontier = nxt
+        if nxt:
+            lv.append([c for c, _ in nxt])
+    return x1, x2, lv, par
+
+
+def tbr_round_multi(tree, loci, backend, dms=None, breaks=None, chunk=16):
+    """One TBR neighbourhood over several loci (src/ptree.ml:1356-1453 with reroots): for the break u-v BOTH
+    components are re-rooted, i.e. every edge of u's side (u suppressed) is paired with every edge of v's side
+    (v suppressed); the edge medians of either side are obtained incrementally exactly like in `spr_round`
+    (the merged edge x1-x2 reuses two medians of the unbroken tree), and all (edge, edge, locus) triples of a chunk
+    of breaks go into ONE cost-only batch.  The pair (merged edge, merged edge) is the unbroken tree and is left out.
+    Edges are named 'm' (merged), None (the lone leaf of a one-leaf side) or (parent, child).
+    Returns (best estimate, (break, edge on u's side, edge on v's side), candidates, alignments issued)."""
+    nl = len(loci)
+    dms = all_directions(tree, loci, backend) if dms is None else dms
+    breaks = tree.edges() if breaks is None else list(breaks)
+    best, ncand, naln = None, 0, 0
+    for c0 in range(0, len(breaks), chunk):
+        part = breaks[c0:c0 + chunk]
+        sides = [(s, t, _side_plan(tree, s, t)) for (u, v) in part for (s, t) in ((u, v), (v, u))]
+        ups = [None if pl is None else [{pl[0]: dm[(pl[1], s)], pl[1]: dm[(pl[0], s)]} for dm in dms] for s, t, pl in sides]
+        depth = max([len(pl[2]) for _, _, pl in sides if pl is not None], default=0)
+        for d in range(depth):
+            batch, own = [], []
+            for k, (s, t, pl) in enumerate(sides):
+                if pl is not None and d < len(pl[2]):
+                    for c in pl[2][d]:
+                        a, sib = pl[3][c]
+                        for l in range(nl):
+                            batch.append((ups[k][l][a][0], dms[l][(sib, a)][0])); own.append((k, l, c, a, sib))
+            naln += len(batch)
+            for (k, l, c, a, sib), (seq, c2) in zip(own, backend.median(batch)):
+                ups[k][l][c] = (seq, c2 + ups[k][l][a][1] + dms[l][(sib, a)][1])
+        # edge medians of every side: the merged edge, then the edges below it
+        batch, own = [], []
+        for k, (s, t, pl) in enumerate(sides):
+            if pl is None:
+                continue
+            x1, x2, lv, par = pl
+            for l in range(nl):
+                batch.append((dms[l][(x1, s)][0], dms[l][(x2, s)][0])); own.append((k, l, "m", dms[l][(x1, s)][1] + dms[l][(x2, s)][1]))
+            for lvl in lv:
+                for c in lvl:
+                    a = par[c][0]
+                    for l in range(nl):
+                        batch.append((ups[k][l][c][0], dms[l][(c, a)][0]))
+                        own.append((k, l, (a, c), ups[k][l][c][1] + dms[l][(c, a)][1]))
+        naln += len(batch)
+        ems = [dict() for _ in sides]
+        for (k, l, e, below), (seq, c2) in zip(own, backend.median(batch)):
+            ems[k].setdefault(e, [None] * nl)[l] = (seq, c2 + below)
+        for k, (s, t, pl) in enumerate(sides):
+            if pl is None:
+                ems[k][None] = [(ls[s], 0) for ls in loci]
+        cand, meta = [], []
+        for bi, brk in enumerate(part):
+            ea_all, eb_all = ems[2 * bi], ems[2 * bi + 1]
+            root_a = None if sides[2 * bi][2] is None else "m"
+            root_b = None if sides[2 * bi + 1][2] is None else "m"
+            for ea, ma in ea_all.items():
+                for eb, mb in eb_all.items():
+                    if ea == root_a and eb == root_b:
+                        continue
+                    base = 0
+                    for l in range(nl):
+                        cand.append((ma[l][0], mb[l][0])); base += ma[l][1] + mb[l][1]
+                    meta.append((brk, ea, eb, base))
+        naln += len(cand)
+        if meta:
+            d = np.asarray(backend.distance(cand), np.int64).reshape(len(meta), nl).sum(axis=1)
+            est = d + np.array([m[3] for m in meta], np.int64)
+            q = int(np.argmin(est))
+            if best is None or int(est[q]) < best[0]:
+                best = (int(est[q]), meta[q][:3])
+        ncand += len(meta)
+    if best is None:
+        return None, None, 0, naln
+    return best[0], best[1], ncand, naln
+
+
+def apply_tbr_multi(tree, move):
+    """cut u-v, suppress the internal ones of u and v, split the chosen edge of either side (re-using the ids u, v)
+    and join the two attachment points"""
+    (u, v), ea, eb = move
+    t = tree.copy()
+    t.remove_edge(u, v)
+
+    def attach(s, e):
+        if e is None:                      # one-leaf side: the leaf itself
+            return s
+        x1, x2 = t.adj[s]
+        t.remove_edge(s, x1); t.remove_edge(s, x2)
+        a, c = (x1, x2) if e == "m" else e
+        if e != "m":
+            t.add_edge(x1, x2)
+            t.remove_edge(a, c)
+        t.add_edge(a, s); t.add_edge(s, c)
+        return s
+    pa, pb = attach(u, ea), attach(v, eb)
+    t.add_edge(pa, pb)
+    return t

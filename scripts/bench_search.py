@@ -73,6 +73,7 @@ def main():
     ap.add_argument("--check", type=int, default=0, help="replay this many medians and candidates on the CPU checker")
     ap.add_argument("--full-median", action="store_true", help="read back the whole DOS.median record per node")
     ap.add_argument("--profile", action="store_true", help="cProfile of the SPR round to stderr")
+    ap.add_argument("--tbr", action="store_true", help="TBR neighbourhood (both sides re-rooted) instead of SPR; --prunings samples breaks")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -116,7 +117,15 @@ def main():
     if a.profile:
         import cProfile, pstats
         prof = cProfile.Profile(); prof.enable()
-    est, move, ncand, naln = treesearch.spr_round(tree, loci, rec, dms=dms, prunings=pr, chunk=a.chunk)
+    if a.tbr:
+        brk = tree.edges()
+        if a.prunings and a.prunings < len(brk):
+            brk = [brk[i] for i in np.linspace(0, len(brk) - 1, a.prunings).astype(int)]
+        pr = brk
+        est, move, ncand, naln = treesearch.tbr_round_multi(tree, loci, rec, dms=dms, breaks=brk, chunk=a.chunk)
+        move = (move[0], [str(move[1])], [str(move[2])]) if move else None
+    else:
+        est, move, ncand, naln = treesearch.spr_round(tree, loci, rec, dms=dms, prunings=pr, chunk=a.chunk)
     if a.profile:
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(28)
@@ -127,7 +136,7 @@ def main():
         nm, nd, cells = [int(x) for x in tot.tolist()]
     else:
         nm, nd, cells = gb.n_median - m0, gb.n_distance - d0, gb.cells_distance - c0
-    out = dict(workload="%d taxa x %d loci (%s bp), random tree, downpass + SPR round" % (a.taxa, a.loci, lens),
+    out = dict(workload="%d taxa x %d loci (%s bp), random tree, downpass + %s round" % (a.taxa, a.loci, lens, "TBR" if a.tbr else "SPR"),
                n_gpus=world, tree_cost=cost, downpass_s=t1 - t0, downpass_medians=(a.taxa - 1) * a.loci,
                all_directions_s=t2 - t1, spr_prunings=len(pr), spr_candidates=ncand, spr_alignments=naln,
                spr_s=t3 - t2, spr_candidates_per_s=ncand / (t3 - t2), spr_medians=nm, spr_distances=nd,

@@ -162,3 +162,51 @@ def test_sharded_spr_and_medians_gloo(port):
     single = run_spr(OracleBackend(port, full, orig), loci_taxa(9, 6, (40, 55)))
     for r in res:
         assert (r[1], r[2]) == (single[1:6], single[7])
+
+
+# ---- TBR round over several loci with incremental medians ----
+
+def run_tbr_multi(backend, loci, chunk=3):
+    tree = treesearch.wagner_build(loci[0], backend)
+    c0, _ = treesearch.downpass(tree, loci, backend)
+    est, move, ncand, naln = treesearch.tbr_round_multi(tree, loci, backend, chunk=chunk)
+    t2 = treesearch.apply_tbr_multi(tree, move)
+    c1, _ = treesearch.downpass(t2, loci, backend)
+    return tree.edges(), c0, est, move, ncand, naln, t2.edges(), c1
+
+
+def _is_binary_tree(edges, n):
+    deg = {}
+    for a, b in edges:
+        deg[a] = deg.get(a, 0) + 1; deg[b] = deg.get(b, 0) + 1
+    t = treesearch.Tree()
+    for a, b in edges:
+        t.add_edge(a, b)
+    return (len(edges) == 2 * n - 3 and all(deg[x] == (1 if x < n else 3) for x in deg)
+            and sorted(x for x in deg if x < n) == list(range(n)) and len(t.component(0, None)) == len(deg))
+
+
+def test_tbr_multi_oracle(port):
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    n = 7
+    loci = loci_taxa(13, n, (45, 60))
+    b = OracleBackend(port, full, orig)
+    r = run_tbr_multi(b, loci)
+    assert _is_binary_tree(r[0], n) and _is_binary_tree(r[6], n)
+    tree = treesearch.wagner_build(loci[0], b)
+    # the TBR neighbourhood contains the SPR neighbourhood (re-rooting one side only) and the unbroken tree is left out
+    _, _, nspr, _ = treesearch.spr_round(tree, loci, b)
+    assert r[4] > nspr / 2
+    # chunking does not change the neighbourhood or its best estimate
+    est2, move2, ncand2, _ = treesearch.tbr_round_multi(tree, loci, b, chunk=100)
+    assert (est2, move2, ncand2) == (r[2], r[3], r[4])
+    # every move of a small neighbourhood yields a valid tree
+    for brk in tree.edges()[:4]:
+        sides = [treesearch._side_plan(tree, s, t) for s, t in (brk, brk[::-1])]
+        names = [[None] if pl is None else ["m"] + [(pl[3][c][0], c) for lvl in pl[2] for c in lvl] for pl in sides]
+        for ea in names[0]:
+            for eb in names[1]:
+                assert _is_binary_tree(treesearch.apply_tbr_multi(tree, (brk, ea, eb)).edges(), n), (brk, ea, eb)
+    # re-inserting at (merged, merged) restores the tree
+    brk = [e for e in tree.edges() if e[0] >= n and e[1] >= n][0]
+    assert treesearch.apply_tbr_multi(tree, (brk, "m", "m")).edges() == tree.edges()
