@@ -123,9 +123,10 @@ def main():
             brk = [brk[i] for i in np.linspace(0, len(brk) - 1, a.prunings).astype(int)]
         pr = brk
         est, move, ncand, naln = treesearch.tbr_round_multi(tree, loci, rec, dms=dms, breaks=brk, chunk=a.chunk)
-        move = (move[0], [str(move[1])], [str(move[2])]) if move else None
+        move_out = [list(move[0]), str(move[1]), str(move[2])] if move else None
     else:
         est, move, ncand, naln = treesearch.spr_round(tree, loci, rec, dms=dms, prunings=pr, chunk=a.chunk)
+        move_out = [list(move[0]), list(move[1])] if move else None
     if a.profile:
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(28)
@@ -140,7 +141,7 @@ def main():
                n_gpus=world, tree_cost=cost, downpass_s=t1 - t0, downpass_medians=(a.taxa - 1) * a.loci,
                all_directions_s=t2 - t1, spr_prunings=len(pr), spr_candidates=ncand, spr_alignments=naln,
                spr_s=t3 - t2, spr_candidates_per_s=ncand / (t3 - t2), spr_medians=nm, spr_distances=nd,
-               spr_distance_gcups=cells / (t3 - t2) / 1e9, best_estimate=est, move=[list(move[0]), list(move[1])] if move else None,
+               spr_distance_gcups=cells / (t3 - t2) / 1e9, best_estimate=est, move=move_out,
                data="synthetic", scaling="strong")
     if a.check and rank == 0:
         from oracle import cost_matrix_oracle as cmo
