@@ -421,19 +421,8 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64):
         part = prunings[c0:c0 + chunk]
         ups, levels, joins = [], [], []       # per pruning: up[l][node]; nodes by depth; join edges (a, c)
         for (u, v) in part:
-            x1, x2 = [w for w in tree.adj[u] if w != v]
+            x1, x2, lv, par = _side_plan(tree, u, v)
             up = [{x1: dm[(x2, u)], x2: dm[(x1, u)]} for dm in dms]
-            lv, frontier, par = [], [(x1, u), (x2, u)], {}
-            while frontier:
-                nxt = []
-                for a, pa in frontier:
-                    ch = [w for w in tree.adj[a] if w != pa]
-                    if ch:
-                        nxt += [(ch[0], a), (ch[1], a)]
-                        par[ch[0]] = (a, ch[1]); par[ch[1]] = (a, ch[0])
-                frontier = nxt
-                if nxt:
-                    lv.append([c for c, _ in nxt])
             ups.append(up); levels.append((lv, par))
             joins.append([(par[c][0], c) for l_ in lv for c in l_])
         for d in range(max(len(lv) for lv, _ in levels)):
