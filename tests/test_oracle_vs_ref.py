@@ -96,3 +96,26 @@ def test_affine_helpers(reflib, port):
             assert np.array_equal(reflib.ancestor_2(rc, x, y), port.ancestor_2(pc, x, y))
             for wg in (0, 1):
                 assert np.array_equal(reflib.median_2(rc, x, y, wg), port.median_2(pc, x, y, wg))
+
+
+def test_arbitrary_alphabet_property(reflib, port):
+    """hypothesis: sequences over the WHOLE bitset alphabet 1..31 (any ambiguity, gap bits anywhere, runs of pure
+    gaps), any length 0..48 on either side, all regimes: both entry points of the restatement equal the reference"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    cms = {}
+    for rname, (s_, g_, go) in REGIMES.items():
+        full, _ = cmo.dna_matrices(s_, g_, go)
+        cms[rname] = (reflib.cm(full), port.cm(full))
+    code = st.integers(min_value=1, max_value=31)
+    seq = st.lists(code, min_size=0, max_size=48)
+
+    @settings(max_examples=400, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(seq, seq, st.sampled_from(sorted(cms)), st.integers(0, 1))
+    def check(a, b, rname, sw):
+        rc, pc = cms[rname]
+        a = np.array([16] + a, np.uint8); b = np.array([16] + b, np.uint8)
+        assert reflib.cost_affine(rc, a, b) == port.cost_affine(pc, a, b)
+        si, sj = (a, b) if len(a) <= len(b) else (b, a)
+        r1, r2 = reflib.align_affine(rc, si, sj, sw), port.align_affine(pc, si, sj, sw)
+        assert r1[0] == r2[0] and all(np.array_equal(x, y) for x, y in zip(r1[1:], r2[1:]))
+    check()
