@@ -55,6 +55,16 @@ class GpuBackend:
         pool.close()
         return [(np.array(r["sequence"][p], np.uint8), int(r["cost2"][p])) for p in range(len(pairs))]
 
+    def single(self, pairs):
+        """[(parent, mine)] -> [(single-assignment sequence, cost)] (seqcs.to_single)"""
+        from .seqcs import to_single
+        if not pairs:
+            return []
+        pool, ia, ib = self._pool(pairs)
+        seqs, cost = to_single(self.ctx, self.h, pool, ia, ib)
+        pool.close()
+        return [(np.array(s, np.uint8), int(c)) for s, c in zip(seqs, cost)]
+
     def distance(self, pairs):
         from .seqcs import DOS
         if not pairs:
@@ -333,6 +343,9 @@ class ShardedBackend:
                 out[int(i)] = (g[q, 16:16 + int(ln)].copy(), int(c2))
         return out
 
+    def single(self, pairs):
+        return self.b.single(pairs)       # O(n) pairs per pass: replicated
+
     def distance(self, pairs):
         import torch
         import torch.distributed as dist
@@ -600,3 +613,40 @@ def apply_tbr_multi(tree, move):
     pa, pb = attach(u, ea), attach(v, eb)
     t.add_edge(pa, pb)
     return t
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Single assignment: the pre-order pass that follows a downpass
+# ------------------------------------------------------------------------------------------------------------
+
+def single_assignment(tree, loci, backend, root=None):
+    """Pre-order single-assignment pass: the root median is resolved against itself, every other node's towards-root
+    median against its parent's single assignment (SeqCS.DOS.to_single = Sequence.Align.closest parent mine,
+    src/seqCS.ml:950-982, src/sequence.ml:1180-1237), level by level from the root, all loci in the same batches.
+    Needs a backend with ``single(pairs of (parent, mine)) -> [(sequence, cost), ...]``.
+    Returns (downpass cost, single-assignment cost = sum of the re-costed parent/child distances, per-locus dict
+    node -> single sequence; the root median is stored under the key 'root')."""
+    root = tree.edges()[0] if root is None else root
+    cost, dms = downpass(tree, loci, backend, root)
+    a, b = root
+    res = backend.median([(dm[(a, b)][0], dm[(b, a)][0]) for dm in dms])
+    singles = [dict() for _ in loci]
+    total = 0
+    for l, ((seq, _), (s1, c1)) in enumerate(zip(res, backend.single([(seq, seq) for seq, _ in res]))):
+        singles[l]["root"] = s1; total += c1
+    up = {a: b, b: a}                       # neighbour towards the root edge
+    above = {a: "root", b: "root"}          # whose single assignment a node is resolved against
+    level = [a, b]
+    while level:
+        out = backend.single([(singles[l][above[x]], dms[l][(x, up[x])][0]) for l in range(len(loci)) for x in level])
+        for l in range(len(loci)):
+            for q, x in enumerate(level):
+                s1, c1 = out[l * len(level) + q]
+                singles[l][x] = s1; total += c1
+        nxt = []
+        for x in level:
+            for y in tree.adj[x]:
+                if y != up[x]:
+                    up[y] = x; above[y] = x; nxt.append(y)
+        level = nxt
+    return cost, int(total), singles

@@ -49,3 +49,17 @@ class OracleBackend:
             else:
                 out.append(int(self._lin(self.po, a, b, max(abs(len(a) - len(b)), 8))[0]))
         return out
+
+    def single(self, pairs):
+        """DOS.to_single (src/seqCS.ml:950-982): empty `mine` stays, an empty parent is replaced by `mine`, otherwise
+        Sequence.Align.closest parent mine under c2_full"""
+        from oracle import cost_matrix_oracle as cmo
+        from tests.helpers import oracle_closest
+        out = []
+        for parent, mine in pairs:
+            if self._empty(parent):
+                parent = mine
+            s, c = oracle_closest(self.P, cmo, self.pf, self.full, parent, mine,
+                                  (lambda x, y: self._lin(self.pf, x, y, None)) if not self.affine else None)
+            out.append((s, int(c)))
+        return out

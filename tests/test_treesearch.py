@@ -210,3 +210,37 @@ def test_tbr_multi_oracle(port):
     # re-inserting at (merged, merged) restores the tree
     brk = [e for e in tree.edges() if e[0] >= n and e[1] >= n][0]
     assert treesearch.apply_tbr_multi(tree, (brk, "m", "m")).edges() == tree.edges()
+
+
+# ---- single assignment (pre-order pass after the downpass) ----
+
+def test_single_assignment_oracle(port):
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    n = 8
+    loci = loci_taxa(31, n, (50, 64))
+    b = OracleBackend(port, full, orig)
+    tree = treesearch.wagner_build(loci[0], b)
+    cost, single_cost, singles = treesearch.single_assignment(tree, loci, b)
+    assert cost == treesearch.downpass(tree, loci, b)[0] and single_cost > 0
+    pf = port.cm(full)
+    root = tree.edges()[0]
+    for l, ls in enumerate(loci):
+        assert set(singles[l]) == set(tree.adj) | {"root"}
+        for x, s in singles[l].items():
+            assert s[0] == 16 and all(bin(int(v)).count("1") == 1 for v in s[1:]), (l, x)     # one base per position
+        for t in range(n):
+            assert np.array_equal(singles[l][t], ls[t])            # an unambiguous leaf is its own single assignment
+    # the single-assignment cost is the sum of the parent/child distances of the assigned sequences
+    tot = 0
+    for l in range(len(loci)):
+        parent = {root[0]: "root", root[1]: "root"}
+        order = [root[0], root[1]]
+        for x in order:
+            up = (root[1] if x == root[0] else root[0]) if parent[x] == "root" else parent[x]
+            for y in tree.adj[x]:
+                if y != up:
+                    parent[y] = x; order.append(y)
+        for x in order:
+            ps, xs = singles[l][parent[x]], singles[l][x]
+            tot += 0 if np.array_equal(ps, xs) else int(port.cost_affine(pf, ps, xs))
+    assert tot == single_cost
