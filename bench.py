@@ -33,7 +33,7 @@ METRIC = "GCUPS (full-matrix-equivalent cell updates/s) of batched affine DO ali
 LENGTHS = (500, 2000, 10000)
 REGIME = (1, 1, 3)          # R1: substitution 1, indel 1, gap opening 3
 SEED = 0x504F5935
-OPS_PER_CELL = {"gapfree": 9, "general": 16}   # scalar int32 add/min per cost-only cell
+OPS_PER_CELL = {"gapfree": 9, "general": 16, "band": 30}   # scalar int32 ops per cost-only cell / per band cell with directions
 
 
 def parse():
@@ -47,6 +47,11 @@ def parse():
     ap.add_argument("--chunk-bases", type=int, default=600_000_000, help="max pool bytes per batch call")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle replay of the timed pairs")
+    ap.add_argument("--no-swap", action="store_true", help="skip the strong-scaled swap-evaluation sub-record")
+    ap.add_argument("--swap-prunings", type=int, default=192, help="SPR prunings of the swap-evaluation sample (whole job)")
+    ap.add_argument("--swap-chunk", type=int, default=24, help="prunings per candidate batch")
+    ap.add_argument("--swap-check", type=int, default=24, help="medians / distances replayed on the CPU checker")
     return ap.parse_args()
 
 
@@ -280,6 +285,7 @@ def main():
     best = torch.zeros(1, dtype=torch.int64, device=dev)
 
     seg_events = {}
+    seg_band_cells = {}
 
     def local_min(costs):
         # candidate min-reduction inside the rank: (cost << 32 | index) packed int64, min over the batch
@@ -296,9 +302,12 @@ def main():
             sequence.cost_2_dev(ctx, cm, pool, w["n"], w["d_ia"].data_ptr(), w["d_ib"].data_ptr(), w["d_cost0"].data_ptr())
             if record:
                 e1.record(stream)
+            bc0 = ctx.stats()["band_cells"] if record else 0
             sequence.align_affine_3_dev(ctx, cm, pool, w["si"], w["sj"], w["d_sw"].data_ptr(), w["d_out_off"].data_ptr(),
                                         w["d_cost1"].data_ptr(), d_outs[0].data_ptr(), d_outs[1].data_ptr(),
                                         d_outs[2].data_ptr(), d_outs[3].data_ptr(), w["d_len"].data_ptr())
+            if record:
+                seg_band_cells[wi] = ctx.stats()["band_cells"] - bc0
             best.copy_(torch.minimum(best, torch.minimum(local_min(w["d_cost0"]), local_min(w["d_cost1"]))))
             if record:
                 e2.record(stream)
@@ -347,6 +356,7 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launches
+    stats0 = ctx.stats()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for k in range(args.steps):
@@ -354,6 +364,9 @@ def main():
     ev1.record(stream)
     barrier()
     launches = ctx.launches - launches0
+    stats1 = ctx.stats()
+    band_cells_step = (stats1["band_cells"] - stats0["band_cells"]) / max(1, args.steps)
+    fills_step = {k: (stats1[k] - stats0[k]) / max(1, args.steps) for k in ("probe_fills", "full_fills", "repeated", "rounds")}
     ms = ev0.elapsed_time(ev1) / max(1, args.steps)
     clocks = sampler.stop() if sampler else {}
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -364,11 +377,15 @@ def main():
     # per-segment breakdown (last timed step)
     breakdown = []
     kernel_ms = {}
+    band_ms = {}
     for wi, w in enumerate(work):
         if wi in seg_events:
             e0, e1, e2 = seg_events[wi]
             t_off, t_on = e0.elapsed_time(e1), e1.elapsed_time(e2)
+            band_ms.setdefault(w["L"], [0.0, 0])
+            band_ms[w["L"]][0] += t_on; band_ms[w["L"]][1] += seg_band_cells.get(wi, 0)
             breakdown.append(dict(L=w["L"], pairs=w["n"], band_off_ms=round(t_off, 3), band_on_ms=round(t_on, 3),
+                                  band_on_cells_computed=int(seg_band_cells.get(wi, 0)),
                                   band_off_gcups=round(w["cells"] / t_off / 1e6, 2), band_on_gcups=round(w["cells"] / t_on / 1e6, 2),
                                   band_off_aln_per_s=round(w["n"] / t_off * 1e3, 1), band_on_aln_per_s=round(w["n"] / t_on * 1e3, 1)))
             kernel_ms.setdefault(w["L"], [0.0, 0])
@@ -391,8 +408,116 @@ def main():
         e2e = dict(value=world * total_cells / te / 1e9, unit="GCUPS", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                    ms_per_step=1e3 * te, alignments_per_s=world * total_aln / te)
 
+    # ---- interior-node-like segment (not part of `value`): every pair carries ambiguity / gap-bit symbols, i.e. takes
+    # the 4-state kernels that a tree pass runs --------------------------------------------------
+    interior = None
+    if not args.no_swap:
+        Li, ni = 2000, min(20000, args.pairs)
+        data, off = synth.pair_pool(SEED + 77, rank * ni, ni, Li, subst=0.15, indel=0.01, decorated=1.0, nthreads=min(threads, 16))
+        lens = np.diff(off)
+        ia = np.arange(0, 2 * ni, 2, dtype=np.int32); ib = ia + 1
+        la, lb = lens[ia], lens[ib]
+        sw = (la > lb).astype(np.uint8)
+        si = np.where(sw == 1, ib, ia).astype(np.int32); sj = np.where(sw == 1, ia, ib).astype(np.int32)
+        caps = (la + lb + 2).astype(np.int64)
+        oo = np.zeros(ni, np.int64); np.cumsum(caps[:-1], out=oo[1:])
+        cells_i = int(((la - 1) * (lb - 1)).sum())
+        dd, do_ = torch.from_numpy(data).to(dev), torch.from_numpy(off).to(dev)
+        dia, dib, dsw, doo = (torch.from_numpy(x).to(dev) for x in (ia, ib, sw, oo))
+        dc0 = torch.empty(ni, dtype=torch.int32, device=dev); dc1 = torch.empty(ni, dtype=torch.int32, device=dev)
+        dl = torch.empty(4 * ni, dtype=torch.int32, device=dev)
+        outs_i = d_outs if int(caps.sum()) + 256 <= d_outs[0].numel() else [torch.empty(int(caps.sum()) + 256, dtype=torch.uint8, device=dev) for _ in range(4)]
+        tms_i = []
+        for rep in range(2):          # first pass warms up
+            pool = sequence.DevicePool(ctx, dd.data_ptr(), do_.data_ptr(), off)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            sequence.cost_2_dev(ctx, cm, pool, ni, dia.data_ptr(), dib.data_ptr(), dc0.data_ptr())
+            e1.record(stream)
+            bc0 = ctx.stats()["band_cells"]
+            sequence.align_affine_3_dev(ctx, cm, pool, si, sj, dsw.data_ptr(), doo.data_ptr(), dc1.data_ptr(), outs_i[0].data_ptr(),
+                                        outs_i[1].data_ptr(), outs_i[2].data_ptr(), outs_i[3].data_ptr(), dl.data_ptr())
+            e2.record(stream)
+            torch.cuda.synchronize()
+            bci = ctx.stats()["band_cells"] - bc0
+            tms_i = [e0.elapsed_time(e1), e1.elapsed_time(e2)]
+            pool.close()
+        interior = dict(L=Li, pairs=ni, decorated=1.0, subst=0.15, band_off_ms=round(tms_i[0], 3), band_on_ms=round(tms_i[1], 3),
+                        band_off_gcups=round(cells_i / tms_i[0] / 1e6, 2), band_on_gcups=round(cells_i / tms_i[1] / 1e6, 2),
+                        band_on_cells_computed=int(bci), band_on_gcells_computed_per_s=round(bci / tms_i[1] / 1e6, 2),
+                        note="100% interior-node-like pairs (4-state kernels); not part of `value`")
+        del dd, do_, dia, dib, dsw, doo, dc0, dc1, dl, outs_i
+
+    # ---- parity of the timed results: a sample of the timed pairs against the CPU checker (outside the timed region) -----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import cost_matrix_oracle as cmo
+        full, _ = cmo.dna_matrices(*REGIME)
+        chk, kind = None, "port"
+        try:
+            from oracle import refbind
+            if refbind.available(True):
+                chk = refbind.RefLib(True); kind = "reference"
+        except Exception:
+            chk = None
+        if chk is None:
+            from oracle.port import Port
+            chk = Port()
+        pc = chk.cm(full)
+        checked = mism = 0
+        per_len = {500: 24, 2000: 10, 10000: 3}
+        seen = set()
+        for w in work:
+            if w["L"] in seen:
+                continue
+            seen.add(w["L"])
+            k = min(w["n"], per_len.get(w["L"], 4))
+            idx = np.linspace(0, w["n"] - 1, k).astype(int)
+            c0 = w["d_cost0"].cpu().numpy(); c1 = w["d_cost1"].cpu().numpy()      # results of the LAST timed step
+            # the four sequences of the sampled pairs: re-run of exactly these pairs through the host C ABI
+            sub = pb.Pool(ctx, [w["data"][w["off"][s]:w["off"][s + 1]] for q in idx for s in (2 * q, 2 * q + 1)])
+            r = sequence.Align.align_affine_3(ctx, cm, sub, np.arange(0, 2 * k, 2, dtype=np.int32), np.arange(1, 2 * k, 2, dtype=np.int32))
+            for j, q in enumerate(idx):
+                a = w["data"][w["off"][2 * q]:w["off"][2 * q + 1]]; b = w["data"][w["off"][2 * q + 1]:w["off"][2 * q + 2]]
+                swp = int(len(a) > len(b))
+                xi, xj = (b, a) if swp else (a, b)
+                oc, om, ow, ori, orj = chk.align_affine(pc, xi, xj, swp)
+                ra, rb = (orj, ori) if swp else (ori, orj)
+                ok = (int(c0[q]) == int(chk.cost_affine(pc, a, b)) and int(c1[q]) == int(oc) and int(r["cost"][j]) == int(oc)
+                      and np.array_equal(om, r["median"][j]) and np.array_equal(ow, r["medianwg"][j])
+                      and np.array_equal(ra, r["res_a"][j]) and np.array_equal(rb, r["res_b"][j]))
+                checked += 1; mism += int(not ok)
+            sub.close()
+        parity = dict(checked=checked, mismatches=mism, against=kind,
+                      what="sampled pairs of every length: cost-only cost and banded cost of the last timed step, plus median / "
+                           "median_wg / both aligned rows of a re-run of the same pairs, vs the CPU checker",
+                      unpinned="the Cost_matrix table fill (OCaml, cannot run here) and the tree-level enumerator are restatements "
+                               "pinned only by self-consistency tests")
+
+    # ---- swap evaluation: one SPR neighbourhood, strong-scaled over the ranks (north star) ------------------------------
+    swap = None
+    if not args.no_swap:
+        from poy5_b200 import swap_eval
+        for w in work:
+            for k in [k for k in w if k.startswith("d_")]:
+                del w[k]
+        del d_outs
+        for ln in lanes:
+            ln["h_outs"] = None
+        torch.cuda.empty_cache()
+        try:
+            swap, sample = swap_eval.run(ctx, rank=rank, world=world, device=dev, prunings=args.swap_prunings, chunk=args.swap_chunk,
+                                         check=args.swap_check, regime=REGIME)
+            if swap is not None and sample is not None:      # rank 0: CPU-checker replay of the recorded sample (untimed)
+                from tests.oracle_backend import replay_sample
+                t5 = time.perf_counter()
+                swap["parity"] = replay_sample(sample[0], sample[1], REGIME)
+                swap["parity"]["replay_s"] = time.perf_counter() - t5
+        except Exception as e:          # reported, never hidden
+            swap = dict(error="%s: %s" % (type(e).__name__, e))
+
     if rank == 0:
-        # dominant kernel: the cost-only wavefront (k_cost_affine) on the longest length
+        # dominant kernels on the longest length: the cost-only wavefront (k_cost_affine) and the banded fill (k_band2)
         Ltop = max(kernel_ms) if kernel_ms else lengths[-1]
         k_ms, k_cells = kernel_ms.get(Ltop, (ms, total_cells))
         n_top = max(1, sum(1 for w in work if w["L"] == Ltop))   # launches of the dominant kernel per step
@@ -403,22 +528,33 @@ def main():
         except Exception:
             pass
         achieved = k_cells * OPS_PER_CELL["gapfree"] / (k_ms * 1e-3) / 1e12
-        traffic = None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same shape, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_cost_affine"]
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same shape, from this round's committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["k_cost_affine"]
             top = [w for w in work if w["L"] == Ltop]
             if tj["length"] == Ltop and all(w["n"] == tj["pairs_per_launch"] for w in top):
-                traffic = tj["dram_bytes_per_launch"]
+                traffic = tj["dram_bytes_per_launch"]; traffic_src = "profiles/r02_traffic.json (ncu --set full of this kernel at this shape)"
         except Exception:
             pass
+        b_ms, b_cells = band_ms.get(Ltop, (0.0, 0))
+        band_roof = None
+        if b_ms > 0 and b_cells > 0:
+            b_ach = b_cells * OPS_PER_CELL["band"] / (b_ms * 1e-3) / 1e12
+            band_roof = dict(bound="int32", kernel="k_band2 family (fills of the threshold-doubling schedule) + k_traceback",
+                             achieved=b_ach, peak=peak_ops / 1e12, unit="Tops/s", frac=b_ach / (peak_ops / 1e12),
+                             cells_computed=int(b_cells), gcells_computed_per_s=b_cells / (b_ms * 1e-3) / 1e9,
+                             note="band cells computed over ALL fills of the band-on calls on the L=%d segments (probe fills and "
+                                  "fills with direction bytes alike) x %d algorithmic ops per traceback cell (SURVEY 8d) / the "
+                                  "band-on time of those segments (CUDA events; includes stop rule, traceback and the host-driven "
+                                  "round trips), vs the same live IADD3-class issue rate" % (Ltop, OPS_PER_CELL["band"]))
         roofline = dict(bound="int32", kernel="k_cost_affine", achieved=achieved, peak=peak_ops / 1e12, unit="Tops/s",
-                        frac=achieved / (peak_ops / 1e12), traffic=traffic,
+                        frac=achieved / (peak_ops / 1e12), traffic=traffic, traffic_source=traffic_src,
                         note="INT32 issue roofline: algorithmic scalar add/min per cell (%d, gap-free cost-only cell) x cells / "
                              "launch time, vs the IADD3-class issue rate measured live by poy_microbench_int "
                              "(DPX VIADDMNMX measured %.2f Tops/s). Launch time from CUDA events around the cost-only "
                              "calls on the L=%d segment (about 10%% of its pairs carry gap bits and run the 4-state path, 16 ops/cell, but are counted at 9)."
                              % (OPS_PER_CELL["gapfree"], dpx_ops / 1e12, Ltop),
-                        sm_clock_mhz_microbench=peak_clock,
+                        sm_clock_mhz_microbench=peak_clock, band=band_roof,
                         hbm=dict(algorithmic_bytes_per_launch=int(k_bytes), achieved_gbs=k_bytes * n_top / (k_ms * 1e-3) / 1e9,
                                  peak_gbs=hbm_peak, frac=k_bytes * n_top / (k_ms * 1e-3) / 1e9 / hbm_peak,
                                  note="sequence bytes in + 4 B cost out per pair (SURVEY 8d): this path is integer-issue bound, not HBM bound"))
@@ -434,8 +570,13 @@ def main():
                     warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="int32", data="synthetic",
                     config=make_config(args.pairs, lengths, world, sum(w["data"].nbytes for w in work)),
-                    alignments_per_s=world * total_aln / (ms * 1e-3), breakdown=breakdown, clocks=clocks, e2e=e2e,
-                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu)
+                    alignments_per_s=world * total_aln / (ms * 1e-3), breakdown=breakdown,
+                    cells_computed=dict(band_on_per_step_per_gpu=int(band_cells_step), band_off_per_step_per_gpu=int(total_cells // 2),
+                                        fills_per_step={k: int(v) for k, v in fills_step.items()},
+                                        note="band on: cells inside the Ukkonen bands summed over every fill of the threshold-doubling "
+                                             "schedule (poy_ctx_stats); band off: the full matrices"),
+                    breakdown_interior=interior, clocks=clocks, e2e=e2e,
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, parity=parity, swap_eval=swap)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

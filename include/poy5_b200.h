@@ -64,6 +64,11 @@ POY_API poy_status poy_ctx_set_arena_limit(poy_ctx *ctx, uint64_t bytes);
 POY_API poy_status poy_ctx_synchronize(poy_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py: gpu_launches) */
 POY_API uint64_t poy_ctx_launch_count(const poy_ctx *ctx);
+/* cumulative counters of this context (SURVEY.md 8d "additionally report cells_computed"): out[0] kernel launches,
+ * out[1] band cells computed by the banded entry points (summed over every fill of the threshold-doubling schedule),
+ * out[2] probe fills (no direction bytes), out[3] fills with direction bytes, out[4] thresholds repeated after a probe,
+ * out[5] schedule rounds, out[6] pairs aligned by the banded entry points, out[7] reserved */
+POY_API poy_status poy_ctx_stats(const poy_ctx *ctx, int64_t out[8]);
 
 /* ---- cost model: replaces the cm_CAML_* setters + cm.c tables --------------
  * Host-side image of `struct cm` for the 5-letter bitset alphabet
@@ -77,6 +82,8 @@ typedef struct {
     int32_t tail[32];        /* c->tail_cost */
     int32_t gap_open;        /* c->gap_open */
     int32_t cost_model_type; /* 0 linear, 1 affine, 2 no alignment (c->cost_model_type) */
+    int32_t is_identity;     /* c->is_identity: the input matrix has a zero diagonal (src/cost_matrix.ml:1097-1104, 1169-1170) */
+    int32_t is_metric;       /* c->is_metric: positive, symmetric and zero diagonal (src/cost_matrix.ml:1117-1139, 1171-1177) */
 } poy_cm_host;
 
 /* Cost_matrix.Two_D construction restated in C++ (src/cost_matrix.ml:721-804,
@@ -161,7 +168,9 @@ POY_API poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, const 
  *                         starts at out_off[p] (capacity len[p] + 1), left-justified, out_len[p] bytes
  *  poy_batch_union        algn_CAML_union (src/algn.c:3657-3678): out has the layout of the inputs
  *  poy_batch_aligned_cost algn_CAML_verify_2 (use_worst = 0) / algn_CAML_worst_2 (use_worst = 1)
- *                         (src/algn.c:3003-3130) = Sequence.Align.max_cost_2 / verify
+ *                         (src/algn.c:3003-3130) = Sequence.Align.max_cost_2 / verify;
+ *                         use_worst = 2 / 3: Sequence.Align.recost ~first_gap:true / false (src/sequence.ml:1244-1307,
+ *                         OCaml in the reference), the cost of two aligned rows with one gap opening per gap block
  *  poy_batch_ancestor_2   algn_CAML_ancestor_2 (src/algn.c:3603-3626,3742): capacity len[p] + 1
  *  poy_batch_closest      the column map of Sequence.Align.closest (src/sequence.ml:1180-1237): column i becomes
  *                         Cost_matrix.Two_D.get_closest cm parent.(i) mine.(i) (src/cost_matrix.ml:1387-1428), then
@@ -186,18 +195,54 @@ POY_API poy_status poy_batch_closest(poy_ctx *ctx, const poy_cm *cm, int32_t n, 
  *                    src/seqCS.ml:705-709); else Sequence.Align.cost_2 under c2_ORIGINAL -- affine:
  *                    algn_CAML_cost_affine_3; linear: shorter first, deltaw = max(|len a - len b|, 8) folded into
  *                    deltawh = count_gaps + deltaw_calc (src/sequence.ml:868-925), algn_CAML_simple_2
- *  poy_dos_median    DOS.median, affine model: an empty child yields the other child with cost 0
+ *  poy_dos_median    DOS.median: an empty child yields the other child with cost 0 (identity matrices; see poy_dos_median2)
  *                    (src/seqCS.ml:991-1039); else Sequence.Align.align_affine_3 under c2_FULL with the shorter
  *                    sequence first and swaped = len a > len b (src/sequence.ml:633-649).  Pair p owns the slot
  *                    [out_off[p], out_off[p] + len_a + len_b + 2) of `median`; its median sequence is
  *                    RIGHT-justified there, out_len[p] bytes long; cost2[p] is the alignment cost.
- *                    POY_ERR_MODEL for non-affine models (compose poy_batch_align_linear + poy_batch_ancestor_2).
+ *                    Linear / no-alignment models: Sequence.Align.align_2 + ancestor_2 (src/seqCS.ml:1058-1071).
  * All array arguments are HOST pointers. */
 POY_API poy_status poy_dos_distance(poy_ctx *ctx, const poy_cm *c2_original, const poy_pool *pool, int32_t n,
                                     const int32_t *a, const int32_t *b, int32_t missing_distance, int32_t *cost);
 POY_API poy_status poy_dos_median(poy_ctx *ctx, const poy_cm *c2_full, const poy_pool *pool, int32_t n, const int32_t *a,
                                   const int32_t *b, const int64_t *out_off, int32_t *cost2, uint8_t *median,
                                   int32_t *out_len);
+
+/* same, with the identity rule of DOS.median made explicit: when c2_original (may be NULL: c2_full's flag is used) has a
+ * non-zero diagonal, a median with one empty child costs Sequence.Align.recost x x c2_original instead of 0
+ * (src/seqCS.ml:992-996, 1027-1031).  Both entry points accept affine AND linear / no-alignment models (linear:
+ * Sequence.Align.align_2 + ancestor_2, src/seqCS.ml:1058-1071). */
+POY_API poy_status poy_dos_median2(poy_ctx *ctx, const poy_cm *c2_full, const poy_cm *c2_original, const poy_pool *pool, int32_t n,
+                                   const int32_t *a, const int32_t *b, const int64_t *out_off, int32_t *cost2, uint8_t *median,
+                                   int32_t *out_len);
+
+/* ---- device-resident node store -------------------------------------------------------------------
+ * The heap of `Sequence.s` values of a tree pass (src/seq.h:52-61; SeqCS.DOS.median allocates a fresh one per call,
+ * src/seqCS.ml:985-1084) kept in HBM: sequences are immutable and named by an int32 id in order of creation.
+ *  poy_store_append    copies host sequences in (observed leaves); *first_id = id of the first one
+ *  poy_store_median    DOS.median of (a[p], b[p]) for n pairs of ids; the medians are appended to the store WITHOUT
+ *                      leaving the device -- only out_id / out_len / cost2 (12 bytes per pair) come back.  A pair with an
+ *                      empty child returns the other child's id (no copy).
+ *  poy_store_distance  DOS.distance over ids (cost-only, c2_original)
+ *  poy_store_truncate  stack discipline: forget every id >= nseq (temporaries of a finished batch of candidates)
+ *  poy_store_read      copies sequences back to the host (reports, tests)
+ *  poy_store_pool      the store as a poy_pool, for every poy_batch_* entry point */
+typedef struct poy_store poy_store;
+POY_API poy_status poy_store_create(poy_ctx *ctx, int64_t cap_bytes, int32_t cap_seqs, poy_store **out);
+POY_API void poy_store_free(poy_ctx *ctx, poy_store *st);
+POY_API const poy_pool *poy_store_pool(const poy_store *st);
+POY_API int32_t poy_store_count(const poy_store *st);
+POY_API int64_t poy_store_bytes(const poy_store *st);
+POY_API poy_status poy_store_append(poy_ctx *ctx, poy_store *st, const uint8_t *data, const int64_t *offsets, int32_t nseq,
+                                    int32_t *first_id);
+POY_API poy_status poy_store_truncate(poy_ctx *ctx, poy_store *st, int32_t nseq);
+POY_API poy_status poy_store_lengths(const poy_store *st, int32_t n, const int32_t *ids, int32_t *len);
+POY_API poy_status poy_store_read(poy_ctx *ctx, const poy_store *st, int32_t n, const int32_t *ids, const int64_t *out_off,
+                                  uint8_t *out);
+POY_API poy_status poy_store_median(poy_ctx *ctx, poy_store *st, const poy_cm *c2_full, const poy_cm *c2_original, int32_t n,
+                                    const int32_t *a, const int32_t *b, int32_t *out_id, int32_t *out_len, int32_t *cost2);
+POY_API poy_status poy_store_distance(poy_ctx *ctx, poy_store *st, const poy_cm *c2_original, int32_t n, const int32_t *a,
+                                      const int32_t *b, int32_t missing_distance, int32_t *cost);
 
 /* ---- INT32 / DPX issue-rate micro-benchmark (roofline denominator) ---------
  * Runs independent chains of one instruction class at full occupancy and

@@ -24,7 +24,7 @@ class CmHost(C.Structure):
     """poy_cm_host (include/poy5_b200.h) == struct cm tables (src/cm.h:33-76)."""
     _fields_ = [("cost", C.c_int32 * 1024), ("worst", C.c_int32 * 1024), ("median", C.c_uint8 * 1024),
                 ("prepend", C.c_int32 * 32), ("tail", C.c_int32 * 32), ("gap_open", C.c_int32),
-                ("cost_model_type", C.c_int32)]
+                ("cost_model_type", C.c_int32), ("is_identity", C.c_int32), ("is_metric", C.c_int32)]
 
 
 def lib_path():
@@ -52,6 +52,7 @@ def load():
     L.poy_ctx_synchronize.argtypes = [vp]
     L.poy_ctx_launch_count.argtypes = [vp]
     L.poy_ctx_launch_count.restype = C.c_uint64
+    L.poy_ctx_stats.argtypes = [vp, vp]
     L.poy_cm_fill.argtypes = [i32p, C.c_int32, C.POINTER(CmHost), C.POINTER(CmHost)]
     L.poy_cm_min_non0.argtypes = [C.POINTER(CmHost)]
     L.poy_cm_get_closest.argtypes = [C.POINTER(CmHost), C.c_int32, C.c_int32]
@@ -75,15 +76,33 @@ def load():
     L.poy_batch_closest.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp]
     L.poy_dos_distance.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp]
     L.poy_dos_median.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.poy_dos_median2.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
+    L.poy_store_create.argtypes = [vp, C.c_int64, C.c_int32, C.POINTER(vp)]
+    L.poy_store_free.argtypes = [vp, vp]
+    L.poy_store_free.restype = None
+    L.poy_store_pool.argtypes = [vp]
+    L.poy_store_pool.restype = vp
+    L.poy_store_count.argtypes = [vp]
+    L.poy_store_count.restype = C.c_int32
+    L.poy_store_bytes.argtypes = [vp]
+    L.poy_store_bytes.restype = C.c_int64
+    L.poy_store_append.argtypes = [vp, vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
+    L.poy_store_truncate.argtypes = [vp, vp, C.c_int32]
+    L.poy_store_lengths.argtypes = [vp, C.c_int32, vp, vp]
+    L.poy_store_read.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
+    L.poy_store_median.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    L.poy_store_distance.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp]
     L.poy_microbench_int.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _LIB = L
     return L
 
 
 EXPORTS = ["poy_ctx_create", "poy_ctx_destroy", "poy_last_error", "poy_status_string", "poy_ctx_set_arena_limit",
-           "poy_ctx_synchronize", "poy_ctx_launch_count", "poy_cm_fill", "poy_cm_min_non0", "poy_cm_get_closest",
+           "poy_ctx_synchronize", "poy_ctx_launch_count", "poy_ctx_stats", "poy_cm_fill", "poy_cm_min_non0", "poy_cm_get_closest",
            "poy_cm_upload", "poy_cm_free", "poy_pool_upload", "poy_pool_from_device", "poy_pool_free",
            "poy_batch_cost_affine", "poy_batch_cost_affine_dev", "poy_batch_align_affine",
            "poy_batch_align_affine_dev", "poy_batch_cost_linear", "poy_batch_align_linear", "poy_batch_median_2", "poy_batch_union",
-           "poy_batch_aligned_cost", "poy_batch_ancestor_2", "poy_batch_closest", "poy_dos_distance", "poy_dos_median",
+           "poy_batch_aligned_cost", "poy_batch_ancestor_2", "poy_batch_closest", "poy_dos_distance", "poy_dos_median", "poy_dos_median2",
+           "poy_store_create", "poy_store_free", "poy_store_pool", "poy_store_count", "poy_store_bytes", "poy_store_append",
+           "poy_store_truncate", "poy_store_lengths", "poy_store_read", "poy_store_median", "poy_store_distance",
            "poy_microbench_int"]

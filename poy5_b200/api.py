@@ -35,6 +35,13 @@ class Context:
     def launches(self):
         return int(self.L.poy_ctx_launch_count(self.h))
 
+    def stats(self):
+        """poy_ctx_stats: dict of cumulative counters (band cells computed, probe / full fills, rounds, ...)"""
+        out = np.zeros(8, np.int64)
+        self.check(self.L.poy_ctx_stats(self.h, _ptr(out)))
+        return dict(launches=int(out[0]), band_cells=int(out[1]), probe_fills=int(out[2]), full_fills=int(out[3]),
+                    repeated=int(out[4]), rounds=int(out[5]), pairs=int(out[6]))
+
     def microbench(self, kind):
         ops = C.c_double(); mhz = C.c_double()
         self.check(self.L.poy_microbench_int(self.h, kind, C.byref(ops), C.byref(mhz)))
@@ -97,4 +104,76 @@ class Pool:
     def close(self):
         if getattr(self, "h", None):
             self.ctx.L.poy_pool_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class Store:
+    """Device-resident node store (poy_store): immutable sequences named by int ids, medians appended in HBM."""
+
+    def __init__(self, ctx, cap_bytes=1 << 24, cap_seqs=4096):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.L.poy_store_create(ctx.h, int(cap_bytes), int(cap_seqs), C.byref(h)))
+        self.h = h
+
+    def __len__(self):
+        return int(self.ctx.L.poy_store_count(self.h))
+
+    @property
+    def nbytes(self):
+        return int(self.ctx.L.poy_store_bytes(self.h))
+
+    def append(self, seqs):
+        """host sequences -> int32 ids"""
+        if not len(seqs):
+            return np.zeros(0, np.int32)
+        lens = np.fromiter((len(s) for s in seqs), np.int64, len(seqs))
+        off = np.zeros(len(seqs) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        data = np.ascontiguousarray(np.concatenate([np.asarray(s, np.uint8) for s in seqs]))
+        first = C.c_int32()
+        self.ctx.check(self.ctx.L.poy_store_append(self.ctx.h, self.h, _ptr(data), _ptr(off), len(seqs), C.byref(first)))
+        return np.arange(first.value, first.value + len(seqs), dtype=np.int32)
+
+    def lengths(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.zeros(len(ids), np.int32)
+        self.ctx.check(self.ctx.L.poy_store_lengths(self.h, len(ids), _ptr(ids), _ptr(out)))
+        return out
+
+    def read(self, ids):
+        """ids -> list of uint8 arrays (device -> host)"""
+        ids = np.ascontiguousarray(ids, np.int32)
+        if not len(ids):
+            return []
+        lens = self.lengths(ids).astype(np.int64)
+        off = np.zeros(len(ids) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        buf = np.zeros(max(1, int(off[-1])), np.uint8)
+        self.ctx.check(self.ctx.L.poy_store_read(self.ctx.h, self.h, len(ids), _ptr(ids), _ptr(off), _ptr(buf)))
+        return [buf[off[q]:off[q + 1]] for q in range(len(ids))]
+
+    def median(self, h, a, b):
+        """SeqCS.DOS.median over ids; medians are appended on the device.  -> (ids, lengths, cost2)"""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        n = len(a)
+        ids = np.zeros(n, np.int32); ln = np.zeros(n, np.int32); c2 = np.zeros(n, np.int32)
+        self.ctx.check(self.ctx.L.poy_store_median(self.ctx.h, self.h, h.c2_full.h, h.c2_original.h, n, _ptr(a), _ptr(b),
+                                                   _ptr(ids), _ptr(ln), _ptr(c2)))
+        return ids, ln, c2
+
+    def distance(self, h, a, b, missing_distance=0):
+        """SeqCS.DOS.distance over ids -> int32 costs"""
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        cost = np.zeros(len(a), np.int32)
+        self.ctx.check(self.ctx.L.poy_store_distance(self.ctx.h, self.h, h.c2_original.h, len(a), _ptr(a), _ptr(b),
+                                                     int(missing_distance), _ptr(cost)))
+        return cost
+
+    def truncate(self, nseq):
+        self.ctx.check(self.ctx.L.poy_store_truncate(self.ctx.h, self.h, int(nseq)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.poy_store_free(self.ctx.h, self.h)
             self.h = None

@@ -46,9 +46,25 @@ __global__ void k_aligned_cost(const DevCM *__restrict__ cm, int n, const uint8_
                                const int64_t *__restrict__ off, const int *__restrict__ len, int use_worst, int *cost) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const int *table = use_worst ? cm->worst32 : cm->cost32;
+    const int *table = use_worst == 1 ? cm->worst32 : cm->cost32;
     const uint8_t *s1 = a + off[p], *s2 = b + off[p];
     const int L = len[p], go = cm->gap_open;
+    if (use_worst >= 2) {
+        const int gopen = cm->model == 1 ? cm->gap_open : 0;
+        // Sequence.Align.recost ?first_gap a b cm (src/sequence.ml:1244-1307, combination branch): one gap opening per
+        // block of columns in which either symbol carries the gap bit; use_worst == 2: first_gap = true (column 0 is
+        // the shared leading gap and is skipped), 3: first_gap = false
+        int res = 0;
+        bool blk = false;
+        for (int i = use_worst == 2 ? 1 : 0; i < L; ++i) {
+            const int x = s1[i] & 31, y = s2[i] & 31;
+            const bool g = ((x | y) & POY_GAP) != 0;
+            res += cm->cost32[(x << 5) + y] + ((g && !blk) ? gopen : 0);
+            blk = g;
+        }
+        cost[p] = res;
+        return;
+    }
     int res = 0, gap_row = 0;
     int i = (L > 0 && (s1[0] & POY_GAP) && (s2[0] & POY_GAP)) ? 1 : 0;
     for (; i < L; ++i) {
@@ -76,10 +92,11 @@ __global__ void k_aligned_cost(const DevCM *__restrict__ cm, int n, const uint8_
 // is reported as out_len = -1.
 __global__ void k_ancestor_2(const DevCM *__restrict__ cm, int n, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
                              const int64_t *__restrict__ off, const int *__restrict__ len, const int64_t *__restrict__ out_off,
-                             uint8_t *out, int *out_len) {
+                             uint8_t *out, int *out_len, const uint8_t *__restrict__ swap) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const uint8_t *s1 = a + off[p], *s2 = b + off[p];
+    const bool sw = swap && swap[p];
+    const uint8_t *s1 = (sw ? b : a) + off[p], *s2 = (sw ? a : b) + off[p];
     uint8_t *o = out + out_off[p];
     const int L = len[p], gap = POY_GAP;
     const bool affine = cm->model == 1;
@@ -126,9 +143,9 @@ cudaError_t launch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int n, const uin
     return cudaGetLastError();
 }
 cudaError_t launch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int n, const uint8_t *a, const uint8_t *b, const int64_t *off,
-                              const int *len, const int64_t *out_off, uint8_t *out, int *out_len) {
+                              const int *len, const int64_t *out_off, uint8_t *out, int *out_len, const uint8_t *swap, int) {
     if (n <= 0) return cudaSuccess;
-    k_ancestor_2<<<(n + 127) / 128, 128, 0, ctx->stream>>>(cm->d, n, a, b, off, len, out_off, out, out_len);
+    k_ancestor_2<<<(n + 127) / 128, 128, 0, ctx->stream>>>(cm->d, n, a, b, off, len, out_off, out, out_len, swap);
     ctx->launches++;
     return cudaGetLastError();
 }

@@ -35,11 +35,19 @@ struct DevCM {
 #define PF_HASGAP 16
 #define PF_PREVGAP 32
 
+// what k_params reads from a cost model: pools (and the node store) remember the signature their per-base parameters
+// were computed for, so switching between c2_full and c2_original (identical under the default affine tables,
+// src/seqCS.ml:51-55) does not recompute them
+struct ParamSig {
+    int prepend[32], gapext[32], gap_open, valid;
+};
+
 struct poy_cm {
-    uint64_t uid;          // unique per upload: pools remember which cost model their parameters belong to
+    uint64_t uid;          // unique per upload
     DevCM *d;
     poy_cm_host h;
     int min_non0, max_entry;
+    ParamSig sig;
 };
 
 struct poy_pool {
@@ -58,8 +66,14 @@ struct poy_pool {
     int32_t nseq;
     int64_t nbytes;
     bool owns_data;
-    uint64_t params_for;       // uid of the cost model the parameters were computed for (0 = none)
-    size_t caps[8];            // capacities of the cached device blocks backing the arrays above
+    ParamSig sig;              // signature of the cost model the parameters were computed for (valid = 0: none)
+    int32_t params_upto;       // sequences [0, params_upto) have parameters for `sig`
+    int32_t flags_upto;        // sequences [0, flags_upto) have h_empty / h_gapcnt
+    uint8_t *d_flags;          // device staging of the per-sequence flags (empty | gap count), 8 bytes per sequence
+    size_t caps[9];            // capacities of the cached device blocks backing the arrays above
+    // node store (store.cu): capacities the arrays above were allocated for; 0 for plain pools
+    int64_t cap_bytes;
+    int32_t cap_seqs;
 };
 
 struct poy_ctx {
@@ -71,10 +85,10 @@ struct poy_ctx {
     uint64_t launches;
     char err[512];
     // grow-only device scratch
-    void *d_scratch[8];
-    size_t scratch_cap[8];
-    void *h_pinned[4];
-    size_t pinned_cap[4];
+    void *d_scratch[12];
+    size_t scratch_cap[12];
+    void *h_pinned[6];
+    size_t pinned_cap[6];
     // auxiliary streams + events: independent launches of one wave run concurrently so that the tail of one
     // overlaps the body of the next
     cudaStream_t aux[4];
@@ -84,6 +98,9 @@ struct poy_ctx {
     void *cache_ptr[64];
     size_t cache_cap[64];
     int cache_n;
+    size_t cache_bytes;
+    int64_t stat_band_cells, stat_probe, stat_full, stat_repeat, stat_rounds, stat_pairs;   // poy_ctx_stats
+    int64_t hint_max_len;  // set by the host entry points for the next *_dev call: longest sequence among the submitted pairs
     // second lane for large banded batches: the batch is cut in two halves whose threshold-doubling rounds run as
     // independent pipelines (own stream set, arenas and host thread), so that the tail of one half's round is
     // filled by the other half's kernels
@@ -125,8 +142,30 @@ struct PairState {        // survives across band fills of the same pair
     long long cells;
 };
 
+// ---- host-side helpers shared by host.cu / dos.cu / store.cu -------------------------------------------------------
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return poy_cuda_fail(ctx, e_, #call); } while (0)
+enum { SL_JOBS = 0, SL_JOBS2 = 1, SL_BOUND = 2, SL_STATE = 3, SL_EBROW = 4, SL_DIR = 5, SL_MISC = 6, SL_WORK = 7,
+       SL_STORE = 8, SL_STORE2 = 9, SL_COUNT = 10 };
+poy_status poy_fail(poy_ctx *ctx, poy_status s, const char *msg);
+poy_status poy_cuda_fail(poy_ctx *ctx, cudaError_t e, const char *where);
+poy_status poy_scratch(poy_ctx *ctx, int slot, size_t bytes, void **out);     // grow-only device scratch slot
+poy_status poy_pinned(poy_ctx *ctx, int slot, size_t bytes, void **out);      // grow-only pinned host slot
+cudaError_t cached_alloc(poy_ctx *ctx, void **out, size_t bytes, size_t *cap_out);
+void cached_free(poy_ctx *ctx, void *p, size_t cap);
+// Every entry point binds the calling thread to the context's device first: host threads other than the one that
+// created the context start out on device 0.
+static inline void bind_device(const poy_ctx *ctx) { if (ctx) cudaSetDevice(ctx->device); }
+// banded alignment of n pairs (affine; linear when h_deltawh != NULL); all d_* are device pointers, h_* host arrays
+poy_status align_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n, const int32_t *h_si,
+                       const int32_t *h_sj, const uint8_t *h_swaped, const int64_t *d_out_off, int32_t *d_cost,
+                       uint8_t *d_median, uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
+                       int32_t *d_out_len, int32_t *h_stats, const int32_t *h_deltawh = nullptr);
+
 // launchers (defined in the .cu files)
-cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool);
+cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool, int s0, int s1);
+cudaError_t launch_seq_flags(poy_ctx *ctx, const poy_pool *pool, int s0, int s1, int2 *d_flags);
+poy_status ensure_params(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool);
+poy_status ensure_flags(poy_ctx *ctx, const poy_pool *pool);
 cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, const int *d_a, const int *d_b,
                                    CostJob *d_jobs, int *d_counts);
 cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
@@ -161,5 +200,13 @@ cudaError_t launch_median_2(poy_ctx *ctx, const poy_cm *cm, int n, const uint8_t
 cudaError_t launch_union(poy_ctx *ctx, int64_t total, const uint8_t *a, const uint8_t *b, uint8_t *out);
 cudaError_t launch_aligned_cost(poy_ctx *ctx, const poy_cm *cm, int n, const uint8_t *a, const uint8_t *b, const int64_t *off,
                                 const int *len, int use_worst, int *cost);
+// swap (optional, device): per pair, exchange the two rows; cap_adjust: unused spare bytes at the slot end (documentation only)
 cudaError_t launch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int n, const uint8_t *a, const uint8_t *b, const int64_t *off,
-                              const int *len, const int64_t *out_off, uint8_t *out, int *out_len);
+                              const int *len, const int64_t *out_off, uint8_t *out, int *out_len, const uint8_t *swap = nullptr,
+                              int cap_adjust = 0);
+poy_status dos_self_recost(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int n, const int32_t *ids, int32_t *cost);
+poy_status dos_median_device(poy_ctx *ctx, const poy_cm *c2_full, const poy_pool *pool, int m, const int32_t *a, const int32_t *b,
+                             const int64_t *h_slot, const int64_t *d_slot, const int64_t *d_slot_end, int64_t slot_total,
+                             int32_t *d_cost, uint8_t *d_median, int32_t *d_mlen, bool *right_justified);
+poy_status pool_alloc(poy_ctx *ctx, poy_pool *p, int64_t nb, int32_t ns);
+poy_status pool_new(poy_ctx *ctx, const int64_t *h_off, int32_t nseq, int32_t cap_seqs, poy_pool **out);

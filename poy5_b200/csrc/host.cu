@@ -13,20 +13,18 @@
 #include "common.cuh"
 
 // ---- error plumbing ---------------------------------------------------------------------
-static poy_status fail(poy_ctx *ctx, poy_status s, const char *msg) {
+poy_status poy_fail(poy_ctx *ctx, poy_status s, const char *msg) {
     if (ctx) { strncpy(ctx->err, msg, sizeof(ctx->err) - 1); ctx->err[sizeof(ctx->err) - 1] = 0; }
     return s;
 }
-static poy_status cuda_fail(poy_ctx *ctx, cudaError_t e, const char *where) {
+poy_status poy_cuda_fail(poy_ctx *ctx, cudaError_t e, const char *where) {
     char buf[400];
     snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
-    return fail(ctx, e == cudaErrorMemoryAllocation ? POY_ERR_NOMEM : POY_ERR_CUDA, buf);
+    return poy_fail(ctx, e == cudaErrorMemoryAllocation ? POY_ERR_NOMEM : POY_ERR_CUDA, buf);
 }
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
 
 // Every entry point binds the calling thread to the context's device first: host threads other than the one that
 // created the context start out on device 0.
-static inline void bind_device(const poy_ctx *ctx) { if (ctx) cudaSetDevice(ctx->device); }
 
 extern "C" const char *poy_status_string(poy_status s) {
     switch (s) {
@@ -88,9 +86,9 @@ extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->twin) { poy_ctx_destroy(ctx->twin); ctx->twin = nullptr; }
     cudaEventDestroy(ctx->ev_twin_start); cudaEventDestroy(ctx->ev_twin_done);
-    for (int s = 0; s < 8; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
+    for (int s = 0; s < 12; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
     for (int i = 0; i < ctx->cache_n; ++i) cudaFree(ctx->cache_ptr[i]);
-    for (int s = 0; s < 4; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
+    for (int s = 0; s < 6; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
     for (int a = 0; a < 4; ++a) { cudaStreamDestroy(ctx->aux[a]); cudaEventDestroy(ctx->ev_join[a]); }
     cudaEventDestroy(ctx->ev_fork);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -109,15 +107,22 @@ extern "C" poy_status poy_ctx_synchronize(poy_ctx *ctx) {
     return POY_OK;
 }
 extern "C" uint64_t poy_ctx_launch_count(const poy_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" poy_status poy_ctx_stats(const poy_ctx *ctx, int64_t out[8]) {
+    if (!ctx || !out) return POY_ERR_ARG;
+    out[0] = (int64_t)ctx->launches; out[1] = ctx->stat_band_cells; out[2] = ctx->stat_probe; out[3] = ctx->stat_full;
+    out[4] = ctx->stat_repeat; out[5] = ctx->stat_rounds; out[6] = ctx->stat_pairs; out[7] = 0;
+    return POY_OK;
+}
 
 // cached device blocks (all users are ordered on ctx->stream, so stream-ordered reuse is safe)
-static cudaError_t cached_alloc(poy_ctx *ctx, void **out, size_t bytes, size_t *cap_out) {
+cudaError_t cached_alloc(poy_ctx *ctx, void **out, size_t bytes, size_t *cap_out) {
     if (bytes < 256) bytes = 256;
     int best = -1;
     for (int i = 0; i < ctx->cache_n; ++i)
         if (ctx->cache_cap[i] >= bytes && ctx->cache_cap[i] <= 4 * bytes && (best < 0 || ctx->cache_cap[i] < ctx->cache_cap[best])) best = i;
     if (best >= 0) {
         *out = ctx->cache_ptr[best]; *cap_out = ctx->cache_cap[best];
+        ctx->cache_bytes -= ctx->cache_cap[best];
         ctx->cache_ptr[best] = ctx->cache_ptr[ctx->cache_n - 1]; ctx->cache_cap[best] = ctx->cache_cap[ctx->cache_n - 1];
         --ctx->cache_n;
         return cudaSuccess;
@@ -126,35 +131,47 @@ static cudaError_t cached_alloc(poy_ctx *ctx, void **out, size_t bytes, size_t *
     while (cap < bytes) cap += cap / 2 + 256;   // geometric size classes so that blocks get reused
     cudaError_t e = cudaMalloc(out, cap);
     if (e != cudaSuccess) {                      // out of memory: drop the cache and retry with the exact size
+        cudaGetLastError();
         for (int i = 0; i < ctx->cache_n; ++i) cudaFree(ctx->cache_ptr[i]);
-        ctx->cache_n = 0;
+        ctx->cache_n = 0; ctx->cache_bytes = 0;
         cap = bytes;
         e = cudaMalloc(out, cap);
     }
     *cap_out = cap;
     return e;
 }
-static void cached_free(poy_ctx *ctx, void *p, size_t cap) {
+void cached_free(poy_ctx *ctx, void *p, size_t cap) {
     if (!p) return;
-    if (ctx && ctx->cache_n < 64 && cap <= (512u << 20)) { ctx->cache_ptr[ctx->cache_n] = p; ctx->cache_cap[ctx->cache_n] = cap; ++ctx->cache_n; }
-    else cudaFree(p);
+    // bounded by entries AND by total bytes (4 GiB): the cache serves short-lived tree-search pools, not bulk batches
+    if (ctx && ctx->cache_n < 64 && cap <= (512u << 20) && ctx->cache_bytes + cap <= (4ull << 30)) {
+        ctx->cache_ptr[ctx->cache_n] = p; ctx->cache_cap[ctx->cache_n] = cap; ++ctx->cache_n; ctx->cache_bytes += cap;
+    } else cudaFree(p);
 }
 
 // grow-only scratch slots
-static poy_status scratch(poy_ctx *ctx, int slot, size_t bytes, void **out) {
+poy_status poy_scratch(poy_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->scratch_cap[slot] < bytes) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_scratch[slot]) { cudaFree(ctx->d_scratch[slot]); ctx->d_scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&ctx->d_scratch[slot], want);
         if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&ctx->d_scratch[slot], want); }
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scratch)");
+        if (e != cudaSuccess) {   // the memory may sit in the block cache of freed pools (this context's or its twin's)
+            cudaGetLastError();
+            for (poy_ctx *c : { ctx, ctx->twin }) {
+                if (!c) continue;
+                for (int i = 0; i < c->cache_n; ++i) cudaFree(c->cache_ptr[i]);
+                c->cache_n = 0; c->cache_bytes = 0;
+            }
+            e = cudaMalloc(&ctx->d_scratch[slot], want);
+        }
+        if (e != cudaSuccess) return poy_cuda_fail(ctx, e, "cudaMalloc(scratch)");
         ctx->scratch_cap[slot] = want;
     }
     *out = ctx->d_scratch[slot];
     return POY_OK;
 }
-static poy_status pinned(poy_ctx *ctx, int slot, size_t bytes, void **out) {
+poy_status poy_pinned(poy_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->pinned_cap[slot] < bytes) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->h_pinned[slot]) { cudaFreeHost(ctx->h_pinned[slot]); ctx->h_pinned[slot] = nullptr; ctx->pinned_cap[slot] = 0; }
@@ -165,7 +182,6 @@ static poy_status pinned(poy_ctx *ctx, int slot, size_t bytes, void **out) {
     *out = ctx->h_pinned[slot];
     return POY_OK;
 }
-enum { SL_JOBS = 0, SL_JOBS2 = 1, SL_BOUND = 2, SL_STATE = 3, SL_EBROW = 4, SL_DIR = 5, SL_MISC = 6, SL_WORK = 7 };
 
 // ---- Cost_matrix.Two_D table construction (src/cost_matrix.ml) --------------------------------
 namespace {
@@ -281,6 +297,8 @@ void fill_cost_matrix(const int32_t single[25], bool create_original, poy_cm_hos
     if (pos && sym && ident) fill_all_combinations(m);
     else fill_bitwise(m, create_original);
     fill_prepend_tail(m);
+    m->is_identity = ident ? 1 : 0;          // set_identity / set_metric, src/cost_matrix.ml:1169-1177
+    m->is_metric = (pos && sym && ident) ? 1 : 0;
 }
 }  // namespace
 
@@ -327,21 +345,24 @@ extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm *
     *out = nullptr;
     int max_entry = 0;
     for (int x = 0; x < 1024; ++x) {
-        if (h->cost[x] < 0) return fail(ctx, POY_ERR_COST_RANGE, "negative cost entry");
+        if (h->cost[x] < 0) return poy_fail(ctx, POY_ERR_COST_RANGE, "negative cost entry");
         max_entry = std::max(max_entry, h->cost[x]);
     }
     for (int x = 0; x < 32; ++x) {
-        if (h->prepend[x] < 0 || h->tail[x] < 0) return fail(ctx, POY_ERR_COST_RANGE, "negative prepend/tail cost");
+        if (h->prepend[x] < 0 || h->tail[x] < 0) return poy_fail(ctx, POY_ERR_COST_RANGE, "negative prepend/tail cost");
         max_entry = std::max(max_entry, std::max(h->prepend[x], h->tail[x]));
     }
     if (h->gap_open < 0 || max_entry >= POY_INF || h->gap_open >= POY_INF)
-        return fail(ctx, POY_ERR_COST_RANGE, "cost entry or gap opening >= HIGH_NUM");
+        return poy_fail(ctx, POY_ERR_COST_RANGE, "cost entry or gap opening >= HIGH_NUM");
     static std::atomic<uint64_t> next_uid{0};   // contexts may be driven from different host threads
     poy_cm *cm = new poy_cm;
     cm->uid = ++next_uid;
     cm->h = *h;
     cm->min_non0 = poy_cm_min_non0(h);
     cm->max_entry = max_entry;
+    memset(&cm->sig, 0, sizeof cm->sig);
+    for (int a = 0; a < 32; ++a) { cm->sig.prepend[a] = h->prepend[a]; cm->sig.gapext[a] = h->cost[(a << 5) + GAPC]; }
+    cm->sig.gap_open = h->gap_open; cm->sig.valid = 1;
     DevCM *img = new DevCM;
     memset(img, 0, sizeof *img);
     for (int a = 0; a < 16; ++a) for (int b = 0; b < 16; ++b) img->cost16[a * 16 + b] = h->cost[(a << 5) + b];
@@ -360,7 +381,7 @@ extern "C" poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *h, poy_cm *
     if (e == cudaSuccess) e = cudaMemcpyAsync(cm->d, img, sizeof(DevCM), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     delete img;
-    if (e != cudaSuccess) { delete cm; return cuda_fail(ctx, e, "poy_cm_upload"); }
+    if (e != cudaSuccess) { delete cm; return poy_cuda_fail(ctx, e, "poy_cm_upload"); }
     *out = cm;
     return POY_OK;
 }
@@ -373,14 +394,17 @@ extern "C" void poy_cm_free(poy_ctx *ctx, poy_cm *cm) {
 }
 
 // ---- pool ----------------------------------------------------------------------------------------
-static poy_status pool_alloc(poy_ctx *ctx, poy_pool *p) {
-    const size_t nb = (size_t)std::max<int64_t>(p->nbytes, 1);
+// `nb` / `ns`: bytes and sequences the per-base / per-sequence arrays are allocated for (the node store asks for more
+// than it currently holds)
+poy_status pool_alloc(poy_ctx *ctx, poy_pool *p, int64_t nb_, int32_t ns_) {
+    const size_t nb = (size_t)std::max<int64_t>(nb_, 1), ns = (size_t)std::max(ns_, 1);
     CK(cached_alloc(ctx, (void **)&p->d_rowp, nb * sizeof(int4), &p->caps[0]));
     CK(cached_alloc(ctx, (void **)&p->d_colp, nb * sizeof(int4), &p->caps[1]));
     CK(cached_alloc(ctx, (void **)&p->d_rowpk, nb * sizeof(unsigned), &p->caps[2]));
     CK(cached_alloc(ctx, (void **)&p->d_h0, nb * sizeof(int), &p->caps[3]));
     CK(cached_alloc(ctx, (void **)&p->d_g0, nb * sizeof(int), &p->caps[4]));
-    CK(cached_alloc(ctx, (void **)&p->d_gapfree, (size_t)std::max(p->nseq, 1), &p->caps[5]));
+    CK(cached_alloc(ctx, (void **)&p->d_gapfree, ns, &p->caps[5]));
+    CK(cached_alloc(ctx, (void **)&p->d_flags, ns * sizeof(int2), &p->caps[8]));
     return POY_OK;
 }
 
@@ -391,6 +415,7 @@ extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
     if (p->owns_data) { cached_free(ctx, p->d_data, p->caps[6]); cached_free(ctx, p->d_off, p->caps[7]); }
     cached_free(ctx, p->d_rowp, p->caps[0]); cached_free(ctx, p->d_colp, p->caps[1]); cached_free(ctx, p->d_rowpk, p->caps[2]);
     cached_free(ctx, p->d_h0, p->caps[3]); cached_free(ctx, p->d_g0, p->caps[4]); cached_free(ctx, p->d_gapfree, p->caps[5]);
+    cached_free(ctx, p->d_flags, p->caps[8]);
     free(p->h_off);
     free(p->h_gapfree);
     free(p->h_empty);
@@ -398,16 +423,21 @@ extern "C" void poy_pool_free(poy_ctx *ctx, poy_pool *p) {
     delete p;
 }
 
-static poy_status pool_new(poy_ctx *ctx, const int64_t *h_off, int32_t nseq, poy_pool **out) {
-    if (nseq < 0 || !h_off || h_off[0] != 0) return fail(ctx, POY_ERR_ARG, "pool offsets must start at 0");
+// host-side bookkeeping of a pool with room for `cap_seqs` sequences
+poy_status pool_new(poy_ctx *ctx, const int64_t *h_off, int32_t nseq, int32_t cap_seqs, poy_pool **out) {
+    if (nseq < 0 || !h_off || h_off[0] != 0) return poy_fail(ctx, POY_ERR_ARG, "pool offsets must start at 0");
     for (int s = 0; s < nseq; ++s)
-        if (h_off[s + 1] <= h_off[s]) return fail(ctx, POY_ERR_ARG, "every pool sequence needs at least its leading gap");
+        if (h_off[s + 1] <= h_off[s]) return poy_fail(ctx, POY_ERR_ARG, "every pool sequence needs at least its leading gap");
+    if (cap_seqs < nseq) cap_seqs = nseq;
     poy_pool *p = new poy_pool;
     memset(p, 0, sizeof *p);
     p->nseq = nseq;
     p->nbytes = h_off[nseq];
-    p->h_gapfree = (uint8_t *)calloc((size_t)nseq + 1, 1);
-    p->h_off = (int64_t *)malloc(sizeof(int64_t) * (nseq + 1));
+    p->h_gapfree = (uint8_t *)calloc((size_t)cap_seqs + 1, 1);
+    p->h_empty = (uint8_t *)calloc((size_t)cap_seqs + 1, 1);
+    p->h_gapcnt = (int32_t *)calloc((size_t)cap_seqs + 1, sizeof(int32_t));
+    p->h_off = (int64_t *)malloc(sizeof(int64_t) * ((size_t)cap_seqs + 1));
+    if (!p->h_gapfree || !p->h_empty || !p->h_gapcnt || !p->h_off) { poy_pool_free(nullptr, p); return poy_fail(ctx, POY_ERR_NOMEM, "host allocation failed"); }
     memcpy(p->h_off, h_off, sizeof(int64_t) * (nseq + 1));
     *out = p;
     return POY_OK;
@@ -418,15 +448,15 @@ extern "C" poy_status poy_pool_upload(poy_ctx *ctx, const uint8_t *data, const i
     if (!ctx || !data || !offsets || !out) return POY_ERR_ARG;
     *out = nullptr;
     poy_pool *p;
-    poy_status s = pool_new(ctx, offsets, nseq, &p);
+    poy_status s = pool_new(ctx, offsets, nseq, nseq, &p);
     if (s != POY_OK) return s;
     p->owns_data = true;
     cudaError_t e = cached_alloc(ctx, (void **)&p->d_data, (size_t)std::max<int64_t>(p->nbytes, 1), &p->caps[6]);
     if (e == cudaSuccess) e = cached_alloc(ctx, (void **)&p->d_off, sizeof(int64_t) * (nseq + 1), &p->caps[7]);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_data, data, (size_t)p->nbytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_off, offsets, sizeof(int64_t) * (nseq + 1), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { poy_pool_free(ctx, p); return cuda_fail(ctx, e, "poy_pool_upload"); }
-    s = pool_alloc(ctx, p);
+    if (e != cudaSuccess) { poy_pool_free(ctx, p); return poy_cuda_fail(ctx, e, "poy_pool_upload"); }
+    s = pool_alloc(ctx, p, p->nbytes, nseq);
     if (s != POY_OK) { poy_pool_free(ctx, p); return s; }
     *out = p;
     return POY_OK;
@@ -438,24 +468,47 @@ extern "C" poy_status poy_pool_from_device(poy_ctx *ctx, const uint8_t *d_data, 
     if (!ctx || !d_data || !d_offsets || !h_offsets || !out) return POY_ERR_ARG;
     *out = nullptr;
     poy_pool *p;
-    poy_status s = pool_new(ctx, h_offsets, nseq, &p);
+    poy_status s = pool_new(ctx, h_offsets, nseq, nseq, &p);
     if (s != POY_OK) return s;
     p->owns_data = false;
     p->d_data = const_cast<uint8_t *>(d_data);
     p->d_off = const_cast<int64_t *>(d_offsets);
-    s = pool_alloc(ctx, p);
+    s = pool_alloc(ctx, p, p->nbytes, nseq);
     if (s != POY_OK) { poy_pool_free(ctx, p); return s; }
     *out = p;
     return POY_OK;
 }
 
-static poy_status ensure_params(poy_ctx *ctx, const poy_cm *cm, const poy_pool *cpool) {
+// Per-base gap parameters of the sequences that do not have them yet for this cost model (all of them when the
+// model's parameter signature differs from the one they were computed for).
+poy_status ensure_params(poy_ctx *ctx, const poy_cm *cm, const poy_pool *cpool) {
     poy_pool *pool = const_cast<poy_pool *>(cpool);
-    if (pool->params_for == cm->uid) return POY_OK;
-    CK(launch_params(ctx, cm, pool));
-    CK(cudaMemcpyAsync(pool->h_gapfree, pool->d_gapfree, (size_t)pool->nseq, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!pool->sig.valid || memcmp(&pool->sig, &cm->sig, sizeof(ParamSig)) != 0) { pool->sig = cm->sig; pool->params_upto = 0; }
+    if (pool->params_upto >= pool->nseq) return POY_OK;
+    const int s0 = pool->params_upto, s1 = pool->nseq;
+    CK(launch_params(ctx, cm, pool, s0, s1));
+    CK(cudaMemcpyAsync(pool->h_gapfree + s0, pool->d_gapfree + s0, (size_t)(s1 - s0), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    pool->params_for = cm->uid;
+    pool->params_upto = s1;
+    return POY_OK;
+}
+
+// Sequence.is_empty / Sequence.count_gaps of the sequences that do not have them yet (device kernel + 8 bytes per
+// sequence read back; pools made by poy_pool_from_device and the node store's medians have no host copy)
+poy_status ensure_flags(poy_ctx *ctx, const poy_pool *cpool) {
+    poy_pool *pool = const_cast<poy_pool *>(cpool);
+    if (pool->flags_upto >= pool->nseq) return POY_OK;
+    bind_device(ctx);
+    const int s0 = pool->flags_upto, s1 = pool->nseq, n = s1 - s0;
+    void *v_pin;
+    poy_status s = poy_pinned(ctx, 4, sizeof(int2) * (size_t)n, &v_pin);
+    if (s != POY_OK) return s;
+    int2 *hf = (int2 *)v_pin;
+    CK(launch_seq_flags(ctx, pool, s0, s1, (int2 *)pool->d_flags + s0));
+    CK(cudaMemcpyAsync(hf, (int2 *)pool->d_flags + s0, sizeof(int2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < n; ++q) { pool->h_empty[s0 + q] = (uint8_t)hf[q].x; pool->h_gapcnt[s0 + q] = hf[q].y; }
+    pool->flags_upto = s1;
     return POY_OK;
 }
 
@@ -469,7 +522,7 @@ static int64_t max_len(const poy_pool *pool) {
 static poy_status domain_check(poy_ctx *ctx, const poy_cm *cm, int64_t len_sum) {
     const int64_t per_step = (int64_t)cm->max_entry + 2 * (int64_t)cm->h.gap_open;
     if (per_step * len_sum + cm->h.gap_open >= POY_INF)
-        return fail(ctx, POY_ERR_COST_RANGE, "sequence lengths x costs can reach HIGH_NUM; the reference is undefined there");
+        return poy_fail(ctx, POY_ERR_COST_RANGE, "sequence lengths x costs can reach HIGH_NUM; the reference is undefined there");
     return POY_OK;
 }
 
@@ -478,19 +531,21 @@ extern "C" poy_status poy_batch_cost_affine_dev(poy_ctx *ctx, const poy_cm *cm, 
                                                 const int32_t *d_a, const int32_t *d_b, int32_t *d_cost) {
     bind_device(ctx);
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!d_a || !d_b || !d_cost))) return POY_ERR_ARG;
-    if (cm->h.cost_model_type != 1) return fail(ctx, POY_ERR_MODEL, "cost_affine needs an affine cost model");
+    if (cm->h.cost_model_type != 1) return poy_fail(ctx, POY_ERR_MODEL, "cost_affine needs an affine cost model");
     if (n == 0) return POY_OK;
-    const int64_t ml = max_len(pool);
+    // `ml`: longest sequence among the submitted pairs when the caller knows it (host entry point), else of the pool
+    const int64_t ml = ctx->hint_max_len > 0 ? ctx->hint_max_len : max_len(pool);
+    ctx->hint_max_len = 0;
     poy_status s = domain_check(ctx, cm, 2 * ml);
     if (s != POY_OK) return s;
     s = ensure_params(ctx, cm, pool);
     if (s != POY_OK) return s;
     void *jobs, *misc, *bound;
-    if ((s = scratch(ctx, SL_JOBS, sizeof(CostJob) * (size_t)n, &jobs)) != POY_OK) return s;
-    if ((s = scratch(ctx, SL_MISC, 64, &misc)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_JOBS, sizeof(CostJob) * (size_t)n, &jobs)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_MISC, 64, &misc)) != POY_OK) return s;
     const int blocks = ctx->sm_count * 4;
     const size_t bound_stride = (size_t)ml + 2;
-    if ((s = scratch(ctx, SL_BOUND, sizeof(int4) * 2 * bound_stride * (size_t)blocks * 4, &bound)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_BOUND, sizeof(int4) * 2 * bound_stride * (size_t)blocks * 4, &bound)) != POY_OK) return s;
     int *counts = (int *)misc;  // [0],[1] = work counters; [2],[3] = job counts
     CK(cudaMemsetAsync(counts, 0, 16, ctx->stream));
     CK(launch_build_cost_jobs(ctx, pool, n, d_a, d_b, (CostJob *)jobs, counts + 2));
@@ -503,14 +558,18 @@ extern "C" poy_status poy_batch_cost_affine(poy_ctx *ctx, const poy_cm *cm, cons
     bind_device(ctx);
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!a || !b || !cost))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
-    for (int p = 0; p < n; ++p)
-        if (a[p] < 0 || a[p] >= pool->nseq || b[p] < 0 || b[p] >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+    int64_t ml = 1;
+    for (int p = 0; p < n; ++p) {
+        if (a[p] < 0 || a[p] >= pool->nseq || b[p] < 0 || b[p] >= pool->nseq) return poy_fail(ctx, POY_ERR_ARG, "pair index out of range");
+        ml = std::max(ml, std::max(pool->h_off[a[p] + 1] - pool->h_off[a[p]], pool->h_off[b[p] + 1] - pool->h_off[b[p]]));
+    }
     void *dbuf;
-    poy_status s = scratch(ctx, SL_STATE, sizeof(int32_t) * 3 * (size_t)n, &dbuf);
+    poy_status s = poy_scratch(ctx, SL_STATE, sizeof(int32_t) * 3 * (size_t)n, &dbuf);
     if (s != POY_OK) return s;
     int32_t *d_a = (int32_t *)dbuf, *d_b = d_a + n, *d_cost = d_b + n;
     CK(cudaMemcpyAsync(d_a, a, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_b, b, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->hint_max_len = ml;    // boundary scratch and domain check from the submitted pairs, not from the whole pool
     s = poy_batch_cost_affine_dev(ctx, cm, pool, n, d_a, d_b, d_cost);
     if (s != POY_OK) return s;
     CK(cudaMemcpyAsync(cost, d_cost, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -558,21 +617,21 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                              uint8_t *d_median, uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
                              int32_t *d_out_len, int32_t *h_stats, const int32_t *h_deltawh = nullptr) {
     const bool linear = h_deltawh != nullptr;
-    if (!linear && cm->h.cost_model_type != 1) return fail(ctx, POY_ERR_MODEL, "align_affine needs an affine cost model");
-    if (linear && cm->h.cost_model_type == 1) return fail(ctx, POY_ERR_MODEL, "the linear-gap entry points need a non-affine cost model");
+    if (!linear && cm->h.cost_model_type != 1) return poy_fail(ctx, POY_ERR_MODEL, "align_affine needs an affine cost model");
+    if (linear && cm->h.cost_model_type == 1) return poy_fail(ctx, POY_ERR_MODEL, "the linear-gap entry points need a non-affine cost model");
     if (n == 0) return POY_OK;
     const bool want_trace = d_median || d_medianwg || d_resi || d_resj || d_out_len;
-    if (want_trace && !d_out_off) return fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
+    if (want_trace && !d_out_off) return poy_fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
     std::vector<HostPair> hp((size_t)n);
     int64_t eb_total = 0, maxsum = 0;
     for (int p = 0; p < n; ++p) {
         const int a = h_si[p], b = h_sj[p];
-        if (a < 0 || a >= pool->nseq || b < 0 || b >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+        if (a < 0 || a >= pool->nseq || b < 0 || b >= pool->nseq) return poy_fail(ctx, POY_ERR_ARG, "pair index out of range");
         HostPair &h = hp[p];
         h.off_i = pool->h_off[a]; h.off_j = pool->h_off[b];
         h.lasti = (int)(pool->h_off[a + 1] - h.off_i) - 1;
         h.lastj = (int)(pool->h_off[b + 1] - h.off_j) - 1;
-        if (h.lastj < h.lasti) return fail(ctx, POY_ERR_ORDER, "pass the shorter one as first");
+        if (h.lastj < h.lasti) return poy_fail(ctx, POY_ERR_ORDER, "pass the shorter one as first");
         h.T = (h.lastj - h.lasti + 1) * cm->min_non0;  // algn_fill_plane_3_aff, src/algn.c:2348-2349
         h.iterations = 0; h.cells = 0; h.done = false; h.fullplane = 0; h.probe = 0; h.want_dirs = 0; h.repeat = 0;
         if (linear) {   // algn_nw_limit / algn_fill_plane_2: full plane or Ukkonen band (src/algn.c:2963, 1141-1176)
@@ -619,12 +678,12 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     }
 
     void *v_state, *v_eb, *v_jobs, *v_misc, *v_pin, *v_pin2;
-    if ((s = scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
-    if ((s = scratch(ctx, SL_EBROW, sizeof(int) * 2 * (size_t)eb_total + 16, &v_eb)) != POY_OK) return s;   // rows + their snapshots
-    if ((s = scratch(ctx, SL_JOBS, sizeof(BandJob) * (size_t)n, &v_jobs)) != POY_OK) return s;
-    if ((s = scratch(ctx, SL_MISC, 256, &v_misc)) != POY_OK) return s;
-    if ((s = pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (size_t)n, &v_pin)) != POY_OK) return s;
-    if ((s = pinned(ctx, 1, (size_t)n + sizeof(int32_t) * (size_t)n, &v_pin2)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_EBROW, sizeof(int) * 2 * (size_t)eb_total + 16, &v_eb)) != POY_OK) return s;   // rows + their snapshots
+    if ((s = poy_scratch(ctx, SL_JOBS, sizeof(BandJob) * (size_t)n, &v_jobs)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_MISC, 256, &v_misc)) != POY_OK) return s;
+    if ((s = poy_pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (size_t)n, &v_pin)) != POY_OK) return s;
+    if ((s = poy_pinned(ctx, 1, (size_t)n + sizeof(int32_t) * (size_t)n, &v_pin2)) != POY_OK) return s;
     PairState *d_state = (PairState *)v_state;
     uint8_t *d_done = (uint8_t *)(d_state + n);
     int *d_eb = (int *)v_eb, *d_eb_snap = d_eb + eb_total;
@@ -720,7 +779,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 ++end;
             }
             void *v_dir;
-            if ((s = scratch(ctx, SL_DIR, (size_t)used, &v_dir)) != POY_OK) return s;
+            if ((s = poy_scratch(ctx, SL_DIR, (size_t)used, &v_dir)) != POY_OK) return s;
             uint8_t *d_dir = (uint8_t *)v_dir;
             BandJob *hj = (BandJob *)v_pin;
             const int nj = (int)(end - pos);
@@ -759,18 +818,18 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                     cudaError_t le;
                     if (linear) le = launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch & 15), d_state, d_dir);
                     else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, pr != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir, lowlat);
-                    if (le != cudaSuccess) { ctx->stream = main_stream; return cuda_fail(ctx, le, "band fill launch"); }
+                    if (le != cudaSuccess) { ctx->stream = main_stream; return poy_cuda_fail(ctx, le, "band fill launch"); }
                 } else {
                     void *v_work;
                     const size_t wstride = 6 * (size_t)((gen_width + 31) & ~31ll);
                     const int blocks = std::min(gen_blocks, q1 - q0);
                     ctx->stream = main_stream;
-                    if ((s = scratch(ctx, SL_WORK, sizeof(int) * wstride * (size_t)blocks, &v_work)) != POY_OK) return s;
+                    if ((s = poy_scratch(ctx, SL_WORK, sizeof(int) * wstride * (size_t)blocks, &v_work)) != POY_OK) return s;
                     ctx->stream = ctx->aux[ax];
                     cudaError_t le;
                     if (linear) le = launch_band_lin_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_dir, (int *)v_work, wstride, blocks);
                     else le = launch_band_generic(ctx, cm, pool, d_jobs + q0, q1 - q0, d_state, d_eb, d_dir, (int *)v_work, wstride, blocks);
-                    if (le != cudaSuccess) { ctx->stream = main_stream; return cuda_fail(ctx, le, "generic band fill launch"); }
+                    if (le != cudaSuccess) { ctx->stream = main_stream; return poy_cuda_fail(ctx, le, "generic band fill launch"); }
                 }
                 ++nlaunch;
                 q0 = q1;
@@ -819,6 +878,12 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     if (d_cost) {
         CK(launch_gather_cost(ctx, d_state, n, d_cost));
     }
+    {
+        int64_t cells = 0;
+        for (int p = 0; p < n; ++p) cells += hp[p].cells;
+        ctx->stat_band_cells += cells; ctx->stat_probe += n_probe; ctx->stat_full += n_full; ctx->stat_repeat += n_repeat;
+        ctx->stat_rounds += rounds; ctx->stat_pairs += n;
+    }
     if (trace) fprintf(stderr, "[poy5_b200] align n=%d rounds=%d waves=%d host prep %.1f ms, device wait %.1f ms; fills: %lld probe, %lld full, %lld repeated\n",
                        n, rounds, waves, t_prep * 1e3, t_wait * 1e3, n_probe, n_full, n_repeat);
     if (h_stats)
@@ -832,10 +897,10 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
 // Large batches are cut in two halves that run align_impl concurrently, the second one on the context's twin
 // (own streams, scratch and host thread).  Every per-pair array is indexed by the pair's position in the batch, so
 // the second half simply gets the pointers advanced by n0.  POY_SPLIT=0 turns this off.
-static poy_status align_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n, const int32_t *h_si,
-                              const int32_t *h_sj, const uint8_t *h_swaped, const int64_t *d_out_off, int32_t *d_cost,
-                              uint8_t *d_median, uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
-                              int32_t *d_out_len, int32_t *h_stats, const int32_t *h_deltawh = nullptr) {
+poy_status align_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n, const int32_t *h_si,
+                       const int32_t *h_sj, const uint8_t *h_swaped, const int64_t *d_out_off, int32_t *d_cost,
+                       uint8_t *d_median, uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj,
+                       int32_t *d_out_len, int32_t *h_stats, const int32_t *h_deltawh) {
     const bool linear = h_deltawh != nullptr;
     const char *se = getenv("POY_SPLIT"), *sm = getenv("POY_SPLIT_MIN");   // POY_SPLIT_MIN: smallest batch that is split (test hook)
     const int split_min = sm ? std::max(2, atoi(sm)) : 4096;
@@ -845,34 +910,49 @@ static poy_status align_split(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
                           d_out_len, h_stats, h_deltawh);
     if (!ctx->twin) {
         poy_status cs = poy_ctx_create(ctx->device, nullptr, &ctx->twin);
-        if (cs != POY_OK) return fail(ctx, cs, "second lane: context creation failed");
+        if (cs != POY_OK) return poy_fail(ctx, cs, "second lane: context creation failed");
         ctx->twin->is_twin = true;
     }
     poy_ctx *tw = ctx->twin;
     poy_status s = ensure_params(ctx, cm, pool);     // once, before the lanes diverge
     if (s != POY_OK) return s;
-    const uint64_t full_arena = ctx->arena_limit;
-    ctx->arena_limit = tw->arena_limit = std::max<uint64_t>(full_arena / 2, 1ull << 20);
     CK(cudaEventRecord(ctx->ev_twin_start, ctx->stream));
     CK(cudaStreamWaitEvent(tw->stream, ctx->ev_twin_start, 0));
+    // the two lanes share the direction arena half and half; restored on every exit path
+    struct ArenaGuard {
+        poy_ctx *c; uint64_t full;
+        ~ArenaGuard() { c->arena_limit = full; }
+    } guard{ ctx, ctx->arena_limit };
+    ctx->arena_limit = tw->arena_limit = std::max<uint64_t>(guard.full / 2, 1ull << 20);
     const int32_t n0 = n / 2, n1 = n - n0;
     const int per = linear ? 2 : 4;
     poy_status s1 = POY_OK;
     const uint64_t tw_launches0 = tw->launches;
-    std::thread lane([&] {
+    auto second = [&] {
         cudaSetDevice(ctx->device);
         s1 = align_impl(tw, cm, pool, n1, h_si + n0, h_sj + n0, h_swaped ? h_swaped + n0 : nullptr,
                         d_out_off ? d_out_off + n0 : nullptr, d_cost ? d_cost + n0 : nullptr, d_median, d_medianwg, d_resi, d_resj,
                         d_out_len ? d_out_len + (size_t)per * n0 : nullptr, h_stats ? h_stats + 4 * (size_t)n0 : nullptr,
                         h_deltawh ? h_deltawh + n0 : nullptr);
-    });
+    };
+    std::thread lane;
+    bool threaded = true;
+    try { lane = std::thread(second); } catch (...) { threaded = false; }   // no C++ exception may cross the C ABI
     const poy_status s0 = align_impl(ctx, cm, pool, n0, h_si, h_sj, h_swaped, d_out_off, d_cost, d_median, d_medianwg, d_resi,
                                      d_resj, d_out_len, h_stats, h_deltawh);
-    lane.join();
-    ctx->arena_limit = full_arena;
+    if (threaded) lane.join(); else second();   // thread creation failed: the second half runs after the first
     ctx->launches += tw->launches - tw_launches0;
+    ctx->stat_band_cells += tw->stat_band_cells; ctx->stat_probe += tw->stat_probe; ctx->stat_full += tw->stat_full;
+    ctx->stat_repeat += tw->stat_repeat; ctx->stat_rounds += tw->stat_rounds; ctx->stat_pairs += tw->stat_pairs;
+    tw->stat_band_cells = tw->stat_probe = tw->stat_full = tw->stat_repeat = tw->stat_rounds = tw->stat_pairs = 0;
     cudaEventRecord(ctx->ev_twin_done, tw->stream);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_twin_done, 0);
+    if (s0 != POY_OK && s1 != POY_OK) {
+        char both[sizeof ctx->err];
+        snprintf(both, sizeof both, "%.240s; second lane: %.240s", ctx->err, tw->err);
+        snprintf(ctx->err, sizeof ctx->err, "%s", both);
+        return s0;
+    }
     if (s0 != POY_OK) return s0;
     if (s1 != POY_OK) { snprintf(ctx->err, sizeof ctx->err, "%s", tw->err); return s1; }
     return POY_OK;
@@ -914,12 +994,12 @@ extern "C" poy_status poy_batch_align_affine(poy_ctx *ctx, const poy_cm *cm, con
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!si || !sj))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     const bool want_trace = median || medianwg || resi || resj || out_len;
-    if (want_trace && !out_off) return fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
+    if (want_trace && !out_off) return poy_fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
     // total output bytes = end of the last slot
     int64_t total = 0;
     if (want_trace)
         for (int p = 0; p < n; ++p) {
-            if (si[p] < 0 || si[p] >= pool->nseq || sj[p] < 0 || sj[p] >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+            if (si[p] < 0 || si[p] >= pool->nseq || sj[p] < 0 || sj[p] >= pool->nseq) return poy_fail(ctx, POY_ERR_ARG, "pair index out of range");
             const int64_t cap = (pool->h_off[si[p] + 1] - pool->h_off[si[p]]) + (pool->h_off[sj[p] + 1] - pool->h_off[sj[p]]) + 2;
             total = std::max(total, out_off[p] + cap);
         }
@@ -927,7 +1007,7 @@ extern "C" poy_status poy_batch_align_affine(poy_ctx *ctx, const poy_cm *cm, con
     const size_t al_total = ((size_t)total + 255) & ~(size_t)255;
     void *v_out;
     const size_t need = sizeof(int64_t) * (size_t)n + sizeof(int32_t) * 5 * (size_t)n + al_total * (size_t)nout + 1024;
-    poy_status s = scratch(ctx, SL_JOBS2, need, &v_out);
+    poy_status s = poy_scratch(ctx, SL_JOBS2, need, &v_out);
     if (s != POY_OK) return s;
     uint8_t *cur = (uint8_t *)v_out;
     int64_t *d_out_off = (int64_t *)cur; cur += sizeof(int64_t) * (size_t)n;
@@ -962,10 +1042,10 @@ extern "C" poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, con
     if (!ctx || !cm || !pool || n < 0 || (n > 0 && (!s1 || !s2 || !deltawh))) return POY_ERR_ARG;
     if (n == 0) return POY_OK;
     const bool want_trace = r1 || r2 || out_len;
-    if (want_trace && !out_off) return fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
+    if (want_trace && !out_off) return poy_fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
     int64_t total = 0;
     for (int p = 0; p < n; ++p) {
-        if (s1[p] < 0 || s1[p] >= pool->nseq || s2[p] < 0 || s2[p] >= pool->nseq) return fail(ctx, POY_ERR_ARG, "pair index out of range");
+        if (s1[p] < 0 || s1[p] >= pool->nseq || s2[p] < 0 || s2[p] >= pool->nseq) return poy_fail(ctx, POY_ERR_ARG, "pair index out of range");
         if (want_trace) {
             const int64_t cap = (pool->h_off[s1[p] + 1] - pool->h_off[s1[p]]) + (pool->h_off[s2[p] + 1] - pool->h_off[s2[p]]);
             total = std::max(total, out_off[p] + cap);
@@ -974,7 +1054,7 @@ extern "C" poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, con
     const size_t al_total = ((size_t)total + 255) & ~(size_t)255;
     void *v_out;
     const size_t need = sizeof(int64_t) * (size_t)n + sizeof(int32_t) * 3 * (size_t)n + al_total * 2 + 1024;
-    poy_status s = scratch(ctx, SL_JOBS2, need, &v_out);
+    poy_status s = poy_scratch(ctx, SL_JOBS2, need, &v_out);
     if (s != POY_OK) return s;
     uint8_t *cur = (uint8_t *)v_out;
     int64_t *d_out_off = (int64_t *)cur; cur += sizeof(int64_t) * (size_t)n;
@@ -1011,13 +1091,13 @@ poy_status stage_rows(poy_ctx *ctx, int n, const uint8_t *rows_a, const uint8_t 
                       const int64_t *out_off, int extra, RowsOnDevice *r) {
     r->total = 0; r->out_total = 0;
     for (int p = 0; p < n; ++p) {
-        if (off[p] < 0 || len[p] < 0) return fail(ctx, POY_ERR_ARG, "negative offset or length");
+        if (off[p] < 0 || len[p] < 0) return poy_fail(ctx, POY_ERR_ARG, "negative offset or length");
         r->total = std::max(r->total, off[p] + len[p]);
         if (out_off) r->out_total = std::max(r->out_total, out_off[p] + len[p] + extra);
     }
     const size_t A = ((size_t)r->total + 255) & ~(size_t)255, O = ((size_t)r->out_total + 255) & ~(size_t)255;
     void *v;
-    poy_status s = scratch(ctx, SL_JOBS2, 2 * A + O + (size_t)n * (8 + 8 + 4 + 4) + 2048, &v);
+    poy_status s = poy_scratch(ctx, SL_JOBS2, 2 * A + O + (size_t)n * (8 + 8 + 4 + 4) + 2048, &v);
     if (s != POY_OK) return s;
     uint8_t *cur = (uint8_t *)v;
     r->a = cur; cur += A; r->b = cur; cur += A; r->out = cur; cur += O;
@@ -1108,7 +1188,7 @@ extern "C" poy_status poy_batch_ancestor_2(poy_ctx *ctx, const poy_cm *cm, int32
     CK(cudaMemcpyAsync(out, r.out, (size_t)r.out_total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(out_len, r.res, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int p = 0; p < n; ++p) if (out_len[p] < 0) return fail(ctx, POY_ERR_ARG, "median should not be 0");
+    for (int p = 0; p < n; ++p) if (out_len[p] < 0) return poy_fail(ctx, POY_ERR_ARG, "median should not be 0");
     return POY_OK;
 }
 
@@ -1117,7 +1197,7 @@ extern "C" poy_status poy_microbench_int(poy_ctx *ctx, int32_t kind, double *ops
     bind_device(ctx);
     if (!ctx || !ops_per_second) return POY_ERR_ARG;
     void *v;
-    poy_status s = scratch(ctx, SL_MISC, 1 << 20, &v);
+    poy_status s = poy_scratch(ctx, SL_MISC, 1 << 20, &v);
     if (s != POY_OK) return s;
     float ms = 0;
     double ops = 0;

@@ -86,12 +86,48 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
     }
 }
 
-cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool) {
-    if (pool->nseq == 0) return cudaSuccess;
-    int blocks = (pool->nseq + 3) / 4;
+// sequences [s0, s1) of the pool (the node store appends sequences and only the new ones need parameters)
+cudaError_t launch_params(poy_ctx *ctx, const poy_cm *cm, poy_pool *pool, int s0, int s1) {
+    const int n = s1 - s0;
+    if (n <= 0) return cudaSuccess;
+    int blocks = (n + 3) / 4;
     if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-    k_params<<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_data, pool->d_off, pool->nseq, pool->d_rowp, pool->d_rowpk, pool->d_colp,
-                                               pool->d_h0, pool->d_g0, pool->d_gapfree);
+    k_params<<<blocks, 128, 0, ctx->stream>>>(cm->d, pool->d_data, pool->d_off + s0, n, pool->d_rowp, pool->d_rowpk, pool->d_colp,
+                                               pool->d_h0, pool->d_g0, pool->d_gapfree + s0);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+// Sequence.is_empty (src/sequence.ml:241-251: every symbol equals the gap code) and Sequence.count_gaps (symbols that
+// carry the gap bit, seq_CAML_count, src/seq.c:644-669) per sequence, from the device bytes: x = empty, y = gap count.
+__global__ void __launch_bounds__(128) k_seq_flags(const uint8_t *__restrict__ data, const int64_t *__restrict__ off, int nseq,
+                                                   int2 *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int s = blockIdx.x * warps_per_block + (threadIdx.x >> 5); s < nseq; s += gridDim.x * warps_per_block) {
+        const int64_t base = off[s];
+        const int len = (int)(off[s + 1] - base);
+        int nongap = 0, gapbit = 0;
+        for (int x = lane; x < len; x += 32) {
+            const int code = data[base + x];
+            nongap += code != POY_GAP;
+            gapbit += (code & POY_GAP) != 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            nongap += __shfl_xor_sync(0xffffffffu, nongap, d);
+            gapbit += __shfl_xor_sync(0xffffffffu, gapbit, d);
+        }
+        if (lane == 0) flags[s] = make_int2(nongap == 0, gapbit);
+    }
+}
+
+cudaError_t launch_seq_flags(poy_ctx *ctx, const poy_pool *pool, int s0, int s1, int2 *d_flags) {
+    const int n = s1 - s0;
+    if (n <= 0) return cudaSuccess;
+    int blocks = (n + 3) / 4;
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    k_seq_flags<<<blocks, 128, 0, ctx->stream>>>(pool->d_data, pool->d_off + s0, n, d_flags);
     ctx->launches++;
     return cudaGetLastError();
 }

@@ -77,6 +77,83 @@ class GpuBackend:
         return [int(x) for x in d]
 
 
+class Node:
+    """Handle of a sequence that lives in the device-resident node store: id + length (what the drivers need on the
+    host: `len(x)` for work estimates, identity for bookkeeping)."""
+    __slots__ = ("id", "n")
+
+    def __init__(self, id_, n):
+        self.id, self.n = int(id_), int(n)
+
+    def __len__(self):
+        return self.n
+
+    def __repr__(self):
+        return "Node(%d, len %d)" % (self.id, self.n)
+
+
+class StoreBackend:
+    """The product path of a tree pass: every sequence is a `Node` handle into ONE device-resident store
+    (poy_store, csrc/store.cu); `median` appends its results in HBM and returns handles, `distance` runs the cost-only
+    batch on ids.  Nothing but ids, lengths and costs crosses PCIe.  `mark()` / `release(mark)` give the drivers
+    stack discipline for the temporaries of a chunk of candidates."""
+
+    def __init__(self, ctx, h, cap_bytes=1 << 26, cap_seqs=1 << 16):
+        from .api import Store
+        self.ctx, self.h = ctx, h
+        self.store = Store(ctx, cap_bytes, cap_seqs)
+        self.n_median = self.n_distance = 0
+        self.cells_distance = 0
+
+    def put(self, seqs):
+        ids = self.store.append(seqs)
+        return [Node(i, len(s)) for i, s in zip(ids, seqs)]
+
+    def fetch(self, nodes):
+        return self.store.read(np.fromiter((x.id for x in nodes), np.int32, len(nodes)))
+
+    def mark(self):
+        return len(self.store)
+
+    def release(self, mark):
+        self.store.truncate(mark)
+
+    def median(self, pairs):
+        if not pairs:
+            return []
+        n = len(pairs)
+        a = np.fromiter((p[0].id for p in pairs), np.int32, n); b = np.fromiter((p[1].id for p in pairs), np.int32, n)
+        ids, ln, c2 = self.store.median(self.h, a, b)
+        self.n_median += n
+        return [(Node(i, l), c) for i, l, c in zip(ids.tolist(), ln.tolist(), c2.tolist())]
+
+    def distance(self, pairs):
+        if not pairs:
+            return []
+        n = len(pairs)
+        a = np.fromiter((p[0].id for p in pairs), np.int32, n); b = np.fromiter((p[1].id for p in pairs), np.int32, n)
+        la = np.fromiter((p[0].n for p in pairs), np.int64, n); lb = np.fromiter((p[1].n for p in pairs), np.int64, n)
+        self.cells_distance += int(((la - 1) * (lb - 1)).sum())
+        self.n_distance += n
+        return self.store.distance(self.h, a, b).tolist()
+
+    def single(self, pairs):
+        """to_single is an O(n) pass per tree: sequences go through the host-array path (seqcs.to_single)"""
+        from .api import Pool
+        from .seqcs import to_single
+        if not pairs:
+            return []
+        flat = self.fetch([x for p in pairs for x in p])
+        pool = Pool(self.ctx, flat)
+        n = len(pairs)
+        seqs, cost = to_single(self.ctx, self.h, pool, np.arange(0, 2 * n, 2, dtype=np.int32), np.arange(1, 2 * n, 2, dtype=np.int32))
+        pool.close()
+        return [(x, int(c)) for x, c in zip(self.put([np.array(s_, np.uint8) for s_ in seqs]), cost)]
+
+    def close(self):
+        self.store.close()
+
+
 class Tree:
     """Unrooted binary tree: leaves 0..n-1 hold observed sequences, internal nodes are created on insertion."""
 
@@ -412,7 +489,7 @@ def spr_prunings(tree, n_leaves):
     return out
 
 
-def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64):
+def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None):
     """One SPR neighbourhood over several loci.  For the pruning (u, v) the rest tree is u's side with u suppressed
     (its neighbours x1, x2 joined); only the medians that *see* the cut are recomputed, top-down from the cut:
 
@@ -424,7 +501,8 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64):
     the Parmap candidate seam of src/ptree.ml:1356-1453 evaluates.  All prunings of a chunk and all loci advance
     in lockstep: one median batch per level, one edge-median batch, ONE distance batch per chunk; the estimate of
     a candidate is the sum over loci.  Returns (best estimate, (pruning, join edge), number of candidates,
-    number of alignments issued); ties resolve to the first candidate in enumeration order."""
+    number of alignments issued); ties resolve to the first candidate in enumeration order.  `where` (a list) receives
+    (index of the winning pruning in `prunings`, index of the join edge within that pruning)."""
     n = len(loci[0])
     dms = all_directions(tree, loci, backend) if dms is None else dms
     prunings = spr_prunings(tree, n) if prunings is None else list(prunings)
@@ -432,6 +510,7 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64):
     best, ncand, naln = None, 0, 0
     for c0 in range(0, len(prunings), chunk):
         part = prunings[c0:c0 + chunk]
+        mark = backend.mark() if hasattr(backend, "mark") else None     # node store: the chunk's medians are temporaries
         ups, levels, joins = [], [], []       # per pruning: up[l][node]; nodes by depth; join edges (a, c)
         for (u, v) in part:
             x1, x2, lv, par = _side_plan(tree, u, v)
@@ -465,18 +544,64 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64):
                 for l in range(nl):
                     em = ems[(k, l, a, c)]
                     cand.append((dms[l][(v, u)][0], em[0])); base += em[1] + dms[l][(v, u)][1]
-                meta.append(((u, v), (a, c), base))
+                meta.append(((u, v), (a, c), base, (c0 + k, len(meta))))
         naln += len(cand)
         d = np.asarray(backend.distance(cand), np.int64).reshape(len(meta), nl).sum(axis=1)
         est = d + np.array([m[2] for m in meta], np.int64)
         if len(est):
             q = int(np.argmin(est))
             if best is None or int(est[q]) < best[0]:
-                best = (int(est[q]), meta[q][0], meta[q][1], ncand + q)
+                best = (int(est[q]), meta[q][0], meta[q][1], ncand + q, meta[q][3])
         ncand += len(meta)
+        if mark is not None:
+            backend.release(mark)
+    if where is not None:
+        where.append(None if best is None else best[4])
     if best is None:
         return None, None, 0, naln
     return best[0], (best[1], best[2]), ncand, naln
+
+
+def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, world=1, device=None):
+    """One SPR neighbourhood strong-scaled over `world` ranks (the Parmap / MPI seam of src/ptree.ml:1356-1408,
+    src/allDirChar.ml:2132-2177): the PRUNINGS are dealt to the ranks by estimated work (LPT on the size of the rest
+    tree), so every candidate of a pruning -- all its join edges, all loci -- is evaluated on one GPU and the
+    incremental medians it needs are computed where they are used; node sequences and the all-direction medians of the
+    unbroken tree are replicated.  The only exchange is the reduction of the best candidate: one MIN all-reduce of the
+    estimate, one of the (pruning, join edge) ordinal among the ranks that hold it (ties resolve to the first candidate
+    in the global enumeration order, whatever the rank count), plus one SUM for the counters.
+    Returns (best estimate, (pruning, join edge), candidates, alignments) -- identical on every rank and for every N."""
+    from . import shard
+    prunings = list(prunings)
+    if world == 1:
+        return spr_round(tree, loci, backend, dms=dms, prunings=prunings, chunk=chunk)
+    import torch
+    import torch.distributed as dist
+    work = [len(tree.component(u, v)) for (u, v) in prunings]
+    mine = shard.lpt_partition(work, world)[rank]
+    where = []
+    est, move, ncand, naln = spr_round(tree, loci, backend, dms=dms, prunings=[prunings[i] for i in mine], chunk=chunk, where=where)
+    big = (1 << 62)
+    t = torch.tensor([big if est is None else int(est)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    gmin = int(t.item())
+    if gmin == big:
+        return None, None, 0, 0
+    mine_ord = big
+    if est is not None and int(est) == gmin:
+        pi, ji = where[0]
+        mine_ord = (int(mine[pi]) << 24) | ji            # join edges per pruning < 2^24
+    o = torch.tensor([mine_ord], dtype=torch.int64, device=device)
+    dist.all_reduce(o, op=dist.ReduceOp.MIN)
+    gord = int(o.item())
+    cnt = torch.tensor([ncand, naln], dtype=torch.int64, device=device)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    # the winner's move is recomputed from the ordinal on every rank (host-only tree walk, no communication)
+    gp, gj = gord >> 24, gord & ((1 << 24) - 1)
+    u, v = prunings[gp]
+    _, _, lv, par = _side_plan(tree, u, v)
+    joins = [(par[c][0], c) for l_ in lv for c in l_]
+    return gmin, ((u, v), joins[gj]), int(cnt[0].item()), int(cnt[1].item())
 
 
 def apply_spr(tree, move):

@@ -63,3 +63,19 @@ class OracleBackend:
                                   (lambda x, y: self._lin(self.pf, x, y, None)) if not self.affine else None)
             out.append((s, int(c)))
         return out
+
+
+def replay_sample(med, dis, regime):
+    """CPU checker replay of a recorded sample of the swap-evaluation workload (poy5_b200.swap_eval.SampleRecorder):
+    med = [(a, b, median, cost2)], dis = [(a, b, cost)] as host arrays.  -> parity dict"""
+    from oracle import cost_matrix_oracle as cmo
+    from oracle.port import Port
+    full, orig = cmo.dna_matrices(*regime)
+    ob = OracleBackend(Port(), full, orig)
+    bad = 0
+    for (a, b, m, c), (om, oc) in zip(med, ob.median([(a, b) for a, b, _, _ in med])):
+        bad += not (np.array_equal(m, om) and c == oc)
+    for (a, b, c), oc in zip(dis, ob.distance([(a, b) for a, b, _ in dis])):
+        bad += int(c != oc)
+    return dict(checked=len(med) + len(dis), checked_medians=len(med), checked_distances=len(dis), mismatches=int(bad),
+                against="oracle port (plain-C restatement of algn.c, pinned to the compiled reference)")

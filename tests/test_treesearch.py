@@ -164,6 +164,80 @@ def test_sharded_spr_and_medians_gloo(port):
         assert (r[1], r[2]) == (single[1:6], single[7])
 
 
+# ---- SPR neighbourhood strong-scaled by pruning (the swap-evaluation workload of bench.py) ----
+
+def _spr_sharded_worker(rank, world, port_no, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.port import Port
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    b = OracleBackend(Port(), full, orig)
+    loci = loci_taxa(9, 7, (40, 55))
+    tree = treesearch.wagner_build(loci[0], b)
+    dms = treesearch.all_directions(tree, loci, b)
+    pr = treesearch.spr_prunings(tree, 7)
+    r = treesearch.spr_round_sharded(tree, loci, b, dms, pr, chunk=3, rank=rank, world=world)
+    q.put((rank, r))
+    dist.destroy_process_group()
+
+
+def test_spr_sharded_by_pruning_gloo(port):
+    """world_size 2 over gloo: prunings dealt to the ranks, best candidate reduced with MIN all-reduces; every rank
+    must report exactly what the single-process round reports (estimate, move, counters)"""
+    world = 2
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    pn = 33700 + os.getpid() % 2000
+    procs = [ctxm.Process(target=_spr_sharded_worker, args=(r, world, pn, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    b = OracleBackend(port, full, orig)
+    loci = loci_taxa(9, 7, (40, 55))
+    tree = treesearch.wagner_build(loci[0], b)
+    single = treesearch.spr_round(tree, loci, b, chunk=1000)
+    for _, r in res:
+        assert r == single
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("go", [3, None])
+def test_store_backend_matches_oracle_replay(ctx, port, go):
+    """device-resident node store: the whole SPR replay (Wagner build, downpass, SPR round with released temporaries,
+    exact rejoin) through StoreBackend handles equals the CPU checker's replay; sampled medians equal byte for byte"""
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.seqcs import Heuristic
+    t2d = Two_D.of_transformations_and_gaps(1, 1, go)
+    full, orig = cmo.dna_matrices(1, 1, go)
+    h = Heuristic(pb.CostModel(ctx, t2d.full), pb.CostModel(ctx, t2d.original))
+    host_loci = loci_taxa(23, 8, (120, 90, 150))
+    sb = treesearch.StoreBackend(ctx, h, cap_bytes=1 << 16, cap_seqs=64)        # tiny: exercises the store's growth
+    loci = [sb.put(ls) for ls in host_loci]
+    got = run_spr(sb, loci)
+    ref = run_spr(OracleBackend(port, full, orig), host_loci)
+    assert got == ref
+    ob = OracleBackend(port, full, orig)
+    pairs = [(loci[0][0], loci[0][1]), (loci[1][2], loci[1][5]), (loci[2][7], loci[2][3])]
+    res = sb.median(pairs)
+    exp = ob.median([(host_loci[0][0], host_loci[0][1]), (host_loci[1][2], host_loci[1][5]), (host_loci[2][7], host_loci[2][3])])
+    for (node, c2), (seq, oc), fetched in zip(res, exp, sb.fetch([r_[0] for r_ in res])):
+        assert c2 == oc and len(node) == len(seq) and np.array_equal(fetched, seq)
+    # medians of medians (inputs that never left the device), and an empty child
+    empty = sb.put([np.array([16], np.uint8)])[0]
+    res2 = sb.median([(res[0][0], res[1][0]), (empty, res[2][0]), (res[1][0], empty)])
+    exp2 = ob.median([(exp[0][0], exp[1][0]), (np.array([16], np.uint8), exp[2][0]), (exp[1][0], np.array([16], np.uint8))])
+    for (node, c2), (seq, oc), fetched in zip(res2, exp2, sb.fetch([r_[0] for r_ in res2])):
+        assert c2 == oc and np.array_equal(fetched, seq)
+    assert sb.distance([(res2[0][0], loci[0][4]), (empty, loci[0][1])]) == ob.distance([(exp2[0][0], host_loci[0][4]), (np.array([16], np.uint8), host_loci[0][1])])
+    sb.close()
+
+
 # ---- TBR round over several loci with incremental medians ----
 
 def run_tbr_multi(backend, loci, chunk=3):
