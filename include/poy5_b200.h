@@ -162,6 +162,21 @@ POY_API poy_status poy_batch_align_linear(poy_ctx *ctx, const poy_cm *cm, const 
                                           const uint8_t *swaped, const int64_t *out_off, int32_t *cost, uint8_t *r1,
                                           uint8_t *r2, int32_t *out_len, int32_t *stats);
 
+/* ---- batch twin of Sequence.NewkkAlign (src/sequence.ml:1831-2062): newkkonen_CAML_algn_affine +
+ * newkkonen_CAML_backtrace_affine (src/newkkonen.c:1472-1495, 1787-1803) ------------------------------------------
+ * The diagonal-storage Ukkonen alignment with the gap-count stop rule (newkk_algn / increaseT / ukktest /
+ * update_internal_cell, src/newkkonen.c:1360-1444, 1155-1171, 1077-1153, 680-870), affine model only: the reference's
+ * non-affine entry point never sets costDiag (:796, :855-856), returns cost 0 and its traceback raises -> POY_ERR_MODEL.
+ * s1[p] must be the shorter sequence (POY_ERR_ORDER = "newkkonen.newkk_algn, s1 len > s2 len"); swaped[p] is what
+ * NewkkAlign.align_2 passes (1 if it exchanged the operands).  r1 / r2 receive the two aligned rows of
+ * backtrace_affine, pair p RIGHT-justified in the slot [out_off[p], out_off[p] + len1 + len2) (get_alignment
+ * allocates sz1 + sz2, src/sequence.ml:1862-1877), out_len[2*p + {0,1}] = their lengths.  r1 == NULL: cost only
+ * (NewkkAlign.cost_2).  stats (optional, n x 4): threshold doublings, 0, final k (newkkonen_CAML_get_k), 1 if the
+ * pair took the trivial path (len1 * 100 < len2, trivial_algn :1351-1356).  All arrays are HOST pointers. */
+POY_API poy_status poy_batch_newkk_align(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, int32_t n, const int32_t *s1,
+                                         const int32_t *s2, const uint8_t *swaped, const int64_t *out_off, int32_t *cost,
+                                         uint8_t *r1, uint8_t *r2, int32_t *out_len, int32_t *stats);
+
 /* ---- column-wise helpers over ALIGNED rows (O(L) per pair) ---------------------------------
  * rows_a / rows_b are packed byte buffers; pair p uses rows_x[off[p] .. off[p] + len[p]).
  *  poy_batch_median_2     seq_CAML_median_2_with_gaps / _no_gaps (src/seq.c:241-296): out slot of pair p

@@ -13,9 +13,9 @@ INT_MIN = -2**31
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "do_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-o", _SO, src, "-lpthread"])
+    srcs = [os.path.join(_HERE, f) for f in ("do_oracle.c", "newkk_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(x) for x in srcs):
+        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-fPIC", "-shared", "-o", _SO] + srcs + ["-lpthread"])
     return _SO
 
 
@@ -48,6 +48,7 @@ class Port:
         L.do_worst_2.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int]
         L.do_verify_2.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int]
         L.do_ancestor_2.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, _u8p]
+        L.do_newkk_align_affine.argtypes = [C.c_void_p, _u8p, C.c_int, _u8p, C.c_int, C.c_int, _u8p, _u8p, _i32p, C.POINTER(AlignStats)]
         self.lin = L.do_lin_scratch_new()
         self.scratch = L.do_scratch_new()
 
@@ -91,6 +92,21 @@ class Port:
                                      off_j.ctypes.data_as(i64p), len_j.ctypes.data_as(_i32p),
                                      None if sw is None else _p8(sw), cost.ctypes.data_as(_i32p), int(nthreads))
         return t, cost
+
+    # -- Sequence.NewkkAlign, affine (src/newkkonen.c) ------------------------------------------
+    def newkk_align(self, cm, s1, s2, swaped=0, with_stats=False):
+        """newkkonen_CAML_algn_affine + newkkonen_CAML_backtrace_affine; s1 must be the shorter sequence.
+        -> (cost, aligned s1, aligned s2[, stats])"""
+        s1 = np.ascontiguousarray(s1, np.uint8); s2 = np.ascontiguousarray(s2, np.uint8)
+        cap = len(s1) + len(s2) + 2
+        o1 = np.zeros(cap, np.uint8); o2 = np.zeros(cap, np.uint8)
+        lens = (C.c_int * 2)()
+        st = AlignStats()
+        r = self.lib.do_newkk_align_affine(cm, _p8(s1), len(s1), _p8(s2), len(s2), int(swaped), _p8(o1), _p8(o2), lens, C.byref(st))
+        if r == INT_MIN:
+            raise RuntimeError("newkkonen: pass the shorter one as first / invalid dir")
+        res = (r, o1[:lens[0]].copy(), o2[:lens[1]].copy())
+        return res + (st,) if with_stats else res
 
     # -- linear gap ---------------------------------------------------------------------------
     def cost_linear(self, cm, s1, s2, deltawh, with_stats=False):

@@ -66,7 +66,9 @@ value seq_CAML_median_2_with_gaps(value s1, value s2, value m, value sm);
 int cm_get_min_non0_cost(cmt c);
 
 /* ---- failwith -> error code -------------------------------------------- */
-static __thread jmp_buf *ref_jmp = NULL;
+/* shared with ref_newkk_driver.c (same shared object) */
+__thread jmp_buf *ref_jmp_shared = NULL;
+#define ref_jmp ref_jmp_shared
 static __thread char ref_errmsg[512];
 
 void caml_failwith(const char *msg) {

@@ -51,6 +51,14 @@ class RefLib:
         L.ref_batch_affine.restype = C.c_double
         L.ref_batch_affine.argtypes = [C.c_void_p, C.c_int, C.c_int, _u8p, _i64p, _i32p, _i64p, _i32p, _u8p,
                                        _i32p, C.c_int]
+        if hasattr(L, "ref_newkk_new"):
+            L.ref_newkk_new.restype = C.c_void_p
+            L.ref_newkk_free.argtypes = [C.c_void_p]
+            L.ref_newkk_get_k.argtypes = [C.c_void_p]
+            L.ref_newkk_cost.argtypes = [C.c_void_p, C.c_void_p, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
+            L.ref_newkk_align.argtypes = [C.c_void_p, C.c_void_p, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _i32p]
+            L.ref_powell_3d.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _i32p]
+            self.ukkm = L.ref_newkk_new()
         self.mat = L.ref_mat_new()
         L.ref_mat_reserve(self.mat, 64, 64)
 
@@ -138,6 +146,44 @@ class RefLib:
     def verify_2(self, cm, a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         return self.lib.ref_verify_2(cm, _p8(a), _p8(b), len(a))
+
+    # -- Sequence.NewkkAlign (src/newkkonen.c) ---------------------------------------
+    def newkk_fresh(self):
+        """a new, never used newkkmat scratch (the reference's is process global: NewkkAlign.default_ukkm)"""
+        self.lib.ref_newkk_free(self.ukkm)
+        self.ukkm = self.lib.ref_newkk_new()
+
+    def newkk_align(self, cm, s1, s2, affine, swaped=0):
+        """-> (cost, aligned s1, aligned s2, final k); requires len(s1) <= len(s2)"""
+        s1 = np.ascontiguousarray(s1, np.uint8); s2 = np.ascontiguousarray(s2, np.uint8)
+        cap = len(s1) + len(s2) + 2
+        outs = [np.zeros(cap, np.uint8) for _ in range(2)]
+        lens = (C.c_int * 2)()
+        r = self.lib.ref_newkk_align(cm, self.ukkm, _p8(s1), len(s1), _p8(s2), len(s2), int(affine), int(swaped),
+                                     _p8(outs[0]), _p8(outs[1]), lens)
+        if r == REF_FAIL:
+            raise self._err()
+        return (r,) + tuple(o[:n].copy() for o, n in zip(outs, lens)) + (self.lib.ref_newkk_get_k(self.ukkm),)
+
+    def newkk_cost(self, cm, s1, s2, affine, swaped=0):
+        s1 = np.ascontiguousarray(s1, np.uint8); s2 = np.ascontiguousarray(s2, np.uint8)
+        r = self.lib.ref_newkk_cost(cm, self.ukkm, _p8(s1), len(s1), _p8(s2), len(s2), int(affine), int(swaped))
+        if r == REF_FAIL:
+            raise self._err()
+        return r
+
+    # -- powell_3D_align (src/ukkCommon.c:109) ------------------------------------------
+    def powell_3d(self, s1, s2, s3, mm, go, ge):
+        """inputs WITHOUT the leading gap; -> (cost, row1, row2, row3)"""
+        ss = [np.ascontiguousarray(x, np.uint8) for x in (s1, s2, s3)]
+        cap = sum(len(x) for x in ss) + 3
+        outs = [np.zeros(cap, np.uint8) for _ in range(3)]
+        lens = (C.c_int * 3)()
+        r = self.lib.ref_powell_3d(_p8(ss[0]), len(ss[0]), _p8(ss[1]), len(ss[1]), _p8(ss[2]), len(ss[2]), int(mm), int(go), int(ge),
+                                   _p8(outs[0]), _p8(outs[1]), _p8(outs[2]), lens)
+        if r == REF_FAIL:
+            raise self._err()
+        return (r,) + tuple(o[:n].copy() for o, n in zip(outs, lens))
 
     # -- threaded batch (CPU baseline) ---------------------------------------------
     def batch_affine(self, cm, mode, seqs, off_i, len_i, off_j, len_j, swaped=None, nthreads=1):

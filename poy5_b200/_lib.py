@@ -92,6 +92,7 @@ def load():
     L.poy_store_read.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
     L.poy_store_median.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.poy_store_distance.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp]
+    L.poy_batch_newkk_align.argtypes = [vp, vp, vp, C.c_int32] + [vp] * 9
     L.poy_microbench_int.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _LIB = L
     return L
@@ -105,4 +106,4 @@ EXPORTS = ["poy_ctx_create", "poy_ctx_destroy", "poy_last_error", "poy_status_st
            "poy_batch_aligned_cost", "poy_batch_ancestor_2", "poy_batch_closest", "poy_dos_distance", "poy_dos_median", "poy_dos_median2",
            "poy_store_create", "poy_store_free", "poy_store_pool", "poy_store_count", "poy_store_bytes", "poy_store_append",
            "poy_store_truncate", "poy_store_lengths", "poy_store_read", "poy_store_median", "poy_store_distance",
-           "poy_microbench_int"]
+           "poy_batch_newkk_align", "poy_microbench_int"]

@@ -85,14 +85,19 @@ struct poy_ctx {
     uint64_t launches;
     char err[512];
     // grow-only device scratch
-    void *d_scratch[12];
-    size_t scratch_cap[12];
+    void *d_scratch[14];
+    size_t scratch_cap[14];
     void *h_pinned[6];
     size_t pinned_cap[6];
     // auxiliary streams + events: independent launches of one wave run concurrently so that the tail of one
     // overlaps the body of the next
     cudaStream_t aux[4];
     cudaEvent_t ev_fork, ev_join[4];
+    // traceback lane: the traceback of the pairs that stopped in round r runs on its own stream while round r+1 is
+    // being filled (two direction arenas / job arrays in turn); ev_tb_done[p] guards the reuse of arena p
+    cudaStream_t tb_stream;
+    cudaEvent_t ev_fin, ev_tb_done[2];
+    bool tb_pending[2];
     // small cache of device blocks released by freed pools: tree-search drivers create and destroy thousands of
     // short-lived pools, and cudaMalloc / cudaFree (a device-wide sync) would dominate their batches
     void *cache_ptr[64];
@@ -145,7 +150,7 @@ struct PairState {        // survives across band fills of the same pair
 // ---- host-side helpers shared by host.cu / dos.cu / store.cu -------------------------------------------------------
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return poy_cuda_fail(ctx, e_, #call); } while (0)
 enum { SL_JOBS = 0, SL_JOBS2 = 1, SL_BOUND = 2, SL_STATE = 3, SL_EBROW = 4, SL_DIR = 5, SL_MISC = 6, SL_WORK = 7,
-       SL_STORE = 8, SL_STORE2 = 9, SL_COUNT = 10 };
+       SL_STORE = 8, SL_STORE2 = 9, SL_DIR2 = 10, SL_JOBSB = 11, SL_COUNT = 12 };
 poy_status poy_fail(poy_ctx *ctx, poy_status s, const char *msg);
 poy_status poy_cuda_fail(poy_ctx *ctx, cudaError_t e, const char *where);
 poy_status poy_scratch(poy_ctx *ctx, int slot, size_t bytes, void **out);     // grow-only device scratch slot

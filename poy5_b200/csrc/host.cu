@@ -64,6 +64,10 @@ extern "C" poy_status poy_ctx_create(int device, void *stream, poy_ctx **out) {
         cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->tb_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fin, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_tb_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_tb_done[1], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_twin_start, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_twin_done, cudaEventDisableTiming);
     {   // direction arena: up to 40% of the free HBM, at most 64 GiB
@@ -86,7 +90,9 @@ extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->twin) { poy_ctx_destroy(ctx->twin); ctx->twin = nullptr; }
     cudaEventDestroy(ctx->ev_twin_start); cudaEventDestroy(ctx->ev_twin_done);
-    for (int s = 0; s < 12; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
+    cudaStreamSynchronize(ctx->tb_stream);
+    cudaStreamDestroy(ctx->tb_stream); cudaEventDestroy(ctx->ev_fin); cudaEventDestroy(ctx->ev_tb_done[0]); cudaEventDestroy(ctx->ev_tb_done[1]);
+    for (int s = 0; s < 14; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
     for (int i = 0; i < ctx->cache_n; ++i) cudaFree(ctx->cache_ptr[i]);
     for (int s = 0; s < 6; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
     for (int a = 0; a < 4; ++a) { cudaStreamDestroy(ctx->aux[a]); cudaEventDestroy(ctx->ev_join[a]); }
@@ -677,18 +683,25 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         }
     }
 
-    void *v_state, *v_eb, *v_jobs, *v_misc, *v_pin, *v_pin2;
-    if ((s = poy_scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + (size_t)n, &v_state)) != POY_OK) return s;
+    void *v_state, *v_eb, *v_jobs, *v_jobs_b, *v_misc, *v_pin, *v_pin2;
+    if ((s = poy_scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + 3 * (size_t)n, &v_state)) != POY_OK) return s;
     if ((s = poy_scratch(ctx, SL_EBROW, sizeof(int) * 2 * (size_t)eb_total + 16, &v_eb)) != POY_OK) return s;   // rows + their snapshots
     if ((s = poy_scratch(ctx, SL_JOBS, sizeof(BandJob) * (size_t)n, &v_jobs)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_JOBSB, sizeof(BandJob) * (size_t)n, &v_jobs_b)) != POY_OK) return s;
     if ((s = poy_scratch(ctx, SL_MISC, 256, &v_misc)) != POY_OK) return s;
     if ((s = poy_pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (size_t)n, &v_pin)) != POY_OK) return s;
     if ((s = poy_pinned(ctx, 1, (size_t)n + sizeof(int32_t) * (size_t)n, &v_pin2)) != POY_OK) return s;
     PairState *d_state = (PairState *)v_state;
     uint8_t *d_done = (uint8_t *)(d_state + n);
+    // the verdicts as the traceback of a round must see them: the next round's stop rule overwrites d_done while the
+    // traceback of this one may still be running
+    uint8_t *d_done_tb[2] = { d_done + n, d_done + 2 * (size_t)n };
     int *d_eb = (int *)v_eb, *d_eb_snap = d_eb + eb_total;
-    BandJob *d_jobs = (BandJob *)v_jobs;
+    BandJob *d_jobs_ab[2] = { (BandJob *)v_jobs, (BandJob *)v_jobs_b };
     int *d_counter = (int *)v_misc;
+    // POY_ASYNC_TB=0: the traceback of a round is waited for before the next round starts (test hook)
+    const char *atb = getenv("POY_ASYNC_TB");
+    const bool async_tb = !(atb && atb[0] == '0');
     uint8_t *h_done = (uint8_t *)v_pin2;
 
     {   // initial per-pair state: EH[0][0] = go, EB row 0 = INF (initialize_matrices_affine, src/algn.c:1875-1898)
@@ -778,8 +791,19 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 used += need;
                 ++end;
             }
+            // Rounds that fit the arena in one wave alternate between two arenas / job arrays, so that the traceback
+            // of the pairs that stop in this round (own stream) overlaps the fills of the next one.
+            const bool single_wave = async_tb && pos == 0 && end == order.size();
+            const int par = single_wave ? (rounds & 1) : 0;
+            if (!single_wave) {
+                for (int q = 0; q < 2; ++q)
+                    if (ctx->tb_pending[q]) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb_done[q], 0)); ctx->tb_pending[q] = false; }
+            } else if (ctx->tb_pending[par]) {
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb_done[par], 0)); ctx->tb_pending[par] = false;
+            }
+            BandJob *d_jobs = d_jobs_ab[par];
             void *v_dir;
-            if ((s = poy_scratch(ctx, SL_DIR, (size_t)used, &v_dir)) != POY_OK) return s;
+            if ((s = poy_scratch(ctx, par ? SL_DIR2 : SL_DIR, (size_t)used, &v_dir)) != POY_OK) return s;
             uint8_t *d_dir = (uint8_t *)v_dir;
             BandJob *hj = (BandJob *)v_pin;
             const int nj = (int)(end - pos);
@@ -844,9 +868,21 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             if (linear) CK(launch_lin_finish(ctx, pool, d_jobs, nj, d_state, d_done));
             else CK(launch_band_finish(ctx, d_jobs, nj, d_state, d_done, pool->d_g0, cm->h.gap_open));
             if (want_trace) {
-                if (linear) CK(launch_traceback_lin(ctx, pool, d_jobs, nj, d_done, d_dir, d_out_off, d_resi, d_resj, d_out_len));
-                else CK(launch_traceback(ctx, cm, pool, d_jobs, nj, d_done, d_dir, d_out_off, d_median, d_medianwg, d_resi,
-                                         d_resj, d_out_len));
+                const uint8_t *tb_done = d_done;
+                if (single_wave) {
+                    CK(cudaMemcpyAsync(d_done_tb[par], d_done, (size_t)n, cudaMemcpyDeviceToDevice, main_stream));
+                    tb_done = d_done_tb[par];
+                    CK(cudaEventRecord(ctx->ev_fin, main_stream));
+                    CK(cudaStreamWaitEvent(ctx->tb_stream, ctx->ev_fin, 0));
+                    ctx->stream = ctx->tb_stream;
+                }
+                cudaError_t te;
+                if (linear) te = launch_traceback_lin(ctx, pool, d_jobs, nj, tb_done, d_dir, d_out_off, d_resi, d_resj, d_out_len);
+                else te = launch_traceback(ctx, cm, pool, d_jobs, nj, tb_done, d_dir, d_out_off, d_median, d_medianwg, d_resi,
+                                           d_resj, d_out_len);
+                ctx->stream = main_stream;
+                if (te != cudaSuccess) return poy_cuda_fail(ctx, te, "traceback launch");
+                if (single_wave) { CK(cudaEventRecord(ctx->ev_tb_done[par], ctx->tb_stream)); ctx->tb_pending[par] = true; }
             }
             { const double t = now(); t_prep += t - t_mark; t_mark = t; }
             CK(cudaStreamSynchronize(ctx->stream));  // the pinned job staging and the arena are reused by the next wave
@@ -875,6 +911,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         }
         active.swap(next);
     }
+    for (int q = 0; q < 2; ++q)      // the caller's stream order must see the traced-back outputs
+        if (ctx->tb_pending[q]) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tb_done[q], 0)); ctx->tb_pending[q] = false; }
     if (d_cost) {
         CK(launch_gather_cost(ctx, d_state, n, d_cost));
     }

@@ -328,3 +328,57 @@ def readjust(ctx, cm, pool, a, b, parent):
     cost = r["cost"].astype(np.int64)
     cost2 = cost[:n] + cost[n:2 * n]
     return {"cost3": cost2 + cost[2 * n:], "cost2": cost2, "sequence": list(new), "aligned_mp": r["res_b"][2 * n:]}
+
+
+class NewkkAlign:
+    """Sequence.NewkkAlign (src/sequence.ml:1831-2062): the diagonal-storage Ukkonen alignment of src/newkkonen.c,
+    affine cost model (the reference's non-affine entry point is broken, see include/poy5_b200.h)."""
+
+    @staticmethod
+    def _order(pool, a, b):
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        exchange = pool.lens[a] > pool.lens[b]          # NewkkAlign.align_2: shorter first, swaped = 1 if exchanged
+        s1 = np.where(exchange, b, a).astype(np.int32); s2 = np.where(exchange, a, b).astype(np.int32)
+        return s1, s2, exchange
+
+    @staticmethod
+    def cost_2(ctx, cm, pool, a, b):
+        """NewkkAlign.cost_2 (src/sequence.ml:1944-1990): newkk_cost2_affine on (shorter, longer).  int32[n]"""
+        s1, s2, _ = NewkkAlign._order(pool, a, b)
+        n = len(s1)
+        cost = np.zeros(n, np.int32)
+        ctx.check(ctx.L.poy_batch_newkk_align(ctx.h, cm.h, pool.h, n, _ptr(s1), _ptr(s2), None, None, _ptr(cost), None, None, None, None))
+        return cost
+
+    @staticmethod
+    def align_2(ctx, cm, pool, a, b, stats=False):
+        """NewkkAlign.align_2 (src/sequence.ml:1879-1942, first_gap = true): -> dict(cost, res_a, res_b[, stats]) with
+        the aligned rows in the caller's operand order."""
+        s1, s2, exchange = NewkkAlign._order(pool, a, b)
+        n = len(s1)
+        caps = (pool.lens[s1] + pool.lens[s2]).astype(np.int64)
+        out_off = np.zeros(n, np.int64)
+        if n > 1:
+            np.cumsum(caps[:-1], out=out_off[1:])
+        total = int(caps.sum())
+        r1 = np.zeros(total, np.uint8); r2 = np.zeros(total, np.uint8)
+        cost = np.zeros(n, np.int32); out_len = np.zeros(2 * n, np.int32)
+        st = np.zeros(4 * n, np.int32) if stats else None
+        sw = exchange.astype(np.uint8)
+        ctx.check(ctx.L.poy_batch_newkk_align(ctx.h, cm.h, pool.h, n, _ptr(s1), _ptr(s2), _ptr(sw), _ptr(out_off), _ptr(cost),
+                                              _ptr(r1), _ptr(r2), _ptr(out_len), _ptr(st)))
+        out_len = out_len.reshape(n, 2)
+        ends = out_off + caps
+        x1 = [r1[ends[p] - out_len[p, 0]:ends[p]] for p in range(n)]
+        x2 = [r2[ends[p] - out_len[p, 1]:ends[p]] for p in range(n)]
+        res = dict(cost=cost, res_a=[x2[p] if exchange[p] else x1[p] for p in range(n)],
+                   res_b=[x1[p] if exchange[p] else x2[p] for p in range(n)])
+        if stats:
+            res["stats"] = st.reshape(n, 4)
+        return res
+
+    @staticmethod
+    def full_median_2(ctx, cm, pool, a, b):
+        """NewkkAlign.full_median_2 (src/sequence.ml:1992-2000): align_2 then Sequence.median_2 of the two rows."""
+        r = NewkkAlign.align_2(ctx, cm, pool, a, b)
+        return median_2(ctx, cm, r["res_a"], r["res_b"], False)      # Sequence.median_2 = seq_CAML_median_2_no_gaps (src/sequence.ml:483-490)

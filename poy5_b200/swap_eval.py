@@ -78,8 +78,30 @@ class SampleRecorder:
         return r
 
 
+def replicate_lane(ctx_device, h_tables, host_loci, src_backend, dms, arena_bytes=None):
+    """A further lane of this rank: own context (stream, scratch arenas), cost models and node store, holding a replica
+    of the observed sequences and of the all-direction medians `dms` of `src_backend` (copied through the host once,
+    untimed setup).  -> (backend, loci, dms) for treesearch.spr_round_sharded(lanes=...)"""
+    import poy5_b200 as pb
+    from . import treesearch
+    from .seqcs import Heuristic
+    c = pb.Context(ctx_device)
+    if arena_bytes:
+        c.set_arena_limit(int(arena_bytes))
+    h = Heuristic(pb.CostModel(c, h_tables.full), pb.CostModel(c, h_tables.original))
+    b = treesearch.StoreBackend(c, h, cap_bytes=max(1 << 26, src_backend.store.nbytes * 2), cap_seqs=1 << 17)
+    loci = [b.put(ls) for ls in host_loci]
+    new_dms = []
+    for l, dm in enumerate(dms):
+        keys = list(dm.keys())
+        seqs = src_backend.fetch([dm[k][0] for k in keys])
+        nodes = b.put([np.array(x, np.uint8) for x in seqs])
+        new_dms.append({k: (nd, dm[k][1]) for k, nd in zip(keys, nodes)})
+    return c, b, loci, new_dms
+
+
 def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=3000, seed=4, prunings=128, chunk=32,
-        check=24, regime=(1, 1, 3), backend=None):
+        check=24, regime=(1, 1, 3), backend=None, lanes=1):
     """One strong-scaled SPR neighbourhood sample.  Returns (record, sample): the `swap_eval` record on rank 0 (None
     elsewhere) and the recorded (medians, distances) sample for the caller's CPU-checker replay (bench.py /
     tests own the checker; nothing in this package touches it)."""
@@ -118,17 +140,35 @@ def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=30
     n_all = len(pr)
     if prunings and prunings < len(pr):
         pr = [pr[i] for i in np.linspace(0, len(pr) - 1, prunings).astype(int)]
+    # further lanes of this rank (concurrent host threads, each with its own context and node store)
+    lane_list, lane_ctx = None, []
+    if lanes > 1:
+        import torch
+        free_b, _ = torch.cuda.mem_get_info(device) if device is not None else (64 << 30, 0)
+        arena = int(min(16 << 30, 0.5 * free_b / lanes))
+        ctx.set_arena_limit(arena)
+        lane_list = [None]
+        for q in range(1, lanes):
+            c, b, lc, dm = replicate_lane(ctx.device, t2d, host_loci, sb, dms, arena)
+            lane_ctx.append((c, b)); lane_list.append((b, lc, dm))
     rec = sb
     if check and rank == 0:
         # expected batch volume on this rank: ~ (4 medians + 1 distance) per (candidate, locus)
         approx = max(1, len(pr) // world) * taxa * nloci
         rec = SampleRecorder(sb, max(1, 4 * approx // max(1, check)), max(1, approx // max(1, check)), cap=check)
     m0, d0, c0 = sb.n_median, sb.n_distance, sb.cells_distance
+    if lane_list is not None:
+        lane_list[0] = (rec, loci, dms)
     barrier(); t3 = time.perf_counter()
-    est, move, ncand, naln = treesearch.spr_round_sharded(tree, loci, rec, dms, pr, chunk=chunk, rank=rank, world=world, device=device)
+    est, move, ncand, naln = treesearch.spr_round_sharded(tree, loci, rec, dms, pr, chunk=chunk, rank=rank, world=world, device=device,
+                                                          lanes=lane_list)
+    for c, _ in lane_ctx:
+        c.synchronize()
     barrier(); t4 = time.perf_counter()
     secs = t4 - t3
     nm, nd, cells = sb.n_median - m0, sb.n_distance - d0, sb.cells_distance - c0
+    for _, b in lane_ctx:
+        nm += b.n_median; nd += b.n_distance; cells += b.cells_distance
     if dist is not None:
         import torch
         tt = torch.tensor([secs], dtype=torch.float64, device=device)
@@ -145,7 +185,7 @@ def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=30
     if rank == 0:
         out = dict(workload="configs[3]-shaped swap evaluation: %d taxa x %d loci (%s bp), random starting tree, one SPR "
                             "neighbourhood sample of %d of %d prunings, every (pruning, join edge, locus) candidate" % (taxa, nloci, lens, len(pr), n_all),
-                   scaling="strong", n_gpus=world, prunings=len(pr), chunk=chunk, candidates=int(ncand), alignments=int(naln),
+                   scaling="strong", n_gpus=world, prunings=len(pr), chunk=chunk, lanes_per_gpu=lanes, candidates=int(ncand), alignments=int(naln),
                    medians=nm, distances=nd, seconds=secs, candidates_per_s=ncand / secs, alignments_per_s=naln / secs,
                    distance_gcups=cells / secs / 1e9, best_estimate=None if est is None else int(est),
                    move=None if move is None else [list(move[0]), list(move[1])], tree_cost=int(cost),
@@ -157,6 +197,8 @@ def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=30
                          "between device-synchronised barriers)",
                    node_store_bytes=sb.store.nbytes)
     sample = (rec.med, rec.dis) if (check and rank == 0) else None
+    for c, b in lane_ctx:
+        b.close(); c.close()
     if backend is None:
         sb.close()
     return out, sample

@@ -517,34 +517,38 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
             up = [{x1: dm[(x2, u)], x2: dm[(x1, u)]} for dm in dms]
             ups.append(up); levels.append((lv, par))
             joins.append([(par[c][0], c) for l_ in lv for c in l_])
-        for d in range(max(len(lv) for lv, _ in levels)):
+        # level d of the incremental medians and the edge medians of the join edges whose up[] became available at
+        # level d-1 go into ONE batch: the dependent chain (up[c] needs up[a]) is latency bound, the edge medians are
+        # independent filler for the same launches
+        ems = {}
+        depth = max(len(lv) for lv, _ in levels)
+        for d in range(depth + 1):
             batch, own = [], []
             for k, (lv, par) in enumerate(levels):
                 if d < len(lv):
                     for c in lv[d]:
                         a, s = par[c]
                         for l in range(nl):
-                            batch.append((ups[k][l][a][0], dms[l][(s, a)][0])); own.append((k, l, c, a, s))
+                            batch.append((ups[k][l][a][0], dms[l][(s, a)][0])); own.append((0, k, l, c, a, s))
+                if 0 < d <= len(lv):
+                    for c in lv[d - 1]:
+                        a = par[c][0]
+                        for l in range(nl):
+                            batch.append((ups[k][l][c][0], dms[l][(c, a)][0])); own.append((1, k, l, c, a, None))
             naln += len(batch)
-            for (k, l, c, a, s), (seq, c2) in zip(own, backend.median(batch)):
-                ups[k][l][c] = (seq, c2 + ups[k][l][a][1] + dms[l][(s, a)][1])
-        batch, own = [], []
-        for k, js in enumerate(joins):
-            for (a, c) in js:
-                for l in range(nl):
-                    batch.append((ups[k][l][c][0], dms[l][(c, a)][0])); own.append((k, l, a, c))
-        naln += len(batch)
-        ems = {}
-        for (k, l, a, c), (seq, c2) in zip(own, backend.median(batch)):
-            ems[(k, l, a, c)] = (seq, c2 + ups[k][l][c][1] + dms[l][(c, a)][1])
+            for (kind, k, l, c, a, s), (seq, c2) in zip(own, backend.median(batch)):
+                if kind == 0:
+                    ups[k][l][c] = (seq, c2 + ups[k][l][a][1] + dms[l][(s, a)][1])
+                else:
+                    ems[(k, l, a, c)] = (seq, c2 + ups[k][l][c][1] + dms[l][(c, a)][1])
         cand, meta = [], []
         for k, ((u, v), js) in enumerate(zip(part, joins)):
-            for (a, c) in js:
+            for ji, (a, c) in enumerate(js):
                 base = 0
                 for l in range(nl):
                     em = ems[(k, l, a, c)]
                     cand.append((dms[l][(v, u)][0], em[0])); base += em[1] + dms[l][(v, u)][1]
-                meta.append(((u, v), (a, c), base, (c0 + k, len(meta))))
+                meta.append(((u, v), (a, c), base, (c0 + k, ji)))
         naln += len(cand)
         d = np.asarray(backend.distance(cand), np.int64).reshape(len(meta), nl).sum(axis=1)
         est = d + np.array([m[2] for m in meta], np.int64)
@@ -562,7 +566,7 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
     return best[0], (best[1], best[2]), ncand, naln
 
 
-def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, world=1, device=None):
+def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, world=1, device=None, lanes=None):
     """One SPR neighbourhood strong-scaled over `world` ranks (the Parmap / MPI seam of src/ptree.ml:1356-1408,
     src/allDirChar.ml:2132-2177): the PRUNINGS are dealt to the ranks by estimated work (LPT on the size of the rest
     tree), so every candidate of a pruning -- all its join edges, all loci -- is evaluated on one GPU and the
@@ -570,38 +574,63 @@ def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, worl
     unbroken tree are replicated.  The only exchange is the reduction of the best candidate: one MIN all-reduce of the
     estimate, one of the (pruning, join edge) ordinal among the ranks that hold it (ties resolve to the first candidate
     in the global enumeration order, whatever the rank count), plus one SUM for the counters.
+
+    `lanes`: a list of (backend, loci, dms) triples, one per concurrent host thread of THIS rank (each with its own
+    context / stream / node store holding a replica of the loci and of the all-direction medians).  A rank's prunings
+    are dealt to its lanes the same way they are dealt to ranks: the dependent median levels of one pruning are latency
+    bound (a level lasts as long as the widest pair's wavefronts), so several independent chains in flight are what
+    keeps the GPU busy -- the role of the reference's Parmap worker processes.
     Returns (best estimate, (pruning, join edge), candidates, alignments) -- identical on every rank and for every N."""
     from . import shard
     prunings = list(prunings)
-    if world == 1:
+    if lanes is None:
+        lanes = [(backend, loci, dms)]
+    nlanes = len(lanes)
+    if world == 1 and nlanes == 1:
         return spr_round(tree, loci, backend, dms=dms, prunings=prunings, chunk=chunk)
-    import torch
-    import torch.distributed as dist
     work = [len(tree.component(u, v)) for (u, v) in prunings]
-    mine = shard.lpt_partition(work, world)[rank]
-    where = []
-    est, move, ncand, naln = spr_round(tree, loci, backend, dms=dms, prunings=[prunings[i] for i in mine], chunk=chunk, where=where)
+    parts = shard.lpt_partition(work, world * nlanes)
     big = (1 << 62)
-    t = torch.tensor([big if est is None else int(est)], dtype=torch.int64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    gmin = int(t.item())
+
+    def run_lane(q):
+        b, lc, dm = lanes[q]
+        mine = parts[rank * nlanes + q]
+        where = []
+        est, move, ncand, naln = spr_round(tree, lc, b, dms=dm, prunings=[prunings[i] for i in mine], chunk=chunk, where=where)
+        if est is None:
+            return big, big, 0, naln
+        pi, ji = where[0]
+        return int(est), (int(mine[pi]) << 24) | ji, ncand, naln        # join edges per pruning < 2^24
+
+    if nlanes == 1:
+        res = [run_lane(0)]
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nlanes) as ex:      # the ctypes calls release the GIL while the GPU works
+            res = list(ex.map(run_lane, range(nlanes)))
+    est, mine_ord = min((r[0], r[1]) for r in res)
+    ncand, naln = sum(r[2] for r in res), sum(r[3] for r in res)
+    gmin, gord = est, mine_ord
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([est], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gmin = int(t.item())
+        o = torch.tensor([mine_ord if est == gmin else big], dtype=torch.int64, device=device)
+        dist.all_reduce(o, op=dist.ReduceOp.MIN)
+        gord = int(o.item())
+        cnt = torch.tensor([ncand, naln], dtype=torch.int64, device=device)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ncand, naln = int(cnt[0].item()), int(cnt[1].item())
     if gmin == big:
         return None, None, 0, 0
-    mine_ord = big
-    if est is not None and int(est) == gmin:
-        pi, ji = where[0]
-        mine_ord = (int(mine[pi]) << 24) | ji            # join edges per pruning < 2^24
-    o = torch.tensor([mine_ord], dtype=torch.int64, device=device)
-    dist.all_reduce(o, op=dist.ReduceOp.MIN)
-    gord = int(o.item())
-    cnt = torch.tensor([ncand, naln], dtype=torch.int64, device=device)
-    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     # the winner's move is recomputed from the ordinal on every rank (host-only tree walk, no communication)
     gp, gj = gord >> 24, gord & ((1 << 24) - 1)
     u, v = prunings[gp]
     _, _, lv, par = _side_plan(tree, u, v)
     joins = [(par[c][0], c) for l_ in lv for c in l_]
-    return gmin, ((u, v), joins[gj]), int(cnt[0].item()), int(cnt[1].item())
+    return gmin, ((u, v), joins[gj]), ncand, naln
 
 
 def apply_spr(tree, move):
