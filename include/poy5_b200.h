@@ -100,6 +100,28 @@ POY_API int32_t poy_cm_get_closest(const poy_cm_host *cm, int32_t a, int32_t b);
 POY_API poy_status poy_cm_upload(poy_ctx *ctx, const poy_cm_host *cm, poy_cm **out);
 POY_API void poy_cm_free(poy_ctx *ctx, poy_cm *cm);
 
+/* ---- 3-D cost model: struct cm_3d (src/cm.h:253-280) for the bit-indexed 5-letter alphabet -----------------------
+ * Tables indexed (((a << 5) + b) << 5) + c like cm_calc_cost_position_3d (src/cm.c:945-953).
+ *  poy_cm3d_fill    Cost_matrix.Three_D.of_two_dim_comb (src/cost_matrix.ml:1605-1652) restated in C++: cost = min
+ *                   over the five single elements of the three 2-D costs (the gap only if the 2-D matrix is metric or
+ *                   at least two inputs contain it), median = the lowest minimising bit (pick_bit)
+ *  poy_cm3d_upload  cm_set_val_3d + the cm_CAML_set_*_3d setters (src/cm.c:704): the tables become device resident
+ *  poy_batch_median_3  the column-wise three-way median of Sequence.Align.align_3_powell_inter
+ *                   (src/sequence.ml:1342-1369): for three aligned rows of equal length, medianwg[x] =
+ *                   Three_D.median a[x] b[x] c[x]; median = gap :: the non-gap ones; cost3 = sum of Three_D.cost.
+ *                   Rows are packed HOST buffers (triple p = rows_x[off[p] .. off[p] + len[p])); the outputs of
+ *                   triple p start at out_off[p] (capacity len[p] + 1), out_len[p] = length of median. */
+typedef struct {
+    int32_t cost[32768];
+    uint8_t median[32768];
+} poy_cm3d_host;
+POY_API poy_status poy_cm3d_fill(const poy_cm_host *c2, poy_cm3d_host *out);
+POY_API poy_status poy_cm3d_upload(poy_ctx *ctx, const poy_cm3d_host *cm3, poy_cm3d **out);
+POY_API void poy_cm3d_free(poy_ctx *ctx, poy_cm3d *cm3);
+POY_API poy_status poy_batch_median_3(poy_ctx *ctx, const poy_cm3d *cm3, int32_t n, const uint8_t *rows_a, const uint8_t *rows_b,
+                                      const uint8_t *rows_c, const int64_t *off, const int32_t *len, const int64_t *out_off,
+                                      uint8_t *median, uint8_t *medianwg, int32_t *out_len, int32_t *cost3);
+
 /* ---- sequence pool: replaces seq_CAML_create/prepend for batch inputs ------
  * `data` holds nseq sequences back to back; sequence s is
  * data[offsets[s] .. offsets[s+1]).  The *_dev variant takes DEVICE pointers

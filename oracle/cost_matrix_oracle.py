@@ -244,3 +244,30 @@ def get_closest(m, a, b):
         if nc < cur:
             best, cur = x, nc
     return best
+
+
+def three_d_of_two_dim_comb(m):
+    """Cost_matrix.Three_D.of_two_dim_comb (src/cost_matrix.ml:1605-1652): -> (cost int32[32,32,32], median uint8[32,32,32]).
+    Restated from the OCaml (cannot run here): parity unpinned by the reference, like the 2-D fill."""
+    n, lcm, gap = m.n, m.lcm, m.gap
+    cost = np.zeros((n, n, n), np.int32); med = np.zeros((n, n, n), np.uint8)
+    for i in range(1, n):
+        for j in range(1, n):
+            for k in range(1, n):
+                best, mm = MAX_INT, 0
+                for l in range(lcm):
+                    inter = 1 << l
+                    shared = int(bool(i & inter)) + int(bool(j & inter)) + int(bool(k & inter))
+                    if m.is_metric or shared >= 2 or inter != gap:
+                        c = int(m.cost[inter, i]) + int(m.cost[inter, j]) + int(m.cost[inter, k])
+                    else:
+                        c = MAX_INT
+                    if c < best:
+                        best, mm = c, inter
+                    elif c == best:
+                        mm |= inter
+                pick = 1
+                while not (pick & mm):
+                    pick <<= 1
+                cost[i, j, k] = best; med[i, j, k] = pick
+    return cost, med

@@ -27,6 +27,11 @@ class CmHost(C.Structure):
                 ("cost_model_type", C.c_int32), ("is_identity", C.c_int32), ("is_metric", C.c_int32)]
 
 
+class Cm3dHost(C.Structure):
+    """poy_cm3d_host == struct cm_3d tables (src/cm.h:253-280), indexed (((a << 5) + b) << 5) + c."""
+    _fields_ = [("cost", C.c_int32 * 32768), ("median", C.c_uint8 * 32768)]
+
+
 def lib_path():
     return os.path.join(_HERE, "libpoy5b200.so")
 
@@ -92,6 +97,11 @@ def load():
     L.poy_store_read.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
     L.poy_store_median.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.poy_store_distance.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp]
+    L.poy_cm3d_fill.argtypes = [C.POINTER(CmHost), C.POINTER(Cm3dHost)]
+    L.poy_cm3d_upload.argtypes = [vp, C.POINTER(Cm3dHost), C.POINTER(vp)]
+    L.poy_cm3d_free.argtypes = [vp, vp]
+    L.poy_cm3d_free.restype = None
+    L.poy_batch_median_3.argtypes = [vp, vp, C.c_int32] + [vp] * 10
     L.poy_batch_newkk_align.argtypes = [vp, vp, vp, C.c_int32] + [vp] * 9
     L.poy_microbench_int.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _LIB = L
@@ -106,4 +116,5 @@ EXPORTS = ["poy_ctx_create", "poy_ctx_destroy", "poy_last_error", "poy_status_st
            "poy_batch_aligned_cost", "poy_batch_ancestor_2", "poy_batch_closest", "poy_dos_distance", "poy_dos_median", "poy_dos_median2",
            "poy_store_create", "poy_store_free", "poy_store_pool", "poy_store_count", "poy_store_bytes", "poy_store_append",
            "poy_store_truncate", "poy_store_lengths", "poy_store_read", "poy_store_median", "poy_store_distance",
-           "poy_batch_newkk_align", "poy_microbench_int"]
+           "poy_batch_newkk_align", "poy_cm3d_fill", "poy_cm3d_upload", "poy_cm3d_free",
+           "poy_batch_median_3", "poy_microbench_int"]

@@ -3,7 +3,7 @@ C++ side of the library (poy_cm_fill); this module only names things the way the
 import ctypes as C
 import numpy as np
 from . import _lib
-from ._lib import CmHost
+from ._lib import CmHost, Cm3dHost
 
 
 class Two_D:
@@ -50,3 +50,24 @@ def min_non0(cm_host):
 
 def get_closest(cm_host, a, b):
     return _lib.load().poy_cm_get_closest(C.byref(cm_host), int(a), int(b))
+
+
+class Three_D:
+    """Cost_matrix.Three_D (src/cost_matrix.ml:1440-1760) for the DNA bitset alphabet: host tables + device handle."""
+
+    def __init__(self, host):
+        self.host = host
+
+    @staticmethod
+    def of_two_dim(cm_host):
+        """Cost_matrix.Three_D.of_two_dim -> of_two_dim_comb (src/cost_matrix.ml:1605-1652, 1707-1724)"""
+        L = _lib.load()
+        out = Cm3dHost()
+        st = L.poy_cm3d_fill(C.byref(cm_host), C.byref(out))
+        if st != 0:
+            raise _lib.PoyError(st, L.poy_status_string(st).decode())
+        return Three_D(out)
+
+    def tables(self):
+        return dict(cost=np.ctypeslib.as_array(self.host.cost).reshape(32, 32, 32).copy(),
+                    median=np.ctypeslib.as_array(self.host.median).reshape(32, 32, 32).copy())

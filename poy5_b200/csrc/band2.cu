@@ -40,27 +40,41 @@ __device__ __forceinline__ void sfor(F &&f) {
     }
 }
 
-// window entries.  meta: bits 0-15 shared-memory byte offset of the cost row / column,
-// bit 16 symbol has the gap bit, bit 17 previous symbol has it, bit 18 gap opening is free here.
+// window entries.
+// Gap-free pairs: meta = shared-memory byte offset of the cost row / column.
+// Pairs with gap-bit symbols: meta = (byte offset of the cost row / column) << 16 | (index of the surcharge class) << 5,
+// so that ONE add of a row and a column entry yields both the table address (high half) and the address of the
+// 32-byte surcharge record of this (row class, column class) in s_lut (bits 5-11); bits 0-2 of a column entry hold
+// the class the column has when it sits on the left border (cell_gen).  ext already carries the END_* tag of the
+// direction byte (DIR fills).
 struct Ent { int ext, opn, meta; };
-#define M_HAS (1 << 16)
-#define M_PREV (1 << 17)
-#define M_GOZ (1 << 18)
 
-template <bool GF>
-__device__ __forceinline__ Ent row_entry(const int4 v) {
+// surcharge class of a base: bit 0 symbol has the gap bit, bit 1 previous symbol has it, bit 2 gap opening is free here
+__device__ __forceinline__ int gap_class(const int4 v) {
+    return ((v.w & PF_HASGAP) ? 1 : 0) | ((v.w & PF_PREVGAP) ? 2 : 0) | (v.z == 0 ? 4 : 0);
+}
+
+template <bool GF, bool DIR>
+__device__ __forceinline__ Ent row_entry(const int4 v, int swoff) {
     Ent e;
-    e.ext = GF ? 0 : (v.x << 8); e.opn = GF ? 0 : (v.y << 8);     // x256: see cell_gf / cell_gen
-    e.meta = ((v.w & 15) << 11);
-    if (!GF) e.meta |= ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
+    if (GF) { e.ext = 0; e.opn = 0; e.meta = ((v.w & 15) << 11); }
+    else {
+        e.ext = (v.x << 8) + (DIR ? 16 : 0); e.opn = (v.y << 8);     // x256: see cell_gf / cell_gen
+        e.meta = ((v.w & 15) << 27) | (gap_class(v) << 8) | swoff;
+    }
     return e;
 }
-template <bool GF>
+template <bool GF, bool DIR>
 __device__ __forceinline__ Ent col_entry(const int4 v, int lane) {
     Ent e;
-    e.ext = GF ? 0 : (v.x << 8); e.opn = GF ? 0 : (v.y << 8);
-    e.meta = (((v.w & 15) << 7) + (lane << 2));
-    if (!GF) e.meta |= ((v.w & PF_HASGAP) ? M_HAS : 0) | ((v.w & PF_PREVGAP) ? M_PREV : 0) | (v.z == 0 ? M_GOZ : 0);
+    if (GF) { e.ext = 0; e.opn = 0; e.meta = (((v.w & 15) << 7) + (lane << 2)); }
+    else {
+        e.ext = (v.x << 8) + (DIR ? 32 : 0); e.opn = (v.y << 8);
+        const int cc = gap_class(v);
+        // at the left border the reference's "previous column symbol" is the column symbol itself
+        const int cc_lb = (cc & 5) | ((cc & 1) << 1);
+        e.meta = ((((v.w & 15) << 7) + (lane << 2)) << 16) | (cc << 5) | cc_lb;
+    }
     return e;
 }
 
@@ -68,40 +82,40 @@ __device__ __forceinline__ Ent col_entry(const int4 v, int lane) {
 // (i-1,j-1), on exit the new cell.  l* = (i,j-1), u* = (i-1,j).  EDGE adds the j == 0 handling of the prologue.
 // Same value-times-256 + tag scheme as cell_gf below (read that comment first); here the ALIGN_TO_* code cannot be
 // taken from the predecessor's todo code (the gap-bit surcharges differ), so it is a second tagged minimum, and
-// the block state EB brings its own END_BLOCK tag.  Byte (tagged format): bits 0-1 todo code, bits 2-3
-// ALIGN_TO code (both: 0/1 = the two gap directions in priority order, 2 = block, 3 = align), bits 4/5/6 = NOT
-// END_VERTICAL / END_HORIZONTAL / END_BLOCK, bit 7 = HORIZONTAL_EQ_VERTICAL.
+// the block state EB brings its own END_BLOCK tag.  Everything that depends on the gap bits of the two symbols and
+// of their predecessors (src/algn.c:1376-1490: the block-diagonal costs, the three surcharges of ALIGN_TO_*) is ONE
+// 32-byte record of s_lut, selected by the sum of the row and column entries: {v, h, block surcharge (with their
+// ALIGN_TO tags), block opening, block extension (with the END_BLOCK tag)}; every minimum is a chain of
+// add-then-min (VIADDMNMX).  Byte (tagged format): bits 0-1 todo code, bits 2-3 ALIGN_TO code (both: 0/1 = the two
+// gap directions in priority order, 2 = block, 3 = align), bits 4/5/6 = NOT END_VERTICAL / END_HORIZONTAL /
+// END_BLOCK, bit 7 = HORIZONTAL_EQ_VERTICAL.
 #define INF256 (POY_INF << 8)
 template <bool EDGE, bool DIR>
 __device__ __forceinline__ unsigned cell_gen(int &CB, int &EV, int &EH, int &EB, unsigned &G, int lCB, int lEH, unsigned lG,
                                              int uCB, int uEV, unsigned uG, const Ent r, const Ent c, const char *s_tab,
-                                             int GO256, bool lb, bool rb, bool jpos, int tagV, int tagH) {
-    // extend horizontal / vertical: ties take the opening (END_* flag)
-    int eH = min(lEH + c.ext + (DIR ? 32 : 0), lCB + c.opn);
-    int eV = min(uEV + r.ext + (DIR ? 16 : 0), uCB + r.opn);
+                                             const char *s_lut, bool lb, bool rb, bool jpos, int tagV, int tagH) {
+    // extend horizontal / vertical: ties take the opening (END_* flag = the tag carried by ext)
+    int eH = __viaddmin_s32(lEH, c.ext, lCB + c.opn);
+    int eV = __viaddmin_s32(uEV, r.ext, uCB + r.opn);
     if (lb) eH = INF256 + (DIR ? 32 : 0);
     if (rb) eV = INF256 + (DIR ? 16 : 0);
     const int nEH = DIR ? (eH & ~255) : eH, nEV = DIR ? (eV & ~255) : eV;
-    const int diag = *(const int *)(s_tab + (r.meta & 0xFFFF) + (c.meta & 0xFFFF));
-    const bool hg_i = (r.meta & M_HAS) != 0, hg_j = (c.meta & M_HAS) != 0;
-    // at the left border the reference's "previous column symbol" is the column symbol itself
-    const bool pg_j = lb ? hg_j : ((c.meta & M_PREV) != 0);
-    const bool both = hg_i && hg_j;
-    const bool clean = !(r.meta & M_PREV) && !pg_j;
-    const int dg = both ? 0 : INF256;
-    const int od = both ? (clean ? 0 : 2 * GO256) : INF256;
-    int eB = min(EB + dg + (DIR ? 64 : 0), CB + od);
-    const bool goz_i = (r.meta & M_GOZ) != 0, goz_j = (c.meta & M_GOZ) != 0;
-    const int v = EV + ((hg_i && !goz_j) ? GO256 : 0);
-    const int h = EH + ((hg_j && !goz_i) ? GO256 : 0);
-    const int dd = EB + ((goz_i && goz_j) ? 0 : GO256);
+    int cm = c.meta;
+    if (lb) cm = (cm & ~0xE0) | ((cm & 7) << 5);
+    const int sum = r.meta + cm;
+    const int diag = *(const int *)(s_tab + ((unsigned)sum >> 16));
+    const char *q = s_lut + (sum & 0xFE0);
+    const int4 sur = *(const int4 *)q;            // x: EV -> CB, y: EH -> CB, z: EB -> CB, w: CB -> EB (block opening)
+    const int dgx = *(const int *)(q + 16);       // EB -> EB (block extension)
+    int eB = __viaddmin_s32(EB, dgx, CB + sur.w);
     // ALIGN_TO_*: tagged minimum over the four ways into CB (tags in bits 2-3)
-    const int mk = DIR ? min(__vimin3_s32(CB + 12, v + 4 * tagV, h + 4 * tagH), dd + 8) : min(__vimin3_s32(CB, v, h), dd);
+    const int mk = __viaddmin_s32(EB, sur.z, __viaddmin_s32(EH, sur.y, __viaddmin_s32(EV, sur.x, DIR ? CB + 12 : CB)));
     int nCB = (DIR ? (mk & ~255) : mk) + diag;
     if (EDGE && !jpos) { nCB = INF256; eB = INF256 + (DIR ? 64 : 0); }
     const int nEB = DIR ? (eB & ~255) : eB;
     // final minimum, its todo code and its tie set
-    const int k = DIR ? min(__vimin3_s32(nEV + tagV, nEH + tagH, nCB + 3), nEB + 2) : min(__vimin3_s32(nEV, nEH, nCB), nEB);
+    const int k = DIR ? __viaddmin_s32(nEB, 2, __viaddmin_s32(nEH, tagH, __viaddmin_s32(nEV, tagV, nCB + 3)))
+                      : min(__vimin3_s32(nEV, nEH, nCB), nEB);
     const bool fV = nEV <= k, fH = nEH <= k, fA = nCB <= k, fD = nEB <= k;
     // gap counters: component-wise max over the chosen predecessors (+1 on the side that gaps)
     const unsigned cD = (fA || fD) ? G : 0u;
@@ -192,6 +206,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state, int *ebrow, uint8_t *dir) {
     constexpr int H = D / 2;
     __shared__ int s_tab_i[256 * 32];  // cost16 replicated per bank: entry e of lane l at [e*32 + l]
+    __shared__ __align__(16) int s_lut_i[GFK ? 8 : 128 * 8];   // surcharge records of cell_gen: [swaped][row class][column class] x 32 B
     __shared__ int s_job;
     __shared__ int s_xe[NW][4];        // slot-0 state of lane 0 of every warp (read by the warp to its left)
     __shared__ int s_xo[NW][4];        // slot-(D-1) state of lane 31 of every warp (read by the warp to its right)
@@ -206,10 +221,25 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         const int e = x >> 5;
         s_tab_i[x] = (GFK ? cm->cost16[e] - cm->prepend[e & 15] - cm->gapext[e >> 4] : cm->cost16[e]) * 256;   // x256: see cell_gf
     }
-    __syncthreads();
-    const char *s_tab = (const char *)s_tab_i;
     const int GO = cm->gap_open;
     const int GO256 = GO << 8;
+    if (!GFK)
+        for (int x = threadIdx.x; x < 128; x += WPB * 32) {
+            const int sw = x >> 6, rc = (x >> 3) & 7, cc = x & 7;
+            const bool hg_i = rc & 1, pv_i = rc & 2, goz_i = rc & 4, hg_j = cc & 1, pv_j = cc & 2, goz_j = cc & 4;
+            const int tV = sw ? 1 : 0, tH = sw ? 0 : 1;
+            const bool both = hg_i && hg_j, clean = !pv_i && !pv_j;
+            int *e = s_lut_i + x * 8;
+            e[0] = ((hg_i && !goz_j) ? GO256 : 0) + (DIR ? 4 * tV : 0);     // EV -> CB: + go_j if the row symbol has the gap bit
+            e[1] = ((hg_j && !goz_i) ? GO256 : 0) + (DIR ? 4 * tH : 0);     // EH -> CB
+            e[2] = ((goz_i && goz_j) ? 0 : GO256) + (DIR ? 8 : 0);          // EB -> CB: + max(go_i, go_j)
+            e[3] = both ? (clean ? 0 : 2 * GO256) : INF256;                 // CB -> EB
+            e[4] = (both ? 0 : INF256) + (DIR ? 64 : 0);                    // EB -> EB
+            e[5] = e[6] = e[7] = 0;
+        }
+    __syncthreads();
+    const char *s_tab = (const char *)s_tab_i;
+    const char *s_lut = (const char *)s_lut_i;
 
     for (;;) {
         int job;
@@ -273,8 +303,9 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         int a = k & 1;
         int i0 = (a - d0 + k) >> 1, j0 = a - i0;
         Ent R[H], C[H + 1];
-        auto load_row = [&](int i) { i = i < 0 ? 0 : (i > lasti ? lasti : i); return row_entry<GF>(rp[i]); };
-        auto load_col = [&](int j) { j = j < 0 ? 0 : (j > lastj ? lastj : j); return col_entry<GF>(cp[j], lane); };
+        const int swoff = swaped ? 2048 : 0;     // second half of s_lut: the ALIGN_TO tags of swapped operands
+        auto load_row = [&](int i) { i = i < 0 ? 0 : (i > lasti ? lasti : i); return row_entry<GF, DIR>(rp[i], swoff); };
+        auto load_col = [&](int j) { j = j < 0 ? 0 : (j > lastj ? lastj : j); return col_entry<GF, DIR>(cp[j], lane); };
         sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; R[h] = load_row(i0 - h); });
         sfor<H + 1>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = load_col(j0 + h); });
 
@@ -314,6 +345,9 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 cj = cj < 0 ? 0 : (cj > lastj ? lastj : cj);
                 nrow = rp[ri]; ncol = cp[cj];
             }
+            // the stale EB row is written by the cells of even rows on the two leftmost diagonals
+            // and of row istar: one test per iteration instead of one per cell
+            const bool stale_hit = !GF && (tid == 0 || (unsigned)(i0 - istar) < (unsigned)H);
             // ---- even diagonals ----
             {
                 if (has_left) pair_wait(bar_O_left);
@@ -343,14 +377,18 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                                               *(const int *)(s_tab + R[h].meta + C[h].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         else
                             b = cell_gen<EDGE, DIR>(CB[u], EV[u], EH[u], EB[u], G[u], lCB, lEH, lG, CB[u + 1], EV[u + 1], G[u + 1],
-                                                    R[h], C[h], s_tab, GO256, lb, u == rbslot, j > 0, tagV, tagH);
+                                                    R[h], C[h], s_tab, s_lut, lb, u == rbslot, j > 0, tagV, tagH);
                         bw[h] = b;
-                        if (!GF) {
-                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u] >> 8;
-                        }
                     }
                 });
                 if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, pack_dir<H>(bw));
+                if (stale_hit && warp_in_band)      // rare: keeps the address arithmetic of the stale row out of the cells
+                sfor<H>([&](auto hc) {
+                    constexpr int h = decltype(hc)::value;
+                    constexpr int u = 2 * h;
+                    const int i = i0 - h, j = j0 + h, d = d0 + u;
+                    if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
+                });
                 if (NW > 1) {
                     if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
                     if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
@@ -385,14 +423,18 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                                               *(const int *)(s_tab + R[h].meta + C[h + 1].meta), GO256, lb, u == rbslot, j > 0, tagV, tagH);
                         else
                             b = cell_gen<EDGE, DIR>(CB[u], EV[u], EH[u], EB[u], G[u], CB[u - 1], EH[u - 1], G[u - 1], uCB, uEV, uG,
-                                                    R[h], C[h + 1], s_tab, GO256, lb, u == rbslot, j > 0, tagV, tagH);
+                                                    R[h], C[h + 1], s_tab, s_lut, lb, u == rbslot, j > 0, tagV, tagH);
                         bw[h] = b;
-                        if (!GF) {
-                            if (!(i & 1) && (d <= 1 || i == istar) && d < B && i <= lasti && j <= lastj) eb[j] = EB[u] >> 8;
-                        }
                     }
                 });
                 if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, pack_dir<H>(bw));
+                if (stale_hit && warp_in_band)
+                sfor<H>([&](auto hc) {
+                    constexpr int h = decltype(hc)::value;
+                    constexpr int u = 2 * h + 1;
+                    const int i = i0 - h, j = j0 + h + 1, d = d0 + u;
+                    if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
+                });
                 if (NW > 1) {
                     if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
                     if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
@@ -403,8 +445,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             sfor<H - 1>([&](auto hc) { constexpr int h = H - 1 - decltype(hc)::value; R[h] = R[h - 1]; });
             sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = C[h + 1]; });
             ++i0; ++j0;
-            R[0] = row_entry<GF>(nrow);
-            C[H] = col_entry<GF>(ncol, lane);
+            R[0] = row_entry<GF, DIR>(nrow, swoff);
+            C[H] = col_entry<GF, DIR>(ncol, lane);
         };
 
         if (!P2P || warp_in_band) {

@@ -489,7 +489,7 @@ def spr_prunings(tree, n_leaves):
     return out
 
 
-def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None):
+def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None, merge_edges=False):
     """One SPR neighbourhood over several loci.  For the pruning (u, v) the rest tree is u's side with u suppressed
     (its neighbours x1, x2 joined); only the medians that *see* the cut are recomputed, top-down from the cut:
 
@@ -517,9 +517,9 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
             up = [{x1: dm[(x2, u)], x2: dm[(x1, u)]} for dm in dms]
             ups.append(up); levels.append((lv, par))
             joins.append([(par[c][0], c) for l_ in lv for c in l_])
-        # level d of the incremental medians and the edge medians of the join edges whose up[] became available at
-        # level d-1 go into ONE batch: the dependent chain (up[c] needs up[a]) is latency bound, the edge medians are
-        # independent filler for the same launches
+        # merge_edges: level d of the incremental medians and the edge medians of the join edges whose up[] became
+        # available at level d-1 go into ONE batch (filler for the latency-bound dependent chain when the chunk is small;
+        # measured slower for large chunks, where one big edge-median batch keeps every round of the band schedule full)
         ems = {}
         depth = max(len(lv) for lv, _ in levels)
         for d in range(depth + 1):
@@ -530,8 +530,8 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
                         a, s = par[c]
                         for l in range(nl):
                             batch.append((ups[k][l][a][0], dms[l][(s, a)][0])); own.append((0, k, l, c, a, s))
-                if 0 < d <= len(lv):
-                    for c in lv[d - 1]:
+                if (merge_edges and 0 < d <= len(lv)) or (not merge_edges and d == depth):
+                    for c in (lv[d - 1] if merge_edges else [c for l_ in lv for c in l_]):
                         a = par[c][0]
                         for l in range(nl):
                             batch.append((ups[k][l][c][0], dms[l][(c, a)][0])); own.append((1, k, l, c, a, None))
