@@ -49,8 +49,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle replay of the timed pairs")
     ap.add_argument("--no-swap", action="store_true", help="skip the strong-scaled swap-evaluation sub-record")
-    ap.add_argument("--swap-prunings", type=int, default=192, help="SPR prunings of the swap-evaluation sample (whole job)")
-    ap.add_argument("--swap-chunk", type=int, default=24, help="prunings per candidate batch")
+    ap.add_argument("--swap-prunings", type=int, default=0, help="SPR prunings of the swap-evaluation workload (whole job); 0 = the full neighbourhood")
+    ap.add_argument("--swap-chunk", type=int, default=192, help="prunings per candidate batch (bounds the node store of a rank)")
     ap.add_argument("--swap-check", type=int, default=24, help="medians / distances replayed on the CPU checker")
     return ap.parse_args()
 

@@ -109,6 +109,13 @@ static int read_seq(value v, unsigned char *out) {
 }
 static void free_val(value v) { free((void *)v); }
 
+/* OCaml-value sequences for tests that drive `*_CAML_*`-shaped entry points directly (tests/test_caml_stubs.py) */
+void *ref_seq_new(const unsigned char *s, int len, int cap) { return (void *)make_seq(s, len, cap); }
+int ref_seq_read(void *v, unsigned char *out) { return read_seq((value)v, out); }
+void ref_val_free(void *v) { free(v); }
+long ref_val_int(int x) { return (long)Val_int(x); }
+int ref_int_val(long v) { return Int_val((value)v); }
+
 /* ---- scratch matrices (Matrix.default, src/matrix.ml:34) ---------------- */
 void *ref_mat_new(void) { return (void *)mat_CAML_create_general(Val_int(0)); }
 void ref_mat_free(void *m) { mat_CAML_flush_memory((value)m); free(m); }

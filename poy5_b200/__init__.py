@@ -7,5 +7,5 @@ implementation of any alignment here: importing works without a GPU (so the buil
 checked), but creating a :class:`Context` raises unless a CUDA device is present.
 """
 from ._lib import PoyError, lib_path, load  # noqa: F401
-from .api import Context, CostModel, Pool, Store  # noqa: F401
+from .api import Context, CostModel, CostModel3D, Pool, Store  # noqa: F401
 from . import cost_matrix, sequence, seqcs  # noqa: F401

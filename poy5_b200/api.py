@@ -79,6 +79,22 @@ class CostModel:
             self.h = None
 
 
+class CostModel3D:
+    """Device-resident 3-D cost model (poy_cm3d, struct cm_3d).  `three_d` is a cost_matrix.Three_D."""
+
+    def __init__(self, ctx, three_d):
+        self.ctx = ctx
+        self.host = three_d.host
+        h = C.c_void_p()
+        ctx.check(ctx.L.poy_cm3d_upload(ctx.h, C.byref(self.host), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.L.poy_cm3d_free(self.ctx.h, self.h)
+            self.h = None
+
+
 class Pool:
     """Device-resident packed sequences (poy_pool).  `seqs` is a list of uint8 arrays, each starting
     with the gap code 16; or pass (data, offsets) directly."""

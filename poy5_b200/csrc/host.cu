@@ -162,6 +162,12 @@ poy_status poy_scratch(poy_ctx *ctx, int slot, size_t bytes, void **out) {
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&ctx->d_scratch[slot], want);
         if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&ctx->d_scratch[slot], want); }
+        if (e != cudaSuccess && slot != SL_DIR2 && ctx->d_scratch[SL_DIR2]) {   // ... or in the second direction arena
+            cudaGetLastError();
+            cudaStreamSynchronize(ctx->tb_stream);
+            cudaFree(ctx->d_scratch[SL_DIR2]); ctx->d_scratch[SL_DIR2] = nullptr; ctx->scratch_cap[SL_DIR2] = 0;
+            e = cudaMalloc(&ctx->d_scratch[slot], want);
+        }
         if (e != cudaSuccess) {   // the memory may sit in the block cache of freed pools (this context's or its twin's)
             cudaGetLastError();
             for (poy_ctx *c : { ctx, ctx->twin }) {
@@ -793,7 +799,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             }
             // Rounds that fit the arena in one wave alternate between two arenas / job arrays, so that the traceback
             // of the pairs that stop in this round (own stream) overlaps the fills of the next one.
-            const bool single_wave = async_tb && pos == 0 && end == order.size();
+            // (the second arena stays small -- a quarter of the limit -- so that the two together never outgrow what a
+            // context was allowed before: large rounds are throughput bound and gain nothing from the overlap)
+            const bool single_wave = async_tb && pos == 0 && end == order.size() && (uint64_t)used * 4 <= ctx->arena_limit;
             const int par = single_wave ? (rounds & 1) : 0;
             if (!single_wave) {
                 for (int q = 0; q < 2; ++q)

@@ -13,7 +13,7 @@
 // DIRECTION_MATRIX, 11 bits) are only written by a second fill of the final band, band-only and anti-diagonal major
 // (cell (i,j) at dir[(i+j) * wh + ((j-i+k) >> 1)]), followed by the traceback, one thread per pair.
 // The non-affine entry point is not offered: update_internal_cell never sets costDiag there (:796, :855-856), every
-// interior cell gets cost 0 and the traceback leaves the band and raises (oracle/newkk_oracle.c, tests/test_newkk.py).
+// interior cell gets cost 0 and the traceback leaves the band and raises (tests/test_newkk.py shows it on the compiled reference).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>

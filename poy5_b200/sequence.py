@@ -191,6 +191,22 @@ def median_2(ctx, cm, rows_a, rows_b, with_gaps):
     return [out[out_off[p]:out_off[p] + out_len[p]] for p in range(n)]
 
 
+def median_3(ctx, cm3, rows_a, rows_b, rows_c):
+    """The column-wise three-way median of Sequence.Align.align_3_powell_inter (src/sequence.ml:1342-1369) over lists of
+    three aligned rows: -> (medians with the leading gap restored, medians with gaps, sum of Three_D.cost per triple)."""
+    a, b, off, lens = _pack_rows(rows_a, rows_b)
+    c, _, _, _ = _pack_rows(rows_c, rows_c)
+    n = len(lens)
+    out_off = off + np.arange(n, dtype=np.int64)
+    tot = int(lens.sum()) + n + 1
+    med = np.zeros(tot, np.uint8); medwg = np.zeros(tot, np.uint8)
+    out_len = np.zeros(n, np.int32); cost3 = np.zeros(n, np.int32)
+    ctx.check(ctx.L.poy_batch_median_3(ctx.h, cm3.h, n, _ptr(a), _ptr(b), _ptr(c), _ptr(off), _ptr(lens), _ptr(out_off), _ptr(med),
+                                       _ptr(medwg), _ptr(out_len), _ptr(cost3)))
+    return ([med[out_off[p]:out_off[p] + out_len[p]] for p in range(n)],
+            [medwg[out_off[p]:out_off[p] + lens[p]] for p in range(n)], cost3)
+
+
 def union(ctx, rows_a, rows_b):
     """Sequence.Align.union (src/sequence.ml:1150-1177 -> algn_CAML_union)."""
     a, b, off, lens = _pack_rows(rows_a, rows_b)
