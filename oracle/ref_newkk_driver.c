@@ -88,7 +88,7 @@ int ref_newkk_align(void *cm, void *m, const unsigned char *s1, int len1, const 
 }
 
 /* ---- powell_3D_align (src/ukkCommon.c:109-145; Sequence.Align.align_3_powell, src/sequence.ml:1309-1340) ----
- * The three inputs are passed WITHOUT the leading gap (the OCaml caller strips it, src/sequence.ml:1321-1326);
+ * The three inputs are complete sequences: copySequence (src/ukkCommon.c:86-107) skips element 0, the leading gap;
  * r1..r3 must hold len1+len2+len3 bytes each; lens[3] = lengths of the three aligned rows. */
 int ref_powell_3d(const unsigned char *s1, int len1, const unsigned char *s2, int len2, const unsigned char *s3, int len3,
                   int mm, int go, int ge, unsigned char *r1, unsigned char *r2, unsigned char *r3, int *lens) {

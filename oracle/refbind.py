@@ -174,7 +174,7 @@ class RefLib:
 
     # -- powell_3D_align (src/ukkCommon.c:109) ------------------------------------------
     def powell_3d(self, s1, s2, s3, mm, go, ge):
-        """inputs WITHOUT the leading gap; -> (cost, row1, row2, row3)"""
+        """inputs WITH the leading gap (copySequence skips element 0); -> (cost, row1, row2, row3)"""
         ss = [np.ascontiguousarray(x, np.uint8) for x in (s1, s2, s3)]
         cap = sum(len(x) for x in ss) + 3
         outs = [np.zeros(cap, np.uint8) for _ in range(3)]

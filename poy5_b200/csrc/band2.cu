@@ -196,7 +196,10 @@ __device__ __forceinline__ void store_dir(uint8_t *p, unsigned packed) {
 // resident CTAs the register allocation aims at: the replicated table (32 KB) allows 6 per SM; the 4-warp class of
 // gap-free pairs is the one where a few registers decide between 4 and 5
 template <int NW, bool GFK> struct MinBlocks {
-    static constexpr int v = GFK ? (NW == 4 ? 5 : 1) : (NW == 4 ? 3 : NW == 3 ? 4 : NW == 6 ? 2 : 1);
+    // pairs with gap-bit symbols: 128 registers per thread (no spills since the surcharge records), i.e. two resident
+    // CTAs of 8 warps / four of 4 warps per SM instead of one / three
+    static constexpr int v = GFK ? (NW == 4 ? 5 : 1)
+                                 : (NW == 8 ? 2 : NW == 4 ? 4 : NW == 3 ? 5 : NW == 5 ? 3 : NW == 6 ? 2 : NW == 2 ? 8 : NW == 1 ? 2 : 1);
 };
 
 template <int D, int NW, int WPB, bool GFK, bool DIR>

@@ -799,9 +799,10 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             }
             // Rounds that fit the arena in one wave alternate between two arenas / job arrays, so that the traceback
             // of the pairs that stop in this round (own stream) overlaps the fills of the next one.
-            // (the second arena stays small -- a quarter of the limit -- so that the two together never outgrow what a
-            // context was allowed before: large rounds are throughput bound and gain nothing from the overlap)
-            const bool single_wave = async_tb && pos == 0 && end == order.size() && (uint64_t)used * 4 <= ctx->arena_limit;
+            // (the second arena stays small -- at most 1 GiB and a quarter of the limit -- so that a context never outgrows
+            // what it was allowed before: large rounds are throughput bound and gain nothing from the overlap)
+            const bool single_wave = async_tb && pos == 0 && end == order.size() && (uint64_t)used * 4 <= ctx->arena_limit &&
+                                     (uint64_t)used <= (1ull << 30);
             const int par = single_wave ? (rounds & 1) : 0;
             if (!single_wave) {
                 for (int q = 0; q < 2; ++q)

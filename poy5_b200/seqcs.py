@@ -110,6 +110,30 @@ class DOS:
         return out
 
 
+def dist_2(ctx, h, pool, n, a, b, use_ukk=False):
+    """DOS.dist_2 h n a b use_ukk (src/seqCS.ml:1181-1198): the cost of joining node `n` between `a` and `b`:
+    tmp = n itself if a is empty, else Sequence.Align.full_median_2 a b under c2_FULL; cost = Sequence.Align.cost_2 n tmp
+    (Sequence.NewkkAlign.cost_2 when use_ukk) under c2_FULL.  n, a, b: pool indices.  -> int64[len(n)]"""
+    from .api import Pool
+    from .sequence import NewkkAlign
+    n = np.ascontiguousarray(n, np.int32); a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+    m = len(n)
+    empty = _is_empty(pool)
+    ea = empty[a]
+    tmp = [None] * m
+    for p in np.flatnonzero(ea):
+        tmp[p] = pool.seq(int(n[p]))
+    idx = np.flatnonzero(~ea)
+    if len(idx):
+        for q, med in zip(idx, Align.full_median_2(ctx, h.c2_full, pool, a[idx], b[idx])):
+            tmp[q] = med
+    scratch = Pool(ctx, [pool.seq(int(x)) for x in n] + [np.asarray(t, np.uint8) for t in tmp])
+    i0 = np.arange(m, dtype=np.int32); i1 = i0 + m
+    cost = (NewkkAlign.cost_2 if use_ukk else Align.cost_2)(ctx, h.c2_full, scratch, i0, i1)
+    scratch.close()
+    return np.asarray(cost, np.int64)
+
+
 def median_3_union(ctx, cm2, pool, parent, aligned_a, aligned_b):
     """DOS.median_3_union (src/seqCS.ml:1151-1178): the live three-sequence path used for final-state
     assignment.  For every node: union of its two aligned children

@@ -85,6 +85,15 @@ class Align:
         return res
 
     @staticmethod
+    def full_median_2(ctx, cm, pool, a, b):
+        """Sequence.Align.full_median_2 (src/sequence.ml:1136-1142): affine -> the median of align_affine_3; otherwise
+        align_2 followed by median_2 of the two rows.  -> list of sequences"""
+        if cm.host.cost_model_type == 1:
+            return Align.align_affine_3(ctx, cm, pool, a, b, want=("median",))["median"]
+        r = Align.align_2(ctx, cm, pool, a, b)
+        return median_2(ctx, cm, r["res_a"], r["res_b"], False)
+
+    @staticmethod
     def align_affine_3(ctx, cm, pool, a, b, want=("median", "medianwg", "resi", "resj"), stats=False):
         """Sequence.Align.align_affine_3 (src/sequence.ml:633-649): puts the shorter sequence first,
         passes `swaped`, and un-swaps the two aligned rows on return.  Returns a dict with

@@ -65,6 +65,30 @@ class SampleRecorder:
         self.km += len(pairs)
         return r
 
+    def median_ids(self, a, b):
+        ids, ln, c2 = self.b.median_ids(a, b)
+        if len(self.med) < self.cap:
+            first = (-self.km) % self.em
+            pick = list(range(first, len(a), self.em))[: self.cap - len(self.med)]
+            if pick:
+                got = self.b.store.read(np.array([x for q in pick for x in (a[q], b[q], ids[q])], np.int32))
+                for j, q in enumerate(pick):
+                    self.med.append((got[3 * j].copy(), got[3 * j + 1].copy(), got[3 * j + 2].copy(), int(c2[q])))
+        self.km += len(a)
+        return ids, ln, c2
+
+    def distance_ids(self, a, b, la, lb):
+        r = self.b.distance_ids(a, b, la, lb)
+        if len(self.dis) < self.cap:
+            first = (-self.kd) % self.ed
+            pick = list(range(first, len(a), self.ed))[: self.cap - len(self.dis)]
+            if pick:
+                got = self.b.store.read(np.array([x for q in pick for x in (a[q], b[q])], np.int32))
+                for j, q in enumerate(pick):
+                    self.dis.append((got[2 * j].copy(), got[2 * j + 1].copy(), int(r[q])))
+        self.kd += len(a)
+        return r
+
     def distance(self, pairs):
         r = self.b.distance(pairs)
         if len(self.dis) < self.cap:

@@ -137,6 +137,22 @@ class StoreBackend:
         self.n_distance += n
         return self.store.distance(self.h, a, b).tolist()
 
+    # the same two calls on id arrays: what the vectorised swap-round driver (spr_round on a node store) uses, so that
+    # a neighbourhood of 10^5 candidates costs numpy index arithmetic on the host instead of one Python object per sequence
+    def median_ids(self, a, b):
+        """int32 id arrays -> (ids, lengths, cost2) arrays of the medians, appended to the store"""
+        if len(a) == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32)
+        self.n_median += len(a)
+        return self.store.median(self.h, np.ascontiguousarray(a, np.int32), np.ascontiguousarray(b, np.int32))
+
+    def distance_ids(self, a, b, la, lb):
+        if len(a) == 0:
+            return np.zeros(0, np.int32)
+        self.cells_distance += int(((np.asarray(la, np.int64) - 1) * (np.asarray(lb, np.int64) - 1)).sum())
+        self.n_distance += len(a)
+        return self.store.distance(self.h, np.ascontiguousarray(a, np.int32), np.ascontiguousarray(b, np.int32))
+
     def single(self, pairs):
         """to_single is an O(n) pass per tree: sequences go through the host-array path (seqcs.to_single)"""
         from .api import Pool
@@ -175,15 +191,16 @@ class Tree:
     def edges(self):
         return sorted((u, v) for u in self.adj for v in self.adj[u] if u < v)
 
-    def new_node(self):
-        return max(self.adj) + 1
+    def new_node(self, n_leaves=0):
+        """id for a new internal node: above every node in the tree AND above the leaf ids 0..n_leaves-1, which may
+        not have been inserted yet"""
+        return max(max(self.adj) + 1, int(n_leaves))
 
-    def insert_leaf(self, leaf, edge):
+    def insert_leaf(self, leaf, edge, n_leaves=0):
         """split `edge` with a new internal node and hang `leaf` on it"""
         u, v = edge
-        w = self.new_node()
-        self.remove_edge(u, v)
-        self.add_edge(u, w); self.add_edge(w, v); self.add_edge(w, leaf)
+        w = self.new_node(max(n_leaves, leaf + 1))
+        self.remove_edge(u, v); self.add_edge(u, w); self.add_edge(w, v); self.add_edge(w, leaf)
         return w
 
     def component(self, start, banned):
@@ -507,6 +524,8 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
     dms = all_directions(tree, loci, backend) if dms is None else dms
     prunings = spr_prunings(tree, n) if prunings is None else list(prunings)
     nl = len(loci)
+    if hasattr(backend, "median_ids") and not merge_edges:
+        return _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where)
     best, ncand, naln = None, 0, 0
     for c0 in range(0, len(prunings), chunk):
         part = prunings[c0:c0 + chunk]
@@ -559,6 +578,85 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
         ncand += len(meta)
         if mark is not None:
             backend.release(mark)
+    if where is not None:
+        where.append(None if best is None else best[4])
+    if best is None:
+        return None, None, 0, naln
+    return best[0], (best[1], best[2]), ncand, naln
+
+
+def _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where):
+    """`spr_round` for a backend whose sequences are ids into a device-resident node store: the same batches (one median
+    batch per level of the chunk, one edge-median batch, one distance batch), assembled with numpy index arrays.
+    Per pruning the rest tree is numbered locally (x1, x2, then BFS levels); `up_*[l, node]` hold id / length /
+    accumulated cost of the median that looks away from the cut, `dm_*[l, edge]` those of the unbroken tree."""
+    nl = len(loci)
+    edges = list(dms[0].keys())
+    eidx = {e: i for i, e in enumerate(edges)}
+    dm_id = np.array([[dm[e][0].id for e in edges] for dm in dms], np.int32)
+    dm_len = np.array([[dm[e][0].n for e in edges] for dm in dms], np.int32)
+    dm_cost = np.array([[dm[e][1] for e in edges] for dm in dms], np.int64)
+    best, ncand, naln = None, 0, 0
+    for c0 in range(0, len(prunings), chunk):
+        part = prunings[c0:c0 + chunk]
+        mark = backend.mark()
+        plans = []
+        for (u, v) in part:
+            x1, x2, lv, par = _side_plan(tree, u, v)
+            loc = {x1: 0, x2: 1}
+            for lvl in lv:
+                for c in lvl:
+                    loc[c] = len(loc)
+            nn = len(loc)
+            up_id = np.zeros((nl, nn), np.int32); up_len = np.zeros((nl, nn), np.int32); up_cost = np.zeros((nl, nn), np.int64)
+            for q, e in ((0, eidx[(x2, u)]), (1, eidx[(x1, u)])):
+                up_id[:, q] = dm_id[:, e]; up_len[:, q] = dm_len[:, e]; up_cost[:, q] = dm_cost[:, e]
+            levels = [(np.array([loc[c] for c in lvl], np.int64), np.array([loc[par[c][0]] for c in lvl], np.int64),
+                       np.array([eidx[(par[c][1], par[c][0])] for c in lvl], np.int64)) for lvl in lv]
+            joins = [(par[c][0], c) for lvl in lv for c in lvl]
+            jc = np.array([loc[c] for _, c in joins], np.int64)
+            je = np.array([eidx[(c, a)] for a, c in joins], np.int64)
+            plans.append(dict(up_id=up_id, up_len=up_len, up_cost=up_cost, levels=levels, joins=joins, jc=jc, je=je, ev=eidx[(v, u)]))
+        for d in range(max(len(p["levels"]) for p in plans)):
+            act = [p for p in plans if d < len(p["levels"])]
+            a = np.concatenate([p["up_id"][:, p["levels"][d][1]].ravel() for p in act])
+            b = np.concatenate([dm_id[:, p["levels"][d][2]].ravel() for p in act])
+            ids, ln, c2 = backend.median_ids(a, b)
+            naln += len(a)
+            at = 0
+            for p in act:
+                ci, pi, si = p["levels"][d]
+                m = nl * len(ci)
+                p["up_id"][:, ci] = ids[at:at + m].reshape(nl, -1); p["up_len"][:, ci] = ln[at:at + m].reshape(nl, -1)
+                p["up_cost"][:, ci] = c2[at:at + m].reshape(nl, -1).astype(np.int64) + p["up_cost"][:, pi] + dm_cost[:, si]
+                at += m
+        a = np.concatenate([p["up_id"][:, p["jc"]].ravel() for p in plans])
+        b = np.concatenate([dm_id[:, p["je"]].ravel() for p in plans])
+        ids, ln, c2 = backend.median_ids(a, b)
+        naln += len(a)
+        at = 0
+        for p in plans:
+            m = nl * len(p["jc"])
+            p["em_id"] = ids[at:at + m].reshape(nl, -1); p["em_len"] = ln[at:at + m].reshape(nl, -1)
+            p["em_cost"] = c2[at:at + m].reshape(nl, -1).astype(np.int64) + p["up_cost"][:, p["jc"]] + dm_cost[:, p["je"]]
+            at += m
+        ca = np.concatenate([np.repeat(dm_id[:, p["ev"]][:, None], len(p["jc"]), axis=1).ravel() for p in plans])
+        la = np.concatenate([np.repeat(dm_len[:, p["ev"]][:, None], len(p["jc"]), axis=1).ravel() for p in plans])
+        cb = np.concatenate([p["em_id"].ravel() for p in plans]); lb = np.concatenate([p["em_len"].ravel() for p in plans])
+        dist = np.asarray(backend.distance_ids(ca, cb, la, lb), np.int64)
+        naln += len(ca)
+        at = 0
+        for k, (p, (u, v)) in enumerate(zip(plans, part)):
+            nj = len(p["jc"])
+            m = nl * nj
+            est = dist[at:at + m].reshape(nl, nj).sum(axis=0) + p["em_cost"].sum(axis=0) + int(dm_cost[:, p["ev"]].sum())
+            at += m
+            if nj:
+                q = int(np.argmin(est))                    # first minimum: ties resolve to the first join edge
+                if best is None or int(est[q]) < best[0]:
+                    best = (int(est[q]), (u, v), p["joins"][q], ncand + q, (c0 + k, q))
+            ncand += nj
+        backend.release(mark)
     if where is not None:
         where.append(None if best is None else best[4])
     if best is None:
@@ -685,6 +783,7 @@ def tbr_round_multi(tree, loci, backend, dms=None, breaks=None, chunk=16):
     best, ncand, naln = None, 0, 0
     for c0 in range(0, len(breaks), chunk):
         part = breaks[c0:c0 + chunk]
+        mark = backend.mark() if hasattr(backend, "mark") else None     # node store: the chunk's medians are temporaries
         sides = [(s, t, _side_plan(tree, s, t)) for (u, v) in part for (s, t) in ((u, v), (v, u))]
         ups = [None if pl is None else [{pl[0]: dm[(pl[1], s)], pl[1]: dm[(pl[0], s)]} for dm in dms] for s, t, pl in sides]
         depth = max([len(pl[2]) for _, _, pl in sides if pl is not None], default=0)
@@ -741,6 +840,8 @@ def tbr_round_multi(tree, loci, backend, dms=None, breaks=None, chunk=16):
             if best is None or int(est[q]) < best[0]:
                 best = (int(est[q]), meta[q][:3])
         ncand += len(meta)
+        if mark is not None:
+            backend.release(mark)
     if best is None:
         return None, None, 0, naln
     return best[0], best[1], ncand, naln

@@ -1,0 +1,11 @@
+#!/bin/bash
+# gpurun with retries while the pod has no free GPU slot (exit code 3: nothing charged).
+# usage: scripts/gpurun_retry.sh [gpurun options] -- 'command'
+for attempt in $(seq 1 20); do
+    /usr/local/graft/bin/gpurun "$@"
+    rc=$?
+    if [ $rc -ne 3 ]; then exit $rc; fi
+    echo "[gpurun_retry] attempt $attempt: no slot, sleeping 90 s" >&2
+    sleep 90
+done
+exit 3

@@ -65,6 +65,47 @@ class OracleBackend:
         return out
 
 
+class OracleStoreBackend:
+    """The id-array interface of treesearch.StoreBackend (put / median_ids / distance_ids / mark / release / fetch) on top
+    of the CPU checker: drives the vectorised swap-round driver without a GPU."""
+
+    def __init__(self, port, full, orig):
+        from poy5_b200.treesearch import Node
+        self.Node = Node
+        self.ob = OracleBackend(port, full, orig)
+        self.seqs = []
+
+    def put(self, seqs):
+        first = len(self.seqs)
+        self.seqs += [np.asarray(s, np.uint8) for s in seqs]
+        return [self.Node(first + i, len(s)) for i, s in enumerate(seqs)]
+
+    def fetch(self, nodes):
+        return [self.seqs[x.id] for x in nodes]
+
+    def mark(self):
+        return len(self.seqs)
+
+    def release(self, mark):
+        del self.seqs[mark:]
+
+    def median(self, pairs):
+        res = self.ob.median([(self.seqs[a.id], self.seqs[b.id]) for a, b in pairs])
+        return [(self.put([m])[0], c) for m, c in res]
+
+    def distance(self, pairs):
+        return self.ob.distance([(self.seqs[a.id], self.seqs[b.id]) for a, b in pairs])
+
+    def median_ids(self, a, b):
+        res = self.ob.median([(self.seqs[int(x)], self.seqs[int(y)]) for x, y in zip(a, b)])
+        nodes = self.put([m for m, _ in res])
+        return (np.array([x.id for x in nodes], np.int32), np.array([x.n for x in nodes], np.int32),
+                np.array([c for _, c in res], np.int32))
+
+    def distance_ids(self, a, b, la, lb):
+        return np.array(self.ob.distance([(self.seqs[int(x)], self.seqs[int(y)]) for x, y in zip(a, b)]), np.int32)
+
+
 def replay_sample(med, dis, regime):
     """CPU checker replay of a recorded sample of the swap-evaluation workload (poy5_b200.swap_eval.SampleRecorder):
     med = [(a, b, median, cost2)], dis = [(a, b, cost)] as host arrays.  -> parity dict"""

@@ -177,3 +177,39 @@ def test_cuda_newkk_errors(ctx):
     st = ctx.L.poy_batch_newkk_align(ctx.h, cm.h, pool.h, 1, one.ctypes.data, zero.ctypes.data, None, None, cost.ctypes.data, None, None,
                                      None, None)
     assert st == -4     # POY_ERR_ORDER: "newkkonen.newkk_algn, s1 len > s2 len"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_ukk", [False, True])
+def test_dos_dist_2(ctx, port, use_ukk):
+    """DOS.dist_2 (src/seqCS.ml:1181-1198): full_median_2 of (a, b) then cost_2 -- Sequence.NewkkAlign.cost_2 when
+    use_ukk -- of n against it, vs the same composition on the CPU checker"""
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.seqcs import Heuristic, dist_2
+    from tests.helpers import oracle_align
+    t2d = Two_D.of_transformations_and_gaps(1, 1, 3)
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    pf = port.cm(full)
+    h = Heuristic(pb.CostModel(ctx, t2d.full), pb.CostModel(ctx, t2d.original))
+    rng = np.random.default_rng(12)
+    seqs = []
+    for t in range(40):
+        anc = synth.random_seq(rng, int(rng.integers(20, 200)))
+        trio = [synth.with_gap(synth.decorate(rng, synth.evolve(rng, anc, 0.1, 0.03), 0.05, 0.05 * (t % 2))) for _ in range(3)]
+        if t % 9 == 0:
+            trio[1] = np.array([16], np.uint8)          # empty a: tmp = n itself
+        seqs += trio
+    pool = pb.Pool(ctx, seqs)
+    idx = np.arange(0, len(seqs), 3, dtype=np.int32)
+    got = dist_2(ctx, h, pool, idx, idx + 1, idx + 2, use_ukk=use_ukk)
+    for q, p in enumerate(idx):
+        n_, a, b = seqs[p], seqs[p + 1], seqs[p + 2]
+        tmp = n_ if (a == 16).all() else oracle_align(port, pf, a, b)[1]
+        if use_ukk:
+            s1, s2 = (tmp, n_) if len(n_) > len(tmp) else (n_, tmp)
+            want = port.newkk_align(pf, s1, s2, 0)[0]
+        else:
+            want = port.cost_affine(pf, n_, tmp)
+        assert got[q] == want, (q, use_ukk)
+    pool.close()

@@ -205,6 +205,45 @@ def test_spr_sharded_by_pruning_gloo(port):
         assert r == single
 
 
+def test_spr_lanes_match_single(port):
+    """several concurrent lanes on one rank (own backend each, prunings dealt like ranks): same result as one lane, with
+    and without the edge medians merged into the level batches"""
+    from oracle.port import Port
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    b = OracleBackend(port, full, orig)
+    loci = loci_taxa(9, 7, (40, 55))
+    tree = treesearch.wagner_build(loci[0], b)
+    dms = treesearch.all_directions(tree, loci, b)
+    pr = treesearch.spr_prunings(tree, 7)
+    single = treesearch.spr_round(tree, loci, b, dms=dms, prunings=pr, chunk=1000)
+    merged = treesearch.spr_round(tree, loci, b, dms=dms, prunings=pr, chunk=4, merge_edges=True)
+    assert merged == single
+    lanes = [(OracleBackend(Port(), full, orig), loci, dms) for _ in range(3)]      # one checker scratch per thread
+    got = treesearch.spr_round_sharded(tree, loci, b, dms, pr, chunk=2, rank=0, world=1, lanes=lanes)
+    assert got == single
+
+
+def test_vectorised_spr_round_matches_generic(port):
+    """the id-array driver that runs on the node store (treesearch._spr_round_ids) issues the same medians / distances as
+    the generic per-object driver: same estimate, move, counters, `where`; chunking does not matter"""
+    from tests.oracle_backend import OracleStoreBackend
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    host_loci = loci_taxa(17, 9, (40, 55, 48))
+    ob = OracleBackend(port, full, orig)
+    tree = treesearch.wagner_build(host_loci[0], ob)
+    dms_h = treesearch.all_directions(tree, host_loci, ob)
+    pr = treesearch.spr_prunings(tree, 9)
+    w0 = []
+    generic = treesearch.spr_round(tree, host_loci, ob, dms=dms_h, prunings=pr, chunk=1000, where=w0)
+    sb = OracleStoreBackend(port, full, orig)
+    loci = [sb.put(ls) for ls in host_loci]
+    dms = treesearch.all_directions(tree, loci, sb)
+    for chunk in (1000, 3):
+        w1 = []
+        got = treesearch.spr_round(tree, loci, sb, dms=dms, prunings=pr, chunk=chunk, where=w1)
+        assert got == generic and w1 == w0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("go", [3, None])
 def test_store_backend_matches_oracle_replay(ctx, port, go):
@@ -284,6 +323,25 @@ def test_tbr_multi_oracle(port):
     # re-inserting at (merged, merged) restores the tree
     brk = [e for e in tree.edges() if e[0] >= n and e[1] >= n][0]
     assert treesearch.apply_tbr_multi(tree, (brk, "m", "m")).edges() == tree.edges()
+
+
+@pytest.mark.gpu
+def test_tbr_multi_store_backend_matches_oracle_replay(ctx, port):
+    """TBR round over several loci with incremental medians on both sides of the break, through the device-resident node
+    store: identical trees, estimate, move, counters and costs to the CPU checker's replay"""
+    import poy5_b200 as pb
+    from poy5_b200.cost_matrix import Two_D
+    from poy5_b200.seqcs import Heuristic
+    t2d = Two_D.of_transformations_and_gaps(1, 1, 3)
+    full, orig = cmo.dna_matrices(1, 1, 3)
+    h = Heuristic(pb.CostModel(ctx, t2d.full), pb.CostModel(ctx, t2d.original))
+    host_loci = loci_taxa(29, 8, (110, 140))
+    sb = treesearch.StoreBackend(ctx, h, cap_bytes=1 << 18, cap_seqs=256)
+    loci = [sb.put(ls) for ls in host_loci]
+    got = run_tbr_multi(sb, loci)
+    ref = run_tbr_multi(OracleBackend(port, full, orig), host_loci)
+    assert got == ref
+    sb.close()
 
 
 # ---- single assignment (pre-order pass after the downpass) ----
