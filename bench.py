@@ -49,8 +49,9 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle replay of the timed pairs")
     ap.add_argument("--no-swap", action="store_true", help="skip the strong-scaled swap-evaluation sub-record")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0] / [2] / [4] sub-records (N = 1 only)")
     ap.add_argument("--swap-prunings", type=int, default=0, help="SPR prunings of the swap-evaluation workload (whole job); 0 = the full neighbourhood")
-    ap.add_argument("--swap-chunk", type=int, default=192, help="prunings per candidate batch (bounds the node store of a rank)")
+    ap.add_argument("--swap-chunk", type=int, default=128, help="prunings per candidate batch (bounds the node store of a rank)")
     ap.add_argument("--swap-check", type=int, default=24, help="medians / distances replayed on the CPU checker")
     return ap.parse_args()
 
@@ -504,6 +505,10 @@ def main():
         del d_outs
         for ln in lanes:
             ln["h_outs"] = None
+        for ln in lanes[1:]:            # the second e2e lane holds tens of GB of direction arena: not needed any more
+            ln["cm"].close(); ln["ctx"].close()
+        del lanes[1:]
+        ctx.trim()
         torch.cuda.empty_cache()
         try:
             swap, sample = swap_eval.run(ctx, rank=rank, world=world, device=dev, prunings=args.swap_prunings, chunk=args.swap_chunk,
@@ -515,6 +520,41 @@ def main():
                 swap["parity"]["replay_s"] = time.perf_counter() - t5
         except Exception as e:          # reported, never hidden
             swap = dict(error="%s: %s" % (type(e).__name__, e))
+
+    # ---- the other BASELINE configurations as short, parity-sampled sub-records (single GPU only).  They run in a child
+    # process with a time-out: a failure of a side record must never take the headline line with it. -------------------
+    configs = None
+    if world == 1 and not args.no_configs and not args.no_swap:
+        import pickle
+        from tests.oracle_backend import replay_sample, replay_triplets
+        configs = {}
+        tmp = tempfile.NamedTemporaryFile(suffix=".pkl", delete=False); tmp.close()
+        torch.cuda.empty_cache()
+        try:
+            subprocess.run([sys.executable, "-m", "poy5_b200.workloads", "--out", tmp.name, "--device", str(local_rank),
+                            "--regime", ",".join(str(x) for x in REGIME)], cwd=ROOT, timeout=240, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL)
+        except Exception as e:
+            configs["note"] = "child process: %s" % type(e).__name__
+        try:
+            with open(tmp.name, "rb") as f:
+                got = pickle.load(f)
+        except Exception:
+            got = {}
+        for name, val in got.items():
+            if isinstance(val, dict):
+                configs[name] = val; continue
+            rec_, sample_ = val
+            try:
+                if sample_ is not None:
+                    rec_["parity"] = replay_triplets(sample_, REGIME) if name == "configs[2]" else replay_sample(sample_[0], sample_[1], REGIME)
+            except Exception as e:
+                rec_["parity"] = dict(error="%s: %s" % (type(e).__name__, e))
+            configs[name] = rec_
+        try:
+            os.unlink(tmp.name)
+        except OSError:
+            pass
 
     if rank == 0:
         # dominant kernels on the longest length: the cost-only wavefront (k_cost_affine) and the banded fill (k_band2)
@@ -576,7 +616,8 @@ def main():
                                         note="band on: cells inside the Ukkonen bands summed over every fill of the threshold-doubling "
                                              "schedule (poy_ctx_stats); band off: the full matrices"),
                     breakdown_interior=interior, clocks=clocks, e2e=e2e,
-                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, parity=parity, swap_eval=swap)
+                    gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, parity=parity, swap_eval=swap,
+                    other_configs=configs)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

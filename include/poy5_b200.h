@@ -62,6 +62,9 @@ POY_API const char *poy_status_string(poy_status s);
  * batches larger than the cap are processed in waves.  Default 8 GiB. */
 POY_API poy_status poy_ctx_set_arena_limit(poy_ctx *ctx, uint64_t bytes);
 POY_API poy_status poy_ctx_synchronize(poy_ctx *ctx);
+/* returns the context's grow-only device scratch (direction arenas, job arrays, cached pool blocks) to the driver; it is
+ * re-allocated on demand.  For callers that switch between workloads of very different shape. */
+POY_API poy_status poy_ctx_trim(poy_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py: gpu_launches) */
 POY_API uint64_t poy_ctx_launch_count(const poy_ctx *ctx);
 /* cumulative counters of this context (SURVEY.md 8d "additionally report cells_computed"): out[0] kernel launches,

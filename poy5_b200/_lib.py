@@ -55,6 +55,7 @@ def load():
     L.poy_status_string.restype = C.c_char_p
     L.poy_ctx_set_arena_limit.argtypes = [vp, C.c_uint64]
     L.poy_ctx_synchronize.argtypes = [vp]
+    L.poy_ctx_trim.argtypes = [vp]
     L.poy_ctx_launch_count.argtypes = [vp]
     L.poy_ctx_launch_count.restype = C.c_uint64
     L.poy_ctx_stats.argtypes = [vp, vp]
@@ -109,7 +110,7 @@ def load():
 
 
 EXPORTS = ["poy_ctx_create", "poy_ctx_destroy", "poy_last_error", "poy_status_string", "poy_ctx_set_arena_limit",
-           "poy_ctx_synchronize", "poy_ctx_launch_count", "poy_ctx_stats", "poy_cm_fill", "poy_cm_min_non0", "poy_cm_get_closest",
+           "poy_ctx_synchronize", "poy_ctx_trim", "poy_ctx_launch_count", "poy_ctx_stats", "poy_cm_fill", "poy_cm_min_non0", "poy_cm_get_closest",
            "poy_cm_upload", "poy_cm_free", "poy_pool_upload", "poy_pool_from_device", "poy_pool_free",
            "poy_batch_cost_affine", "poy_batch_cost_affine_dev", "poy_batch_align_affine",
            "poy_batch_align_affine_dev", "poy_batch_cost_linear", "poy_batch_align_linear", "poy_batch_median_2", "poy_batch_union",

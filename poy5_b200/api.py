@@ -28,6 +28,10 @@ class Context:
     def synchronize(self):
         self.check(self.L.poy_ctx_synchronize(self.h))
 
+    def trim(self):
+        """give the grow-only device scratch back to the driver (re-allocated on demand)"""
+        self.check(self.L.poy_ctx_trim(self.h))
+
     def set_arena_limit(self, nbytes):
         self.check(self.L.poy_ctx_set_arena_limit(self.h, int(nbytes)))
 

@@ -106,6 +106,23 @@ extern "C" poy_status poy_ctx_set_arena_limit(poy_ctx *ctx, uint64_t bytes) {
     ctx->arena_limit = bytes;
     return POY_OK;
 }
+// give the grow-only device scratch (direction arenas, job arrays, ...) and the block cache back to the driver;
+// everything is re-allocated on demand.  For callers that switch from one kind of workload to another.
+extern "C" poy_status poy_ctx_trim(poy_ctx *ctx) {
+    bind_device(ctx);
+    if (!ctx) return POY_ERR_ARG;
+    for (poy_ctx *c : { ctx, ctx->twin }) {
+        if (!c) continue;
+        cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->tb_stream);
+        for (int a = 0; a < 4; ++a) cudaStreamSynchronize(c->aux[a]);
+        for (int s = 0; s < 14; ++s)
+            if (c->d_scratch[s]) { cudaFree(c->d_scratch[s]); c->d_scratch[s] = nullptr; c->scratch_cap[s] = 0; }
+        for (int i = 0; i < c->cache_n; ++i) cudaFree(c->cache_ptr[i]);
+        c->cache_n = 0; c->cache_bytes = 0;
+    }
+    return POY_OK;
+}
+
 extern "C" poy_status poy_ctx_synchronize(poy_ctx *ctx) {
     bind_device(ctx);
     if (!ctx) return POY_ERR_ARG;

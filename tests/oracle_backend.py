@@ -120,3 +120,20 @@ def replay_sample(med, dis, regime):
         bad += int(c != oc)
     return dict(checked=len(med) + len(dis), checked_medians=len(med), checked_distances=len(dis), mismatches=int(bad),
                 against="oracle port (plain-C restatement of algn.c, pinned to the compiled reference)")
+
+
+def replay_triplets(sample, regime):
+    """CPU checker replay of recorded (parent, child 1, child 2, cost, median) triplets of the median_3_union path
+    (poy5_b200.workloads.config3): union of the aligned children, parent x union alignment, median_2"""
+    from oracle import cost_matrix_oracle as cmo
+    from oracle.port import Port
+    from tests.helpers import oracle_align
+    full, _ = cmo.dna_matrices(*regime)
+    P = Port(); pf = P.cm(full)
+    bad = 0
+    for p, c1, c2, cost, med in sample:
+        _, _, _, ra, rb = oracle_align(P, pf, c1, c2)
+        u = P.union(ra, rb)
+        oc, _, _, xa, xb = oracle_align(P, pf, p, u)
+        bad += not (oc == cost and np.array_equal(P.median_2(pf, xa, xb, False), med))
+    return dict(checked=len(sample), mismatches=int(bad), against="oracle port (plain-C restatement of algn.c, pinned to the compiled reference)")

@@ -376,3 +376,21 @@ def test_single_assignment_oracle(port):
             ps, xs = singles[l][parent[x]], singles[l][x]
             tot += 0 if np.array_equal(ps, xs) else int(port.cost_affine(pf, ps, xs))
     assert tot == single_cost
+
+
+@pytest.mark.gpu
+def test_baseline_config_workloads_small(ctx):
+    """poy5_b200.workloads (the configs[0] / [2] / [4] sub-records of bench.py) at toy sizes: every recorded sample
+    replays on the CPU checker without a mismatch"""
+    from poy5_b200 import workloads
+    from tests.oracle_backend import replay_sample, replay_triplets
+    r1, s1 = workloads.config1(ctx, taxa=7, L=120, check=8)
+    assert r1["tbr_candidates"] > 20 and r1["cost_after_tbr"] <= r1["build_cost"] + 50
+    p1 = replay_sample(s1[0], s1[1], (1, 1, 3))
+    assert p1["checked"] > 0 and p1["mismatches"] == 0
+    r3, s3 = workloads.config3(ctx, triplets=40, L=150, chunk=20, check=5)
+    p3 = replay_triplets(s3, (1, 1, 3))
+    assert p3["checked"] == 5 and p3["mismatches"] == 0 and r3["sum_cost"] > 0
+    r5, s5 = workloads.config5(ctx, taxa=12, L=300, prunings=3, check=6)
+    p5 = replay_sample(s5[0], s5[1], (1, 1, 3))
+    assert r5["spr_candidates"] > 10 and p5["checked"] > 0 and p5["mismatches"] == 0
