@@ -125,7 +125,7 @@ def replicate_lane(ctx_device, h_tables, host_loci, src_backend, dms, arena_byte
 
 
 def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=3000, seed=4, prunings=128, chunk=32,
-        check=24, regime=(1, 1, 3), backend=None, lanes=1):
+        check=24, regime=(1, 1, 3), backend=None, lanes=1, merge_edges=False):
     """One strong-scaled SPR neighbourhood sample.  Returns (record, sample): the `swap_eval` record on rank 0 (None
     elsewhere) and the recorded (medians, distances) sample for the caller's CPU-checker replay (bench.py /
     tests own the checker; nothing in this package touches it)."""
@@ -184,8 +184,9 @@ def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=30
     if lane_list is not None:
         lane_list[0] = (rec, loci, dms)
     barrier(); t3 = time.perf_counter()
+    timing = {}
     est, move, ncand, naln = treesearch.spr_round_sharded(tree, loci, rec, dms, pr, chunk=chunk, rank=rank, world=world, device=device,
-                                                          lanes=lane_list)
+                                                          lanes=lane_list, merge_edges=merge_edges, timing=timing)
     for c, _ in lane_ctx:
         c.synchronize()
     barrier(); t4 = time.perf_counter()
@@ -193,6 +194,13 @@ def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=30
     nm, nd, cells = sb.n_median - m0, sb.n_distance - d0, sb.cells_distance - c0
     for _, b in lane_ctx:
         nm += b.n_median; nd += b.n_distance; cells += b.cells_distance
+    per_rank = None
+    if dist is not None and timing:
+        import torch
+        mine_t = torch.tensor([timing["local_seconds"], float(timing["local_prunings"])], dtype=torch.float64, device=device)
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        per_rank = [dict(seconds=round(float(x[0]), 3), prunings=int(x[1])) for x in allt]
     if dist is not None:
         import torch
         tt = torch.tensor([secs], dtype=torch.float64, device=device)
@@ -219,7 +227,7 @@ def run(ctx, rank=0, world=1, device=None, taxa=200, nloci=5, lmin=1000, lmax=30
                    sharding="prunings dealt to ranks by LPT on rest-tree size; 2 MIN + 1 SUM all-reduce per round",
                    timed="incremental medians + edge medians + cost-only distances + best-candidate reduction, max over ranks (host clock "
                          "between device-synchronised barriers)",
-                   node_store_bytes=sb.store.nbytes)
+                   node_store_bytes=sb.store.nbytes, per_rank=per_rank, merge_edges=bool(merge_edges))
     sample = (rec.med, rec.dis) if (check and rank == 0) else None
     for c, b in lane_ctx:
         b.close(); c.close()

@@ -506,6 +506,15 @@ def spr_prunings(tree, n_leaves):
     return out
 
 
+def _even_chunk(n, chunk):
+    """`chunk` is an upper bound (memory); the prunings are cut into equal chunks, because every chunk pays the same
+    latency-bound chain of median levels however few prunings share it"""
+    if n <= 0:
+        return max(1, chunk)
+    k = (n + chunk - 1) // chunk
+    return (n + k - 1) // k
+
+
 def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None, merge_edges=False):
     """One SPR neighbourhood over several loci.  For the pruning (u, v) the rest tree is u's side with u suppressed
     (its neighbours x1, x2 joined); only the medians that *see* the cut are recomputed, top-down from the cut:
@@ -524,9 +533,10 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
     dms = all_directions(tree, loci, backend) if dms is None else dms
     prunings = spr_prunings(tree, n) if prunings is None else list(prunings)
     nl = len(loci)
-    if hasattr(backend, "median_ids") and not merge_edges:
-        return _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where)
+    if hasattr(backend, "median_ids"):
+        return _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where, merge_edges)
     best, ncand, naln = None, 0, 0
+    chunk = _even_chunk(len(prunings), chunk)
     for c0 in range(0, len(prunings), chunk):
         part = prunings[c0:c0 + chunk]
         mark = backend.mark() if hasattr(backend, "mark") else None     # node store: the chunk's medians are temporaries
@@ -585,7 +595,7 @@ def spr_round(tree, loci, backend, dms=None, prunings=None, chunk=64, where=None
     return best[0], (best[1], best[2]), ncand, naln
 
 
-def _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where):
+def _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where, merge_edges=False):
     """`spr_round` for a backend whose sequences are ids into a device-resident node store: the same batches (one median
     batch per level of the chunk, one edge-median batch, one distance batch), assembled with numpy index arrays.
     Per pruning the rest tree is numbered locally (x1, x2, then BFS levels); `up_*[l, node]` hold id / length /
@@ -597,6 +607,7 @@ def _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where):
     dm_len = np.array([[dm[e][0].n for e in edges] for dm in dms], np.int32)
     dm_cost = np.array([[dm[e][1] for e in edges] for dm in dms], np.int64)
     best, ncand, naln = None, 0, 0
+    chunk = _even_chunk(len(prunings), chunk)
     for c0 in range(0, len(prunings), chunk):
         part = prunings[c0:c0 + chunk]
         mark = backend.mark()
@@ -617,10 +628,26 @@ def _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where):
             jc = np.array([loc[c] for _, c in joins], np.int64)
             je = np.array([eidx[(c, a)] for a, c in joins], np.int64)
             plans.append(dict(up_id=up_id, up_len=up_len, up_cost=up_cost, levels=levels, joins=joins, jc=jc, je=je, ev=eidx[(v, u)]))
-        for d in range(max(len(p["levels"]) for p in plans)):
+        depth = max(len(p["levels"]) for p in plans)
+        for p in plans:
+            nj = len(p["jc"])
+            p["em_id"] = np.zeros((nl, nj), np.int32); p["em_len"] = np.zeros((nl, nj), np.int32); p["em_cost"] = np.zeros((nl, nj), np.int64)
+            p["jstart"] = np.concatenate([[0], np.cumsum([len(l_[0]) for l_ in p["levels"]])]).astype(np.int64)   # joins are in level order
+        for d in range(depth + 1):
+            # level d of the dependent medians; with merge_edges also the edge medians of the join edges below level d-1
+            # (filler for the latency-bound chain), otherwise all edge medians in one last batch
             act = [p for p in plans if d < len(p["levels"])]
-            a = np.concatenate([p["up_id"][:, p["levels"][d][1]].ravel() for p in act])
-            b = np.concatenate([dm_id[:, p["levels"][d][2]].ravel() for p in act])
+            if merge_edges:
+                eact = [(p, int(p["jstart"][d - 1]), int(p["jstart"][d])) for p in plans if 0 < d <= len(p["levels"])]
+            else:
+                eact = [(p, 0, len(p["jc"])) for p in plans] if d == depth else []
+            parts_a = [p["up_id"][:, p["levels"][d][1]].ravel() for p in act] + [p["up_id"][:, p["jc"][j0:j1]].ravel() for p, j0, j1 in eact]
+            parts_b = [dm_id[:, p["levels"][d][2]].ravel() for p in act] + [dm_id[:, p["je"][j0:j1]].ravel() for p, j0, j1 in eact]
+            if not parts_a:
+                continue
+            a = np.concatenate(parts_a); b = np.concatenate(parts_b)
+            if len(a) == 0:
+                continue
             ids, ln, c2 = backend.median_ids(a, b)
             naln += len(a)
             at = 0
@@ -630,16 +657,12 @@ def _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where):
                 p["up_id"][:, ci] = ids[at:at + m].reshape(nl, -1); p["up_len"][:, ci] = ln[at:at + m].reshape(nl, -1)
                 p["up_cost"][:, ci] = c2[at:at + m].reshape(nl, -1).astype(np.int64) + p["up_cost"][:, pi] + dm_cost[:, si]
                 at += m
-        a = np.concatenate([p["up_id"][:, p["jc"]].ravel() for p in plans])
-        b = np.concatenate([dm_id[:, p["je"]].ravel() for p in plans])
-        ids, ln, c2 = backend.median_ids(a, b)
-        naln += len(a)
-        at = 0
-        for p in plans:
-            m = nl * len(p["jc"])
-            p["em_id"] = ids[at:at + m].reshape(nl, -1); p["em_len"] = ln[at:at + m].reshape(nl, -1)
-            p["em_cost"] = c2[at:at + m].reshape(nl, -1).astype(np.int64) + p["up_cost"][:, p["jc"]] + dm_cost[:, p["je"]]
-            at += m
+            for p, j0, j1 in eact:
+                m = nl * (j1 - j0)
+                p["em_id"][:, j0:j1] = ids[at:at + m].reshape(nl, -1); p["em_len"][:, j0:j1] = ln[at:at + m].reshape(nl, -1)
+                p["em_cost"][:, j0:j1] = (c2[at:at + m].reshape(nl, -1).astype(np.int64) + p["up_cost"][:, p["jc"][j0:j1]]
+                                          + dm_cost[:, p["je"][j0:j1]])
+                at += m
         ca = np.concatenate([np.repeat(dm_id[:, p["ev"]][:, None], len(p["jc"]), axis=1).ravel() for p in plans])
         la = np.concatenate([np.repeat(dm_len[:, p["ev"]][:, None], len(p["jc"]), axis=1).ravel() for p in plans])
         cb = np.concatenate([p["em_id"].ravel() for p in plans]); lb = np.concatenate([p["em_len"].ravel() for p in plans])
@@ -664,7 +687,8 @@ def _spr_round_ids(tree, loci, backend, dms, prunings, chunk, where):
     return best[0], (best[1], best[2]), ncand, naln
 
 
-def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, world=1, device=None, lanes=None):
+def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, world=1, device=None, lanes=None, merge_edges=False,
+                      timing=None):
     """One SPR neighbourhood strong-scaled over `world` ranks (the Parmap / MPI seam of src/ptree.ml:1356-1408,
     src/allDirChar.ml:2132-2177): the PRUNINGS are dealt to the ranks by estimated work (LPT on the size of the rest
     tree), so every candidate of a pruning -- all its join edges, all loci -- is evaluated on one GPU and the
@@ -685,7 +709,7 @@ def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, worl
         lanes = [(backend, loci, dms)]
     nlanes = len(lanes)
     if world == 1 and nlanes == 1:
-        return spr_round(tree, loci, backend, dms=dms, prunings=prunings, chunk=chunk)
+        return spr_round(tree, loci, backend, dms=dms, prunings=prunings, chunk=chunk, merge_edges=merge_edges)
     work = [len(tree.component(u, v)) for (u, v) in prunings]
     parts = shard.lpt_partition(work, world * nlanes)
     big = (1 << 62)
@@ -694,18 +718,24 @@ def spr_round_sharded(tree, loci, backend, dms, prunings, chunk=64, rank=0, worl
         b, lc, dm = lanes[q]
         mine = parts[rank * nlanes + q]
         where = []
-        est, move, ncand, naln = spr_round(tree, lc, b, dms=dm, prunings=[prunings[i] for i in mine], chunk=chunk, where=where)
+        est, move, ncand, naln = spr_round(tree, lc, b, dms=dm, prunings=[prunings[i] for i in mine], chunk=chunk, where=where,
+                                            merge_edges=merge_edges)
         if est is None:
             return big, big, 0, naln
         pi, ji = where[0]
         return int(est), (int(mine[pi]) << 24) | ji, ncand, naln        # join edges per pruning < 2^24
 
+    import time as _time
+    _t0 = _time.perf_counter()
     if nlanes == 1:
         res = [run_lane(0)]
     else:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(nlanes) as ex:      # the ctypes calls release the GIL while the GPU works
             res = list(ex.map(run_lane, range(nlanes)))
+    if timing is not None:      # this rank's own share, before it meets the others in the reduction
+        timing["local_seconds"] = _time.perf_counter() - _t0
+        timing["local_prunings"] = int(sum(len(parts[rank * nlanes + q]) for q in range(nlanes)))
     est, mine_ord = min((r[0], r[1]) for r in res)
     ncand, naln = sum(r[2] for r in res), sum(r[3] for r in res)
     gmin, gord = est, mine_ord

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--check", type=int, default=16)
     ap.add_argument("--lanes", type=int, default=1)
+    ap.add_argument("--merge-edges", action="store_true")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -32,7 +33,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = pb.Context(local)
     out, sample = swap_eval.run(ctx, rank=rank, world=world, device=dev, taxa=a.taxa, nloci=a.loci, lmin=a.lmin, lmax=a.lmax,
-                                seed=a.seed, prunings=a.prunings, chunk=a.chunk, check=a.check, lanes=a.lanes)
+                                seed=a.seed, prunings=a.prunings, chunk=a.chunk, check=a.check, lanes=a.lanes, merge_edges=a.merge_edges)
     if rank == 0:
         if sample is not None:
             from tests.oracle_backend import replay_sample

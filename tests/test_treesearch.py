@@ -238,9 +238,9 @@ def test_vectorised_spr_round_matches_generic(port):
     sb = OracleStoreBackend(port, full, orig)
     loci = [sb.put(ls) for ls in host_loci]
     dms = treesearch.all_directions(tree, loci, sb)
-    for chunk in (1000, 3):
+    for chunk, merge in ((1000, False), (3, False), (4, True)):
         w1 = []
-        got = treesearch.spr_round(tree, loci, sb, dms=dms, prunings=pr, chunk=chunk, where=w1)
+        got = treesearch.spr_round(tree, loci, sb, dms=dms, prunings=pr, chunk=chunk, where=w1, merge_edges=merge)
         assert got == generic and w1 == w0
 
 
