@@ -599,7 +599,7 @@ def main():
                                  peak_gbs=hbm_peak, frac=k_bytes * n_top / (k_ms * 1e-3) / 1e9 / hbm_peak,
                                  note="sequence bytes in + 4 B cost out per pair (SURVEY 8d): this path is integer-issue bound, not HBM bound"))
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # the CPU baseline leg runs at N = 1 only
             try:
                 cpu = cpu_reference(lengths, threads)
                 cpu = dict(value=cpu["value"], unit=cpu["unit"], cores=cpu["cores"], kind=cpu["kind"], sample=cpu["sample"],

@@ -750,7 +750,12 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const char *pe = getenv("POY_PROBE");   // POY_PROBE=0 turns the probe fills off, 2 forces them on small batches too (test hook)
     // small batches are latency bound (a repeated threshold is one more round trip), probes only pay when the
     // fills saturate the GPU
-    const bool use_probes = !(pe && pe[0] == '0') && (n >= 1024 || (pe && pe[0] == '2'));
+    // POY_PROBE_MIN / POY_PROBE_MIN4: smallest batch in which gap-free / 4-state pairs are probed (tuning hooks)
+    const char *pm = getenv("POY_PROBE_MIN"), *pm4 = getenv("POY_PROBE_MIN4");
+    const int probe_min = pm ? atoi(pm) : 1024, probe_min4 = pm4 ? atoi(pm4) : 1024;
+    const bool forced = pe && pe[0] == '2';
+    const bool use_probes = !(pe && pe[0] == '0') && (n >= std::min(probe_min, probe_min4) || forced);
+    const bool probe_gf = forced || n >= probe_min, probe_4s = forced || n >= probe_min4;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
     // POY_LOWLAT=0 turns the low-latency kernel shapes off, 2 forces them (test hook); default: rounds with at most
@@ -779,7 +784,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             // change, and the repeated fill starts from the snapshot.  Without traceback outputs nobody needs
             // directions at all.
             h.probe = 0;
-            if (!linear && h.dclass != 0 && h.lasti != 0 && use_probes) {
+            if (!linear && h.dclass != 0 && h.lasti != 0 && use_probes && (h.gapfree ? probe_gf : probe_4s)) {
                 if (!want_trace) h.probe = 1;
                 else if (!h.want_dirs) {
                     const int newp = (2 * h.T - delta) / 2;
