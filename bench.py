@@ -526,7 +526,7 @@ def main():
     configs = None
     if world == 1 and not args.no_configs and not args.no_swap:
         import pickle
-        from tests.oracle_backend import replay_sample, replay_triplets
+        from tests.oracle_backend import replay_sample, replay_triplets, replay_newkk
         configs = {}
         tmp = tempfile.NamedTemporaryFile(suffix=".pkl", delete=False); tmp.close()
         torch.cuda.empty_cache()
@@ -547,7 +547,8 @@ def main():
             rec_, sample_ = val
             try:
                 if sample_ is not None:
-                    rec_["parity"] = replay_triplets(sample_, REGIME) if name == "configs[2]" else replay_sample(sample_[0], sample_[1], REGIME)
+                    rec_["parity"] = (replay_triplets(sample_, REGIME) if name == "configs[2]" else replay_newkk(sample_, REGIME) if name == "newkkonen"
+                                      else replay_sample(sample_[0], sample_[1], REGIME))
             except Exception as e:
                 rec_["parity"] = dict(error="%s: %s" % (type(e).__name__, e))
             configs[name] = rec_

@@ -28,7 +28,9 @@
 //  * DIR = false is the probe fill: same states and gap counters, no direction bytes.
 #include <stdlib.h>
 #include <type_traits>
+#include <cooperative_groups.h>
 #include "common.cuh"
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -171,6 +173,25 @@ __device__ __forceinline__ unsigned cell_gf(int &CB, int &EV, int &EH, int &K, u
 __device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void pair_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
+// 16-byte mailbox records between the CTAs of a cluster (generic addresses: the local copy is polled, the neighbour's
+// copy is written through distributed shared memory); one vector access each, the sequence number travels in .w
+__device__ __forceinline__ void st_mailbox(volatile int4 *p, int x, int y, int z, int w) {
+    asm volatile("st.volatile.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ int4 ld_mailbox(const volatile int4 *p) {
+    int4 v;
+    asm volatile("ld.volatile.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// bounded poll (a lost hand-over must end as a wrong result that the parity tests catch, never as a hung GPU)
+__device__ __forceinline__ int4 wait_mailbox(const volatile int4 *p, int expect, bool &failed) {
+    int4 v = ld_mailbox(p);
+    if (failed) return v;
+    for (int spin = 0; v.w != expect && spin < (1 << 16); ++spin) v = ld_mailbox(p);
+    failed = v.w != expect;           // give up for the rest of this pair: ~1 ms lost once, not per sub-step
+    return v;
+}
+
 // low bytes of H words -> one little-endian word (PRMT: three byte permutes for four cells)
 template <int H>
 __device__ __forceinline__ unsigned pack_dir(const unsigned (&b)[H]) {
@@ -202,20 +223,43 @@ template <int NW, bool GFK> struct MinBlocks {
                                  : (NW == 8 ? 2 : NW == 4 ? 4 : NW == 3 ? 5 : NW == 5 ? 3 : NW == 6 ? 2 : NW == 2 ? 8 : NW == 1 ? 2 : 1);
 };
 
-template <int D, int NW, int WPB, bool GFK, bool DIR>
-__global__ void __launch_bounds__(WPB * 32, MinBlocks<NW, GFK>::v)
+// CL > 1: one pair per thread-block CLUSTER of CL CTAs of NW warps each ("cooperative tiled bands" for wide bands in
+// latency-bound rounds): warp w of CTA c owns the diagonals of global warp c * NW + w.  Inside a CTA the warps hand their
+// strip edges over exactly as before (shared-memory mailboxes + pairwise named barriers); between the last warp of CTA c
+// and the first warp of CTA c + 1 the 16-byte mailbox record {CB, EV|EH, G, sequence number} is written into the
+// NEIGHBOUR's shared memory (distributed shared memory, one vector store) and the consumer polls its own copy for the
+// sequence number it expects -- no cluster-wide barrier inside a fill (a cluster.sync costs ~380 cycles and flushes
+// L1; a DSMEM store ~215).  Two slots per direction (sequence parity): a producer cannot get more than one hand-over
+// ahead of its consumer because it needs the consumer's reply for its own next sub-step.
+template <int D, int NW, int WPB, bool GFK, bool DIR, int CL = 1>
+__global__ void __launch_bounds__(WPB * 32, CL > 1 ? 1 : MinBlocks<NW, GFK>::v)
 k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
         const int *__restrict__ h0v, const int *__restrict__ g0v, const unsigned *__restrict__ rowpk,
         const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state, int *ebrow, uint8_t *dir) {
     constexpr int H = D / 2;
+    static_assert(CL == 1 || (NW > 1 && NW <= 8), "cluster shapes use the pairwise-barrier path inside each CTA");
+    __shared__ __align__(16) int4 s_cx_left[2];    // CL > 1: written by the CTA to the left (its last warp's slot D-1)
+    __shared__ __align__(16) int4 s_cx_right[2];   // CL > 1: written by the CTA to the right (its first warp's slot 0)
     __shared__ int s_tab_i[256 * 32];  // cost16 replicated per bank: entry e of lane l at [e*32 + l]
     __shared__ __align__(16) int s_lut_i[GFK ? 8 : 128 * 8];   // surcharge records of cell_gen: [swaped][row class][column class] x 32 B
     __shared__ int s_job;
     __shared__ int s_xe[NW][4];        // slot-0 state of lane 0 of every warp (read by the warp to its left)
     __shared__ int s_xo[NW][4];        // slot-(D-1) state of lane 31 of every warp (read by the warp to its right)
     static_assert(NW == 1 || WPB == NW, "cooperating warps fill the whole CTA");
-    const int lane = threadIdx.x & 31, warp = (NW == 1) ? 0 : (threadIdx.x >> 5);
-    const int tid = (NW == 1) ? lane : (int)threadIdx.x;   // thread index within the group that owns the pair
+    int crank = 0;
+    if constexpr (CL > 1) crank = (int)cg::this_cluster().block_rank();
+    const int lane = threadIdx.x & 31, lw = (NW == 1) ? 0 : (threadIdx.x >> 5);      // lw: warp within the CTA
+    const int warp = lw + crank * NW;                                                // warp within the group that owns the pair
+    const int tid = (NW == 1) ? lane : (int)threadIdx.x + crank * NW * 32;           // thread index within that group
+    volatile int4 *rem_left_cx_right = nullptr, *rem_right_cx_left = nullptr;        // the neighbours' mailboxes for this CTA
+    const int *rem_job = &s_job;
+    if constexpr (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        if (threadIdx.x < 2) { s_cx_left[threadIdx.x] = make_int4(0, 0, 0, -1); s_cx_right[threadIdx.x] = make_int4(0, 0, 0, -1); }
+        if (crank > 0) rem_left_cx_right = (volatile int4 *)cluster.map_shared_rank(&s_cx_right[0], crank - 1);
+        if (crank + 1 < CL) rem_right_cx_left = (volatile int4 *)cluster.map_shared_rank(&s_cx_left[0], crank + 1);
+        rem_job = cluster.map_shared_rank(&s_job, 0);
+    }
     // Gap-free launches work in a shifted domain: every state of cell (i,j) is carried minus S_j + R_i (the sums
     // of the column / row gap extensions up to j / i), which moves the "+ ge" of EH and EV into the table as
     // cost[a][b] - prepend[b] - cost[a][gap].  All comparisons of a cell are between states of the same shift, so
@@ -250,6 +294,11 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             job = 0;
             if (lane == 0) job = atomicAdd(counter, 1);
             job = __shfl_sync(0xffffffffu, job, 0);
+        } else if constexpr (CL > 1) {
+            cg::this_cluster().sync();           // every CTA is done with the previous pair (and with its mailboxes)
+            if (tid == 0) s_job = atomicAdd(counter, 1);
+            cg::this_cluster().sync();
+            job = *rem_job;
         } else {
             __syncthreads();
             if (tid == 0) s_job = atomicAdd(counter, 1);
@@ -319,13 +368,20 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         // ids, so that class keeps __syncthreads.
         constexpr bool P2P = (NW > 1 && NW <= 8);
         const bool warp_in_band = (NW == 1) || (warp * 32 * D < B);
-        const bool has_left = P2P && warp > 0;
-        const bool has_right = P2P && warp + 1 < NW && (warp + 1) * 32 * D < B;
-        const int bar_E_mine = warp, bar_E_right = warp + 1;            // E(w) = id w, w = 1 .. NW-1
-        const int bar_O_mine = NW + warp, bar_O_left = NW + warp - 1;   // O(w) = id NW + w, w = 0 .. NW-2
+        const bool has_left = P2P && lw > 0;
+        const bool has_right = P2P && lw + 1 < NW && (warp + 1) * 32 * D < B;
+        // cluster shapes: the neighbour across the CTA boundary
+        const bool rem_left = CL > 1 && lw == 0 && crank > 0 && warp_in_band;
+        const bool rem_right = CL > 1 && lw == NW - 1 && crank + 1 < CL && (warp + 1) * 32 * D < B;
+        const int seqbase = (job + 1) << 16;                            // hand-over sequence numbers of this pair
+        int it = 0;
+        bool mb_failed = false;
+        const int bar_E_mine = lw, bar_E_right = lw + 1;                // E(w) = id w, w = 1 .. NW-1
+        const int bar_O_mine = NW + lw, bar_O_left = NW + lw - 1;       // O(w) = id NW + w, w = 0 .. NW-2
         if (NW > 1) {
-            if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
-            if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
+            if (lane == 0) { s_xe[lw][0] = CB[0]; s_xe[lw][1] = EV[0]; s_xe[lw][2] = (int)G[0]; }
+            if (lane == 31) { s_xo[lw][0] = CB[D - 1]; s_xo[lw][1] = EH[D - 1]; s_xo[lw][2] = (int)G[D - 1]; }
+            if (CL > 1 && rem_right && lane == 31) st_mailbox(rem_right_cx_left, CB[D - 1], EH[D - 1], (int)G[D - 1], seqbase);
             __syncthreads();
             if (P2P && warp_in_band && has_right) pair_arrive(bar_O_mine);   // row 0 stands in for "odd sub-step -1"
         } else {
@@ -357,7 +413,11 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
                 int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
                 unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
-                if (NW > 1 && lane == 0 && warp > 0) { sCB = s_xo[warp - 1][0]; sEH = s_xo[warp - 1][1]; sG = (unsigned)s_xo[warp - 1][2]; }
+                if (NW > 1 && lane == 0 && lw > 0) { sCB = s_xo[lw - 1][0]; sEH = s_xo[lw - 1][1]; sG = (unsigned)s_xo[lw - 1][2]; }
+                if (CL > 1 && rem_left && lane == 0) {
+                    const int4 v = wait_mailbox(&s_cx_left[it & 1], seqbase + it, mb_failed);
+                    sCB = v.x; sEH = v.y; sG = (unsigned)v.z;
+                }
                 unsigned bw[H];
                 sfor<H>([&](auto hc) { bw[decltype(hc)::value] = 0u; });
                 if (warp_in_band)
@@ -393,7 +453,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
                 });
                 if (NW > 1) {
-                    if (lane == 0) { s_xe[warp][0] = CB[0]; s_xe[warp][1] = EV[0]; s_xe[warp][2] = (int)G[0]; }
+                    if (lane == 0) { s_xe[lw][0] = CB[0]; s_xe[lw][1] = EV[0]; s_xe[lw][2] = (int)G[0]; }
+                    if (CL > 1 && rem_left && lane == 0) st_mailbox(rem_left_cx_right + (it & 1), CB[0], EV[0], (int)G[0], seqbase + it + 1);
                     if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
                     else __syncthreads();
                 }
@@ -404,7 +465,11 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 int sCB = __shfl_down_sync(0xffffffffu, CB[0], 1);
                 int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
                 unsigned sG = __shfl_down_sync(0xffffffffu, G[0], 1);
-                if (NW > 1 && lane == 31 && warp < NW - 1) { sCB = s_xe[warp + 1][0]; sEV = s_xe[warp + 1][1]; sG = (unsigned)s_xe[warp + 1][2]; }
+                if (NW > 1 && lane == 31 && lw < NW - 1) { sCB = s_xe[lw + 1][0]; sEV = s_xe[lw + 1][1]; sG = (unsigned)s_xe[lw + 1][2]; }
+                if (CL > 1 && rem_right && lane == 31) {
+                    const int4 v = wait_mailbox(&s_cx_right[it & 1], seqbase + it + 1, mb_failed);
+                    sCB = v.x; sEV = v.y; sG = (unsigned)v.z;
+                }
                 unsigned bw[H];
                 sfor<H>([&](auto hc) { bw[decltype(hc)::value] = 0u; });
                 if (warp_in_band)
@@ -439,7 +504,9 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
                 });
                 if (NW > 1) {
-                    if (lane == 31) { s_xo[warp][0] = CB[D - 1]; s_xo[warp][1] = EH[D - 1]; s_xo[warp][2] = (int)G[D - 1]; }
+                    if (lane == 31) { s_xo[lw][0] = CB[D - 1]; s_xo[lw][1] = EH[D - 1]; s_xo[lw][2] = (int)G[D - 1]; }
+                    if (CL > 1 && rem_right && lane == 31)
+                        st_mailbox(rem_right_cx_left + ((it + 1) & 1), CB[D - 1], EH[D - 1], (int)G[D - 1], seqbase + it + 1);
                     if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
                     else __syncthreads();
                 }
@@ -447,7 +514,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             // ---- slide the windows one row down / one column right ----
             sfor<H - 1>([&](auto hc) { constexpr int h = H - 1 - decltype(hc)::value; R[h] = R[h - 1]; });
             sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = C[h + 1]; });
-            ++i0; ++j0;
+            ++i0; ++j0; ++it;
             R[0] = row_entry<GF, DIR>(nrow, swoff);
             C[H] = col_entry<GF, DIR>(ncol, lane);
         };
@@ -478,6 +545,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         // one kind of pair per launch (GFK): the 3-state path needs ~35 fewer registers, i.e. one more resident CTA
         if constexpr (GFK) run(std::true_type{}); else run(std::false_type{});
     }
+    if constexpr (CL > 1) cg::this_cluster().sync();     // no CTA may exit while a neighbour can still touch its shared memory
 }
 
 template <int D, int NW>
@@ -497,6 +565,30 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
 #undef LAUNCH
     ctx->launches++;
     return cudaGetLastError();
+}
+
+// one pair per cluster of CL CTAs (NW warps each): persistent clusters, one CTA per SM
+template <int D, int NW, int CL>
+static cudaError_t launch_cluster(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
+                                  bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+    cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
+    if (e != cudaSuccess) return e;
+    const int nclusters = std::max(1, std::min(njobs, ctx->sm_count / CL));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nclusters * CL)); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const DevCM *a0 = cm->d; const int4 *a1 = pool->d_rowp, *a2 = pool->d_colp; const int *a3 = pool->d_h0, *a4 = pool->d_g0;
+    const unsigned *a5 = pool->d_rowpk;
+#define LAUNCHC(GFV, DIRV) e = cudaLaunchKernelEx(&cfg, k_band2<D, NW, NW, GFV, DIRV, CL>, a0, a1, a2, a3, a4, a5, d_jobs, njobs, d_counter, \
+                                                  d_state, d_ebrow, d_dir)
+    if (gapfree) { if (probe) LAUNCHC(true, false); else LAUNCHC(true, true); }
+    else { if (probe) LAUNCHC(false, false); else LAUNCHC(false, true); }
+#undef LAUNCHC
+    ctx->launches++;
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // class = number of diagonals one CTA covers.  Warps right of the band idle, so the in-between sizes (3, 5, 6
@@ -520,6 +612,17 @@ int band2_stride_for(int cls, long long B) {
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
                          bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, bool lowlat) {
     if (njobs <= 0) return cudaSuccess;
+    // Cluster shapes (one pair over 2 or 4 SMs, 4 diagonals per thread): latency-bound rounds with bands of 1280 diagonals
+    // and more, where a fill lasts as long as the issue rate of ONE SM allows.  POY_CLUSTER=0 turns them off, 2 forces
+    // them for every class (test hook).
+    {
+        const char *ce = getenv("POY_CLUSTER");
+        const bool off = ce && ce[0] == '0', forced = ce && ce[0] == '2';
+        if (!off && njobs < 60000 && (forced || (lowlat && cls >= 1280))) {
+            if (cls <= 2048) return launch_cluster<4, 8, 2>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir);
+            if (cls == 4096) return launch_cluster<4, 8, 4>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir);
+        }
+    }
 #define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir)
     if (lowlat)
         switch (cls) {

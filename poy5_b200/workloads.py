@@ -114,6 +114,32 @@ def config5(ctx, taxa=1000, L=10000, prunings=6, regime=(1, 1, 3), check=8, seed
     return out, sample
 
 
+def newkk(ctx, pairs=2000, L=2000, regime=(1, 1, 3), check=8):
+    """Sequence.NewkkAlign.align_2 (src/newkkonen.c, affine entry point) on interior-node-like pairs: cost + both aligned
+    rows per pair, threshold doubling inside the kernel."""
+    import poy5_b200 as pb
+    from .cost_matrix import Two_D
+    from .sequence import NewkkAlign
+    cm = pb.CostModel(ctx, Two_D.of_transformations_and_gaps(*regime).full)
+    data, off = synth.pair_pool(4242, 0, pairs, L, subst=0.10, indel=0.01, decorated=0.5)
+    seqs = [data[off[s]:off[s + 1]] for s in range(2 * pairs)]
+    pool = pb.Pool(ctx, seqs)
+    ia = np.arange(0, 2 * pairs, 2, dtype=np.int32); ib = ia + 1
+    NewkkAlign.cost_2(ctx, cm, pool, ia[:64], ib[:64])          # warm-up
+    ctx.synchronize(); t0 = time.perf_counter()
+    r = NewkkAlign.align_2(ctx, cm, pool, ia, ib, stats=True)
+    ctx.synchronize(); secs = time.perf_counter() - t0
+    lens = np.diff(off)
+    cells = int(((lens[ia] - 1) * (lens[ib] - 1)).sum())
+    out = dict(workload="Sequence.NewkkAlign.align_2: %d pairs of %d bp" % (pairs, L), seconds=secs, alignments_per_s=pairs / secs,
+               gcups_full_matrix_equivalent=cells / secs / 1e9, mean_doublings=float(r["stats"][:, 0].mean()),
+               median_final_k=int(np.median(r["stats"][:, 2])))
+    sample = [(seqs[2 * p], seqs[2 * p + 1], int(r["cost"][p]), np.array(r["res_a"][p], np.uint8), np.array(r["res_b"][p], np.uint8))
+              for p in np.linspace(0, pairs - 1, check).astype(int)]
+    pool.close(); cm.close()
+    return out, sample
+
+
 def main():
     """python -m poy5_b200.workloads --out FILE [--device D]: runs the three workloads in THIS process and pickles
     {name: (record, sample) | {"error": ...}} -- bench.py runs it as a child process so that a failure or a time-out of
@@ -132,7 +158,8 @@ def main():
     out = {}
     jobs = (("configs[0]", config1, dict(taxa=7, L=120) if a.small else {}),
             ("configs[2]", config3, dict(triplets=40, L=150, chunk=20) if a.small else {}),
-            ("configs[4]", config5, dict(taxa=12, L=300, prunings=3) if a.small else {}))
+            ("configs[4]", config5, dict(taxa=12, L=300, prunings=3) if a.small else {}),
+            ("newkkonen", newkk, dict(pairs=40, L=200) if a.small else {}))
     for name, fn, kw in jobs:
         try:
             out[name] = fn(ctx, regime=regime, **kw)

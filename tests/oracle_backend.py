@@ -137,3 +137,19 @@ def replay_triplets(sample, regime):
         oc, _, _, xa, xb = oracle_align(P, pf, p, u)
         bad += not (oc == cost and np.array_equal(P.median_2(pf, xa, xb, False), med))
     return dict(checked=len(sample), mismatches=int(bad), against="oracle port (plain-C restatement of algn.c, pinned to the compiled reference)")
+
+
+def replay_newkk(sample, regime):
+    """CPU checker replay of recorded Sequence.NewkkAlign.align_2 results (poy5_b200.workloads.newkk): (a, b, cost, row a, row b)"""
+    from oracle import cost_matrix_oracle as cmo
+    from oracle.port import Port
+    full, _ = cmo.dna_matrices(*regime)
+    P = Port(); pf = P.cm(full)
+    bad = 0
+    for a, b, cost, ra, rb in sample:
+        sw = int(len(a) > len(b))
+        s1, s2 = (b, a) if sw else (a, b)
+        oc, o1, o2 = P.newkk_align(pf, s1, s2, sw)
+        xa, xb = (o2, o1) if sw else (o1, o2)
+        bad += not (oc == cost and np.array_equal(xa, ra) and np.array_equal(xb, rb))
+    return dict(checked=len(sample), mismatches=int(bad), against="oracle/newkk_oracle.c (restatement pinned to the compiled src/newkkonen.c)")

@@ -394,3 +394,7 @@ def test_baseline_config_workloads_small(ctx):
     r5, s5 = workloads.config5(ctx, taxa=12, L=300, prunings=3, check=6)
     p5 = replay_sample(s5[0], s5[1], (1, 1, 3))
     assert r5["spr_candidates"] > 10 and p5["checked"] > 0 and p5["mismatches"] == 0
+    from tests.oracle_backend import replay_newkk
+    rn, sn = workloads.newkk(ctx, pairs=40, L=200, check=6)
+    pn = replay_newkk(sn, (1, 1, 3))
+    assert pn["checked"] == 6 and pn["mismatches"] == 0 and rn["alignments_per_s"] > 0
