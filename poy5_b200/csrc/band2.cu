@@ -46,23 +46,21 @@ __device__ __forceinline__ void sfor(F &&f) {
 // Gap-free pairs: meta = shared-memory byte offset of the cost row / column.
 // Pairs with gap-bit symbols: meta = (byte offset of the cost row / column) << 16 | (index of the surcharge class) << 5,
 // so that ONE add of a row and a column entry yields both the table address (high half) and the address of the
-// 32-byte surcharge record of this (row class, column class) in s_lut (bits 5-11); bits 0-2 of a column entry hold
+// 32-byte surcharge record of this (row class, column class) in s_lut (bits 5-11); bits 12-14 of a column entry hold
 // the class the column has when it sits on the left border (cell_gen).  ext already carries the END_* tag of the
 // direction byte (DIR fills).
 struct Ent { int ext, opn, meta; };
 
-// surcharge class of a base: bit 0 symbol has the gap bit, bit 1 previous symbol has it, bit 2 gap opening is free here
-__device__ __forceinline__ int gap_class(const int4 v) {
-    return ((v.w & PF_HASGAP) ? 1 : 0) | ((v.w & PF_PREVGAP) ? 2 : 0) | (v.z == 0 ? 4 : 0);
-}
-
+// The class / table-offset fields come ready-made in the flags word of the per-base parameters (k_params, PF_ROW_* /
+// PF_COL_* in common.cuh): an entry's meta is one masked OR.  Surcharge class of a base: {symbol has the gap bit,
+// previous symbol has it, gap opening is free here}; rows order the bits (has, prev, free), columns (prev, has, free).
 template <bool GF, bool DIR>
 __device__ __forceinline__ Ent row_entry(const int4 v, int swoff) {
     Ent e;
-    if (GF) { e.ext = 0; e.opn = 0; e.meta = ((v.w & 15) << 11); }
+    if (GF) { e.ext = 0; e.opn = 0; e.meta = v.w & PF_ROW_GF_MASK; }
     else {
         e.ext = (v.x << 8) + (DIR ? 16 : 0); e.opn = (v.y << 8);     // x256: see cell_gf / cell_gen
-        e.meta = ((v.w & 15) << 27) | (gap_class(v) << 8) | swoff;
+        e.meta = (v.w & PF_ROW_MASK) | swoff;
     }
     return e;
 }
@@ -72,10 +70,8 @@ __device__ __forceinline__ Ent col_entry(const int4 v, int lane) {
     if (GF) { e.ext = 0; e.opn = 0; e.meta = (((v.w & 15) << 7) + (lane << 2)); }
     else {
         e.ext = (v.x << 8) + (DIR ? 32 : 0); e.opn = (v.y << 8);
-        const int cc = gap_class(v);
-        // at the left border the reference's "previous column symbol" is the column symbol itself
-        const int cc_lb = (cc & 5) | ((cc & 1) << 1);
-        e.meta = ((((v.w & 15) << 7) + (lane << 2)) << 16) | (cc << 5) | cc_lb;
+        // bits 12-14: at the left border the reference's "previous column symbol" is the column symbol itself
+        e.meta = (v.w & PF_COL_MASK) | (lane << 18);
     }
     return e;
 }
@@ -103,7 +99,7 @@ __device__ __forceinline__ unsigned cell_gen(int &CB, int &EV, int &EH, int &EB,
     if (rb) eV = INF256 + (DIR ? 16 : 0);
     const int nEH = DIR ? (eH & ~255) : eH, nEV = DIR ? (eV & ~255) : eV;
     int cm = c.meta;
-    if (lb) cm = (cm & ~0xE0) | ((cm & 7) << 5);
+    cm ^= (cm ^ (cm >> 7)) & (lb ? 0xE0 : 0);     // left border: the class of bits 12-14 replaces the one of bits 5-7
     const int sum = r.meta + cm;
     const int diag = *(const int *)(s_tab + ((unsigned)sum >> 16));
     const char *q = s_lut + (sum & 0xFE0);
@@ -240,11 +236,14 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     static_assert(CL == 1 || (NW > 1 && NW <= 8), "cluster shapes use the pairwise-barrier path inside each CTA");
     __shared__ __align__(16) int4 s_cx_left[2];    // CL > 1: written by the CTA to the left (its last warp's slot D-1)
     __shared__ __align__(16) int4 s_cx_right[2];   // CL > 1: written by the CTA to the right (its first warp's slot 0)
-    __shared__ int s_tab_i[256 * 32];  // cost16 replicated per bank: entry e of lane l at [e*32 + l]
-    __shared__ __align__(16) int s_lut_i[GFK ? 8 : 128 * 8];   // surcharge records of cell_gen: [swaped][row class][column class] x 32 B
+    // one array, so that both tables are addressed from one base register:
+    //   s_tab_i: cost16 replicated per bank, entry e of lane l at [e*32 + l]
+    //   s_lut_i: surcharge records of cell_gen, [swaped][row class][column class] x 32 B
+    __shared__ __align__(16) int s_mem_i[256 * 32 + (GFK ? 8 : 128 * 8)];
+    int *const s_tab_i = s_mem_i, *const s_lut_i = s_mem_i + 256 * 32;
     __shared__ int s_job;
-    __shared__ int s_xe[NW][4];        // slot-0 state of lane 0 of every warp (read by the warp to its left)
-    __shared__ int s_xo[NW][4];        // slot-(D-1) state of lane 31 of every warp (read by the warp to its right)
+    __shared__ __align__(16) int4 s_xe[NW];   // slot-0 state of lane 0 of every warp (read by the warp to its left): one 16-byte access
+    __shared__ __align__(16) int4 s_xo[NW];   // slot-(D-1) state of lane 31 of every warp (read by the warp to its right)
     static_assert(NW == 1 || WPB == NW, "cooperating warps fill the whole CTA");
     int crank = 0;
     if constexpr (CL > 1) crank = (int)cg::this_cluster().block_rank();
@@ -273,7 +272,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     if (!GFK)
         for (int x = threadIdx.x; x < 128; x += WPB * 32) {
             const int sw = x >> 6, rc = (x >> 3) & 7, cc = x & 7;
-            const bool hg_i = rc & 1, pv_i = rc & 2, goz_i = rc & 4, hg_j = cc & 1, pv_j = cc & 2, goz_j = cc & 4;
+            const bool hg_i = rc & 1, pv_i = rc & 2, goz_i = rc & 4, pv_j = cc & 1, hg_j = cc & 2, goz_j = cc & 4;
             const int tV = sw ? 1 : 0, tH = sw ? 0 : 1;
             const bool both = hg_i && hg_j, clean = !pv_i && !pv_j;
             int *e = s_lut_i + x * 8;
@@ -316,6 +315,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         const int delta = lastj - lasti, B = delta + 2 * k + 1;
         const int4 *rp = rowp + J.off_i;
         const int4 *cp = colp + J.off_j;
+        asm("" : "+l"(rp)); asm("" : "+l"(cp));   // keep the per-pair bases whole: a window load is base + 16 * index (one IMAD.WIDE)
         const int *h0 = h0v + J.off_j;
         const int *g0 = g0v + J.off_j;
         int *eb = ebrow + J.eb_off;
@@ -356,8 +356,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         int i0 = (a - d0 + k) >> 1, j0 = a - i0;
         Ent R[H], C[H + 1];
         const int swoff = swaped ? 2048 : 0;     // second half of s_lut: the ALIGN_TO tags of swapped operands
-        auto load_row = [&](int i) { i = i < 0 ? 0 : (i > lasti ? lasti : i); return row_entry<GF, DIR>(rp[i], swoff); };
-        auto load_col = [&](int j) { j = j < 0 ? 0 : (j > lastj ? lastj : j); return col_entry<GF, DIR>(cp[j], lane); };
+        auto load_row = [&](int i) { i = i < 0 ? 0 : (i > lasti ? lasti : i); return row_entry<GF, DIR>(__ldg(rp + i), swoff); };
+        auto load_col = [&](int j) { j = j < 0 ? 0 : (j > lastj ? lastj : j); return col_entry<GF, DIR>(__ldg(cp + j), lane); };
         sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; R[h] = load_row(i0 - h); });
         sfor<H + 1>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = load_col(j0 + h); });
 
@@ -379,8 +379,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         const int bar_E_mine = lw, bar_E_right = lw + 1;                // E(w) = id w, w = 1 .. NW-1
         const int bar_O_mine = NW + lw, bar_O_left = NW + lw - 1;       // O(w) = id NW + w, w = 0 .. NW-2
         if (NW > 1) {
-            if (lane == 0) { s_xe[lw][0] = CB[0]; s_xe[lw][1] = EV[0]; s_xe[lw][2] = (int)G[0]; }
-            if (lane == 31) { s_xo[lw][0] = CB[D - 1]; s_xo[lw][1] = EH[D - 1]; s_xo[lw][2] = (int)G[D - 1]; }
+            if (lane == 0) s_xe[lw] = make_int4(CB[0], EV[0], (int)G[0], 0);
+            if (lane == 31) s_xo[lw] = make_int4(CB[D - 1], EH[D - 1], (int)G[D - 1], 0);
             if (CL > 1 && rem_right && lane == 31) st_mailbox(rem_right_cx_left, CB[D - 1], EH[D - 1], (int)G[D - 1], seqbase);
             __syncthreads();
             if (P2P && warp_in_band && has_right) pair_arrive(bar_O_mine);   // row 0 stands in for "odd sub-step -1"
@@ -389,6 +389,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         }
 
         const int a_end = lasti + lastj;
+        uint8_t *dptr = dbase + (size_t)a * stride + tid * H;   // direction bytes of this thread on anti-diagonal a (advanced per iteration)
         int a_main = delta + k + 2;                     // first anti-diagonal whose band cells all have i >= 1, j >= 1
         if ((a_main ^ a) & 1) ++a_main;
         const int istar = lasti & ~1;                   // last even row: source of the stale EB row
@@ -400,9 +401,16 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             int4 nrow = make_int4(0, 0, 0, 0), ncol = make_int4(0, 0, 0, 0);
             if (warp_in_band) {
                 int ri = i0 + 1, cj = j0 + 1 + H;
-                ri = ri < 0 ? 0 : (ri > lasti ? lasti : ri);
-                cj = cj < 0 ? 0 : (cj > lastj ? lastj : cj);
-                nrow = rp[ri]; ncol = cp[cj];
+                if (EDGE) {
+                    ri = ri < 0 ? 0 : (ri > lasti ? lasti : ri);
+                    cj = cj < 0 ? 0 : (cj > lastj ? lastj : cj);
+                } else {
+                    // past a_main every band cell has i >= 1, j >= 1: only the slots right of the band can still sit
+                    // on a negative row, and what they load is never used -- one unsigned minimum keeps it in range
+                    ri = (int)min((unsigned)ri, (unsigned)lasti);
+                    cj = (int)min((unsigned)cj, (unsigned)lastj);
+                }
+                nrow = __ldg(rp + ri); ncol = __ldg(cp + cj);
             }
             // the stale EB row is written by the cells of even rows on the two leftmost diagonals
             // and of row istar: one test per iteration instead of one per cell
@@ -413,7 +421,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 int sCB = __shfl_up_sync(0xffffffffu, CB[D - 1], 1);
                 int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
                 unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
-                if (NW > 1 && lane == 0 && lw > 0) { sCB = s_xo[lw - 1][0]; sEH = s_xo[lw - 1][1]; sG = (unsigned)s_xo[lw - 1][2]; }
+                if (NW > 1 && lane == 0 && lw > 0) { const int4 v = s_xo[lw - 1]; sCB = v.x; sEH = v.y; sG = (unsigned)v.z; }
                 if (CL > 1 && rem_left && lane == 0) {
                     const int4 v = wait_mailbox(&s_cx_left[it & 1], seqbase + it, mb_failed);
                     sCB = v.x; sEH = v.y; sG = (unsigned)v.z;
@@ -444,7 +452,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         bw[h] = b;
                     }
                 });
-                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)a * stride + tid * H, pack_dir<H>(bw));
+                if (DIR && warp_in_band) store_dir<H>(dptr, pack_dir<H>(bw));
                 if (stale_hit && warp_in_band)      // rare: keeps the address arithmetic of the stale row out of the cells
                 sfor<H>([&](auto hc) {
                     constexpr int h = decltype(hc)::value;
@@ -453,7 +461,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
                 });
                 if (NW > 1) {
-                    if (lane == 0) { s_xe[lw][0] = CB[0]; s_xe[lw][1] = EV[0]; s_xe[lw][2] = (int)G[0]; }
+                    if (lane == 0) s_xe[lw] = make_int4(CB[0], EV[0], (int)G[0], 0);
                     if (CL > 1 && rem_left && lane == 0) st_mailbox(rem_left_cx_right + (it & 1), CB[0], EV[0], (int)G[0], seqbase + it + 1);
                     if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
                     else __syncthreads();
@@ -465,7 +473,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 int sCB = __shfl_down_sync(0xffffffffu, CB[0], 1);
                 int sEV = __shfl_down_sync(0xffffffffu, EV[0], 1);
                 unsigned sG = __shfl_down_sync(0xffffffffu, G[0], 1);
-                if (NW > 1 && lane == 31 && lw < NW - 1) { sCB = s_xe[lw + 1][0]; sEV = s_xe[lw + 1][1]; sG = (unsigned)s_xe[lw + 1][2]; }
+                if (NW > 1 && lane == 31 && lw < NW - 1) { const int4 v = s_xe[lw + 1]; sCB = v.x; sEV = v.y; sG = (unsigned)v.z; }
                 if (CL > 1 && rem_right && lane == 31) {
                     const int4 v = wait_mailbox(&s_cx_right[it & 1], seqbase + it + 1, mb_failed);
                     sCB = v.x; sEV = v.y; sG = (unsigned)v.z;
@@ -495,7 +503,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         bw[h] = b;
                     }
                 });
-                if (DIR && warp_in_band) store_dir<H>(dbase + (size_t)(a + 1) * stride + tid * H, pack_dir<H>(bw));
+                if (DIR && warp_in_band) store_dir<H>(dptr + stride, pack_dir<H>(bw));
                 if (stale_hit && warp_in_band)
                 sfor<H>([&](auto hc) {
                     constexpr int h = decltype(hc)::value;
@@ -504,7 +512,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
                 });
                 if (NW > 1) {
-                    if (lane == 31) { s_xo[lw][0] = CB[D - 1]; s_xo[lw][1] = EH[D - 1]; s_xo[lw][2] = (int)G[D - 1]; }
+                    if (lane == 31) s_xo[lw] = make_int4(CB[D - 1], EH[D - 1], (int)G[D - 1], 0);
                     if (CL > 1 && rem_right && lane == 31)
                         st_mailbox(rem_right_cx_left + ((it + 1) & 1), CB[D - 1], EH[D - 1], (int)G[D - 1], seqbase + it + 1);
                     if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
@@ -515,6 +523,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             sfor<H - 1>([&](auto hc) { constexpr int h = H - 1 - decltype(hc)::value; R[h] = R[h - 1]; });
             sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = C[h + 1]; });
             ++i0; ++j0; ++it;
+            dptr += 2 * (size_t)stride;
             R[0] = row_entry<GF, DIR>(nrow, swoff);
             C[H] = col_entry<GF, DIR>(ncol, lane);
         };

@@ -34,6 +34,15 @@ struct DevCM {
 // w = flags: bits 0-3 code&15, bit 4 code has the gap bit, bit 5 previous base has the gap bit
 #define PF_HASGAP 16
 #define PF_PREVGAP 32
+// precomputed window-entry fields of the band kernel in the same word (k_params writes them, band2.cu masks them out)
+#define PF_ROW_CLASS_SHIFT 8      // row role: surcharge class, bits 8-10
+#define PF_ROW_GF_SHIFT 11        // row role: code & 15 at bits 11-14 (gap-free table row offset)
+#define PF_ROW_TAB_SHIFT 27       // row role: code & 15 at bits 27-30 (table row offset << 16)
+#define PF_ROW_MASK 0x78000700
+#define PF_ROW_GF_MASK 0x00007800
+#define PF_COL_LB_SHIFT 12        // column role: class on the left border, bits 12-14 (class itself: bits 5-7)
+#define PF_COL_TAB_SHIFT 23       // column role: code & 15 at bits 23-26 (table column offset << 16)
+#define PF_COL_MASK 0x078070E0
 
 // what k_params reads from a cost model: pools (and the node store) remember the signature their per-base parameters
 // were computed for, so switching between c2_full and c2_original (identical under the default affine tables,

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
                 const int code = data[base + x] & 31;
                 const int prev = x > 0 ? (data[base + x - 1] & 31) : 0;
                 const int curgap = code & POY_GAP, prevgap = prev & POY_GAP;
-                const int flags = (code & POY_NOGAP) | (curgap ? PF_HASGAP : 0) | (prevgap ? PF_PREVGAP : 0) | (code << 8);
+                const int flags = (code & POY_NOGAP) | (curgap ? PF_HASGAP : 0) | (prevgap ? PF_PREVGAP : 0);
                 int4 r = make_int4(0, 0, 0, flags), c = make_int4(0, 0, 0, flags);
                 if (x >= 1) {
                     const int gopen = gap_opening_at(x, prev, code, go);
@@ -57,9 +57,16 @@ __global__ void __launch_bounds__(128) k_params(const DevCM *__restrict__ cm, co
                     c.z = gopen;
                     if (curgap) anygap = 1;
                 }
+                code15 = code & POY_NOGAP;
+                // bits 6-31 of the flags word: the window-entry fields of the band kernel (band2.cu, row_entry /
+                // col_entry), ready to be masked out.  Surcharge class = {symbol has the gap bit, previous symbol has
+                // it, gap opening is free here}; the column side keeps PF_PREVGAP as its bit 0 and also carries the
+                // class the column has on the left border (previous symbol := the symbol itself).
+                const int hg = curgap ? 1 : 0, pv = prevgap ? 1 : 0, goz = (r.z == 0) ? 1 : 0;
+                r.w |= ((hg | (pv << 1) | (goz << 2)) << PF_ROW_CLASS_SHIFT) | (code15 << PF_ROW_GF_SHIFT) | (code15 << PF_ROW_TAB_SHIFT);
+                c.w |= (hg << 6) | (goz << 7) | ((hg | (hg << 1) | (goz << 2)) << PF_COL_LB_SHIFT) | (code15 << PF_COL_TAB_SHIFT);
                 rowp[base + x] = r;
                 colp[base + x] = c;
-                code15 = code & POY_NOGAP;
             }
             // inclusive warp scans of hl, ge_c and the row-role gap extension
             int sh = hl, sg = ge_c, sr = ge_row;
