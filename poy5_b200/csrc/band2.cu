@@ -414,7 +414,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             }
             // the stale EB row is written by the cells of even rows on the two leftmost diagonals
             // and of row istar: one test per iteration instead of one per cell
-            const bool stale_hit = !GF && (tid == 0 || (unsigned)(i0 - istar) < (unsigned)H);
+            const bool stale_hit = !GF && ((tid == 0 && !(i0 & 1)) || (unsigned)(i0 - istar) < (unsigned)H);
             // ---- even diagonals ----
             {
                 if (has_left) pair_wait(bar_O_left);
@@ -452,20 +452,14 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         bw[h] = b;
                     }
                 });
-                if (DIR && warp_in_band) store_dir<H>(dptr, pack_dir<H>(bw));
-                if (stale_hit && warp_in_band)      // rare: keeps the address arithmetic of the stale row out of the cells
-                sfor<H>([&](auto hc) {
-                    constexpr int h = decltype(hc)::value;
-                    constexpr int u = 2 * h;
-                    const int i = i0 - h, j = j0 + h, d = d0 + u;
-                    if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
-                });
                 if (NW > 1) {
                     if (lane == 0) s_xe[lw] = make_int4(CB[0], EV[0], (int)G[0], 0);
                     if (CL > 1 && rem_left && lane == 0) st_mailbox(rem_left_cx_right + (it & 1), CB[0], EV[0], (int)G[0], seqbase + it + 1);
                     if (P2P) { if (has_left) pair_arrive(bar_E_mine); }
                     else __syncthreads();
                 }
+                // (after the hand-over: the neighbour does not wait for this store)
+                if (DIR && warp_in_band) store_dir<H>(dptr, pack_dir<H>(bw));
             }
             // ---- odd diagonals ----
             {
@@ -503,14 +497,6 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                         bw[h] = b;
                     }
                 });
-                if (DIR && warp_in_band) store_dir<H>(dptr + stride, pack_dir<H>(bw));
-                if (stale_hit && warp_in_band)
-                sfor<H>([&](auto hc) {
-                    constexpr int h = decltype(hc)::value;
-                    constexpr int u = 2 * h + 1;
-                    const int i = i0 - h, j = j0 + h + 1, d = d0 + u;
-                    if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
-                });
                 if (NW > 1) {
                     if (lane == 31) s_xo[lw] = make_int4(CB[D - 1], EH[D - 1], (int)G[D - 1], 0);
                     if (CL > 1 && rem_right && lane == 31)
@@ -518,7 +504,18 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
                     else __syncthreads();
                 }
+                if (DIR && warp_in_band) store_dir<H>(dptr + stride, pack_dir<H>(bw));
             }
+            // the stale EB row: every slot was written once in this iteration (even slots in the first sub-step), so one
+            // rare block serves both; it keeps the address arithmetic of the stale row out of the cells
+            if (stale_hit && warp_in_band)
+            sfor<D>([&](auto uc) {
+                constexpr int u = decltype(uc)::value;
+                const int i = i0 - u / 2, j = j0 + (u + 1) / 2, d = d0 + u;
+                if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
+            });
+            // the window entries prefetched at the top are first touched here: the load had the whole iteration to land
+            asm volatile("" : "+r"(nrow.x), "+r"(nrow.y), "+r"(nrow.w), "+r"(ncol.x), "+r"(ncol.y), "+r"(ncol.w));
             // ---- slide the windows one row down / one column right ----
             sfor<H - 1>([&](auto hc) { constexpr int h = H - 1 - decltype(hc)::value; R[h] = R[h - 1]; });
             sfor<H>([&](auto hc) { constexpr int h = decltype(hc)::value; C[h] = C[h + 1]; });

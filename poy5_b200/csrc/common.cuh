@@ -85,6 +85,7 @@ struct poy_pool {
     int32_t cap_seqs;
 };
 
+#define POY_N_AUX 8
 struct poy_ctx {
     int device;
     cudaStream_t stream;
@@ -99,9 +100,9 @@ struct poy_ctx {
     void *h_pinned[6];
     size_t pinned_cap[6];
     // auxiliary streams + events: independent launches of one wave run concurrently so that the tail of one
-    // overlaps the body of the next
-    cudaStream_t aux[4];
-    cudaEvent_t ev_fork, ev_join[4];
+    // overlaps the body of the next (8: a latency-bound round has up to 6-8 band classes, none should queue behind another)
+    cudaStream_t aux[POY_N_AUX];
+    cudaEvent_t ev_fork, ev_join[POY_N_AUX];
     // traceback lane: the traceback of the pairs that stopped in round r runs on its own stream while round r+1 is
     // being filled (two direction arenas / job arrays in turn); ev_tb_done[p] guards the reuse of arena p
     cudaStream_t tb_stream;

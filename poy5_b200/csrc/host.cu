@@ -59,7 +59,7 @@ extern "C" poy_status poy_ctx_create(int device, void *stream, poy_ctx **out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return POY_ERR_CUDA; }
         ctx->owns_stream = true;
     }
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < POY_N_AUX; ++a) {
         cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking);
         cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming);
     }
@@ -95,7 +95,7 @@ extern "C" void poy_ctx_destroy(poy_ctx *ctx) {
     for (int s = 0; s < 14; ++s) if (ctx->d_scratch[s]) cudaFree(ctx->d_scratch[s]);
     for (int i = 0; i < ctx->cache_n; ++i) cudaFree(ctx->cache_ptr[i]);
     for (int s = 0; s < 6; ++s) if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
-    for (int a = 0; a < 4; ++a) { cudaStreamDestroy(ctx->aux[a]); cudaEventDestroy(ctx->ev_join[a]); }
+    for (int a = 0; a < POY_N_AUX; ++a) { cudaStreamDestroy(ctx->aux[a]); cudaEventDestroy(ctx->ev_join[a]); }
     cudaEventDestroy(ctx->ev_fork);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
@@ -114,7 +114,7 @@ extern "C" poy_status poy_ctx_trim(poy_ctx *ctx) {
     for (poy_ctx *c : { ctx, ctx->twin }) {
         if (!c) continue;
         cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->tb_stream);
-        for (int a = 0; a < 4; ++a) cudaStreamSynchronize(c->aux[a]);
+        for (int a = 0; a < POY_N_AUX; ++a) cudaStreamSynchronize(c->aux[a]);
         for (int s = 0; s < 14; ++s)
             if (c->d_scratch[s]) { cudaFree(c->d_scratch[s]); c->d_scratch[s] = nullptr; c->scratch_cap[s] = 0; }
         for (int i = 0; i < c->cache_n; ++i) cudaFree(c->cache_ptr[i]);
@@ -861,7 +861,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             CK(cudaEventRecord(ctx->ev_fork, main_stream));
             unsigned used_aux = 0;
             while (q0 < nj) {
-                const int ax = nlaunch & 3;
+                const int ax = nlaunch & (POY_N_AUX - 1);
                 ctx->stream = ctx->aux[ax];
                 if (!(used_aux & (1u << ax))) { cudaStreamWaitEvent(ctx->stream, ctx->ev_fork, 0); used_aux |= 1u << ax; }
                 const int cls = hp[order[pos + q0]].dclass, gf = hp[order[pos + q0]].gapfree, pr = hp[order[pos + q0]].probe;
@@ -890,7 +890,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 q0 = q1;
             }
             ctx->stream = main_stream;
-            for (int ax = 0; ax < 4; ++ax)
+            for (int ax = 0; ax < POY_N_AUX; ++ax)
                 if (used_aux & (1u << ax)) {
                     CK(cudaEventRecord(ctx->ev_join[ax], ctx->aux[ax]));
                     CK(cudaStreamWaitEvent(main_stream, ctx->ev_join[ax], 0));
