@@ -188,6 +188,27 @@ __device__ __forceinline__ int4 wait_mailbox(const volatile int4 *p, int expect,
     return v;
 }
 
+// Progress words of speculative fills (global memory, one per fill): rows completed by the thread that owns the two
+// leftmost diagonals, SPEC_DONE at the end, SPEC_FAILED if the fill gave up.  Polls are bounded: a predecessor that is
+// not running (kernels serialised by a tool, a GPU shared with another process) must end as a fill the host repeats,
+// never as a hung GPU.
+__device__ __forceinline__ void spec_publish(int *p, int v) {
+    __threadfence();
+    *(volatile int *)p = v;
+}
+__device__ __forceinline__ int spec_wait(const int *p, int need) {     // returns the last value read: >= need unless it gave up
+    int v = *(const volatile int *)p;
+    for (int spin = 0; v >= 0 && v < need && spin < (1 << 18); ++spin) { __nanosleep(200); v = *(const volatile int *)p; }
+    __threadfence();
+    return v;
+}
+// what a fill publishes when it is over: status 1 = gave up, 2 = abandoned (an earlier doubling stopped), else complete
+__device__ __forceinline__ int spec_final(int status, const PairState *st) {
+    if (status == 1) return SPEC_FAILED;
+    if (status == 2) return SPEC_ABORT;
+    return *(const volatile int *)&st->done ? SPEC_STOP : SPEC_DONE;
+}
+
 // low bytes of H words -> one little-endian word (PRMT: three byte permutes for four cells)
 template <int H>
 __device__ __forceinline__ unsigned pack_dir(const unsigned (&b)[H]) {
@@ -231,7 +252,7 @@ template <int D, int NW, int WPB, bool GFK, bool DIR, int CL = 1>
 __global__ void __launch_bounds__(WPB * 32, CL > 1 ? 1 : MinBlocks<NW, GFK>::v)
 k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 *__restrict__ colp,
         const int *__restrict__ h0v, const int *__restrict__ g0v, const unsigned *__restrict__ rowpk,
-        const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state, int *ebrow, uint8_t *dir) {
+        const BandJob *__restrict__ jobs, int njobs, int *counter, PairState *state, int *ebrow, uint8_t *dir, int *prog) {
     constexpr int H = D / 2;
     static_assert(CL == 1 || (NW > 1 && NW <= 8), "cluster shapes use the pairwise-barrier path inside each CTA");
     __shared__ __align__(16) int4 s_cx_left[2];    // CL > 1: written by the CTA to the left (its last warp's slot D-1)
@@ -242,6 +263,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     __shared__ __align__(16) int s_mem_i[256 * 32 + (GFK ? 8 : 128 * 8)];
     int *const s_tab_i = s_mem_i, *const s_lut_i = s_mem_i + 256 * 32;
     __shared__ int s_job;
+    __shared__ int s_spec;                         // speculative fills: 1 = this fill gave up on its predecessor, 2 = it was abandoned (rank 0's copy counts)
+    __shared__ int s_astop;                        // ... last anti-diagonal to compute once the fill is abandoned (every CTA's own copy)
     __shared__ __align__(16) int4 s_xe[NW];   // slot-0 state of lane 0 of every warp (read by the warp to its left): one 16-byte access
     __shared__ __align__(16) int4 s_xo[NW];   // slot-(D-1) state of lane 31 of every warp (read by the warp to its right)
     static_assert(NW == 1 || WPB == NW, "cooperating warps fill the whole CTA");
@@ -252,12 +275,16 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
     const int tid = (NW == 1) ? lane : (int)threadIdx.x + crank * NW * 32;           // thread index within that group
     volatile int4 *rem_left_cx_right = nullptr, *rem_right_cx_left = nullptr;        // the neighbours' mailboxes for this CTA
     const int *rem_job = &s_job;
+    volatile int *rem_spec = &s_spec;
+    int pub_slot = -1;                               // progress slot of the fill just completed (published at the next CTA-wide sync)
+    int pub_stat = 0;                                // NW == 1: status of that fill (see spec_final)
     if constexpr (CL > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         if (threadIdx.x < 2) { s_cx_left[threadIdx.x] = make_int4(0, 0, 0, -1); s_cx_right[threadIdx.x] = make_int4(0, 0, 0, -1); }
         if (crank > 0) rem_left_cx_right = (volatile int4 *)cluster.map_shared_rank(&s_cx_right[0], crank - 1);
         if (crank + 1 < CL) rem_right_cx_left = (volatile int4 *)cluster.map_shared_rank(&s_cx_left[0], crank + 1);
         rem_job = cluster.map_shared_rank(&s_job, 0);
+        rem_spec = (volatile int *)cluster.map_shared_rank(&s_spec, 0);
     }
     // Gap-free launches work in a shifted domain: every state of cell (i,j) is carried minus S_j + R_i (the sums
     // of the column / row gap extensions up to j / i), which moves the "+ ge" of EH and EV into the table as
@@ -289,24 +316,61 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
 
     for (;;) {
         int job;
+        // a speculative fill that is complete says so once every thread's stale-row stores are out (fence, CTA-wide sync)
+        if (pub_slot >= 0) __threadfence();
         if (NW == 1) {
             job = 0;
-            if (lane == 0) job = atomicAdd(counter, 1);
+            __syncwarp();
+            if (lane == 0) {
+                if (pub_slot >= 0) spec_publish(prog + pub_slot, spec_final(pub_stat, state + pub_slot));
+                job = atomicAdd(counter, 1);
+            }
             job = __shfl_sync(0xffffffffu, job, 0);
         } else if constexpr (CL > 1) {
             cg::this_cluster().sync();           // every CTA is done with the previous pair (and with its mailboxes)
-            if (tid == 0) s_job = atomicAdd(counter, 1);
+            if (tid == 0) {
+                if (pub_slot >= 0) spec_publish(prog + pub_slot, spec_final(s_spec, state + pub_slot));
+                s_job = atomicAdd(counter, 1); s_spec = 0;
+            }
+            if (threadIdx.x == 0) s_astop = 0x7fffffff;
             cg::this_cluster().sync();
             job = *rem_job;
         } else {
             __syncthreads();
-            if (tid == 0) s_job = atomicAdd(counter, 1);
+            if (tid == 0) {
+                if (pub_slot >= 0) spec_publish(prog + pub_slot, spec_final(s_spec, state + pub_slot));
+                s_job = atomicAdd(counter, 1); s_spec = 0; s_astop = 0x7fffffff;
+            }
             __syncthreads();
             job = s_job;
         }
+        pub_slot = -1; pub_stat = 0;
         if (job >= njobs) break;
         const BandJob J = jobs[job];
         if (J.lasti == 0) continue;
+        // speculative fill: wait until the previous doubling's fill has left the stale EB entries this one starts from
+        const bool spec = (J.swaped & 128) != 0;
+        if (spec && J.dep >= 0) {
+            int st0 = 0;                      // 1 = gave up, 2 = an earlier doubling stopped: nothing to do
+            auto judge = [&](int v) { return v >= SPEC_STOP ? 2 : (v < J.need ? 1 : 0); };
+            if (NW == 1) {
+                if (lane == 0) st0 = judge(spec_wait(prog + J.dep, J.need));
+                st0 = __shfl_sync(0xffffffffu, st0, 0);
+            } else if constexpr (CL > 1) {
+                if (tid == 0) s_spec = judge(spec_wait(prog + J.dep, J.need));
+                cg::this_cluster().sync();
+                st0 = *rem_spec;
+            } else {
+                if (tid == 0) s_spec = judge(spec_wait(prog + J.dep, J.need));
+                __syncthreads();
+                st0 = s_spec;
+            }
+            if (st0 != 0) {                   // nothing was touched (1: the host runs this doubling again, on its own)
+                if (tid == 0) spec_publish(prog + J.pair, st0 == 1 ? SPEC_FAILED : SPEC_ABORT);
+                continue;
+            }
+        }
+        if (spec) pub_slot = J.pair;
         // gap-free pairs (J.swaped bit 2, all jobs of a GFK launch) take the 3-state code path
         auto run = [&](auto gf_c) {
         constexpr bool GF = decltype(gf_c)::value;
@@ -323,7 +387,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         uint8_t *dbase = dir + J.dir_off;
         const int stride = J.stride;
         const int d0 = tid * D;
-        const int eh00 = st->eh00;
+        const int eh00 = spec ? J.eh00 : st->eh00;
         const int rbslot = (B - 1) - d0;  // slot holding the right border, if 0 <= rbslot < D
 
         int CB[D], EV[D], EH[D], EB[D];
@@ -344,7 +408,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     EH[u] = j0 == 0 ? (eh00 << 8) : CB[u];
                     EV[u] = INF256;
                 }
-                EB[u] = GF ? INF256 : (eb[j0] << 8);          // the stale EB row is kept unscaled in memory
+                EB[u] = GF ? INF256 : (__ldcg(eb + j0) << 8);  // the stale EB row is kept unscaled in memory (L2: another SM may have written it)
                 G[u] = (unsigned)j0 & 0xFFFFu;
             } else {
                 CB[u] = EV[u] = EH[u] = EB[u] = K[u] = INF256; G[u] = 0u;
@@ -389,6 +453,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         }
 
         const int a_end = lasti + lastj;
+        int mid_stat = 0;                               // speculative fill, thread 0 (NW == 1: its warp): 1 = gave up on the predecessor in mid-run, 2 = abandoned
+        int astop = 0x7fffffff;                         // ... last anti-diagonal to compute once the fill is abandoned
         uint8_t *dptr = dbase + (size_t)a * stride + tid * H;   // direction bytes of this thread on anti-diagonal a (advanced per iteration)
         int a_main = delta + k + 2;                     // first anti-diagonal whose band cells all have i >= 1, j >= 1
         if ((a_main ^ a) & 1) ++a_main;
@@ -397,6 +463,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         // one loop iteration = anti-diagonals a (even diagonals) and a+1 (odd diagonals)
         auto iteration = [&](auto edge_c) {
             constexpr bool EDGE = decltype(edge_c)::value;
+            if (NW > 1 && spec) astop = *(volatile int *)&s_astop;
             // next window entries: issued now, consumed after both sub-steps (hides the L1/L2 latency)
             int4 nrow = make_int4(0, 0, 0, 0), ncol = make_int4(0, 0, 0, 0);
             if (warp_in_band) {
@@ -508,12 +575,39 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             }
             // the stale EB row: every slot was written once in this iteration (even slots in the first sub-step), so one
             // rare block serves both; it keeps the address arithmetic of the stale row out of the cells
-            if (stale_hit && warp_in_band)
+            if (stale_hit && warp_in_band && !(spec && (NW == 1 ? mid_stat : *rem_spec) != 0))
             sfor<D>([&](auto uc) {
                 constexpr int u = decltype(uc)::value;
                 const int i = i0 - u / 2, j = j0 + (u + 1) / 2, d = d0 + u;
                 if (!(i & 1) && (d <= 1 || i == istar) && d < B && i >= 1 && i <= lasti && j >= 0 && j <= lastj) eb[j] = EB[u] >> 8;
             });
+            // speculative fills, every 16th iteration, the thread of the two leftmost diagonals (the one furthest down
+            // the matrix): say how far the stale row is written, and stay behind the previous doubling's fill so that
+            // the stores to the shared row land in the order of the doublings
+            if (spec && (it & 15) == 15 && !GF) {
+                if (tid == 0 && mid_stat == 0) {
+                    spec_publish(prog + J.pair, i0);
+                    if (J.dep >= 0) {
+                        const int want = (i0 + 18 >= istar) ? SPEC_DONE : i0 + 18;
+                        const int v = spec_wait(prog + J.dep, want);
+                        if (v >= SPEC_STOP) {
+                            // an earlier doubling is the result: every warp leaves the loop after the same anti-diagonal,
+                            // far enough ahead that all of them have seen the new bound by then
+                            mid_stat = 2;
+                            astop = a + (CL > 1 ? 192 : 64);
+                            if (NW > 1) {
+                                *rem_spec = 2;
+                                if constexpr (CL > 1) { for (int r = 0; r < CL; ++r) *(volatile int *)cg::this_cluster().map_shared_rank(&s_astop, r) = astop; }
+                                else *(volatile int *)&s_astop = astop;
+                            }
+                        } else if (v < want) {
+                            mid_stat = 1;
+                            if (NW > 1) *rem_spec = 1;
+                        }
+                    }
+                }
+                if (NW == 1) { mid_stat = __shfl_sync(0xffffffffu, mid_stat, 0); astop = __shfl_sync(0xffffffffu, astop, 0); }
+            }
             // the window entries prefetched at the top are first touched here: the load had the whole iteration to land
             asm volatile("" : "+r"(nrow.x), "+r"(nrow.y), "+r"(nrow.w), "+r"(ncol.x), "+r"(ncol.y), "+r"(ncol.w));
             // ---- slide the windows one row down / one column right ----
@@ -526,8 +620,8 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         };
 
         if (!P2P || warp_in_band) {
-            for (; a <= a_end && a < a_main; a += 2) iteration(std::true_type{});
-            for (; a <= a_end; a += 2) iteration(std::false_type{});
+            for (; a <= a_end && a < a_main && a <= astop; a += 2) iteration(std::true_type{});
+            for (; a <= a_end && a <= astop; a += 2) iteration(std::false_type{});
             if (has_left) pair_wait(bar_O_left);   // drains the last arrive of the left neighbour
         }
 
@@ -542,11 +636,17 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     fin >>= 8;
                     if (GF) fin += g0[lastj] + (int)(rowpk[J.off_i + lasti] & 0x0FFFFFFFu);
                     st->cost = fin;
-                    st->gapnum = max((int)(G[u] & 0xFFFFu), (int)(G[u] >> 16));
+                    const int gapnum = max((int)(G[u] & 0xFFFFu), (int)(G[u] >> 16));
+                    st->gapnum = gapnum;
+                    if (spec) {     // the stop rule (algn_newkk_test_aff; k_band_finish evaluates the same on its own): later doublings look at it
+                        const int p = (J.T - delta) / 2, newp = (2 * J.T - delta) / 2;
+                        st->done = (gapnum < p || newp - lastj + 1 >= 0) ? 1 : 0;
+                    }
                 }
             });
         }
         if (tid == 0 && min(k, lasti) >= 2) st->eh00 = POY_INF;  // an even row wrote EH[.][0] = INF into row buffer 0
+        if (NW == 1) pub_stat = mid_stat;
         };
         // one kind of pair per launch (GFK): the 3-state path needs ~35 fewer registers, i.e. one more resident CTA
         if constexpr (GFK) run(std::true_type{}); else run(std::false_type{});
@@ -556,7 +656,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
 
 template <int D, int NW>
 static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
-                              bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+                              bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_prog) {
     cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
     if (e != cudaSuccess) return e;
     constexpr int WPB = NW == 1 ? 8 : NW;
@@ -565,7 +665,7 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
     const int cap = ctx->sm_count * 6;   // more CTAs than can be resident just queue behind the persistent ones
     if (blocks > cap) blocks = cap;
 #define LAUNCH(GFV, DIRV) k_band2<D, NW, WPB, GFV, DIRV><<<blocks, WPB * 32, 0, ctx->stream>>>(cm->d, pool->d_rowp, pool->d_colp, \
-        pool->d_h0, pool->d_g0, pool->d_rowpk, d_jobs, njobs, d_counter, d_state, d_ebrow, d_dir)
+        pool->d_h0, pool->d_g0, pool->d_rowpk, d_jobs, njobs, d_counter, d_state, d_ebrow, d_dir, d_prog)
     if (gapfree) { if (probe) LAUNCH(true, false); else LAUNCH(true, true); }
     else { if (probe) LAUNCH(false, false); else LAUNCH(false, true); }
 #undef LAUNCH
@@ -576,7 +676,7 @@ static cudaError_t launch_one(poy_ctx *ctx, const poy_cm *cm, const poy_pool *po
 // one pair per cluster of CL CTAs (NW warps each): persistent clusters, one CTA per SM
 template <int D, int NW, int CL>
 static cudaError_t launch_cluster(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
-                                  bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir) {
+                                  bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_prog) {
     cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
     if (e != cudaSuccess) return e;
     const int nclusters = std::max(1, std::min(njobs, ctx->sm_count / CL));
@@ -589,7 +689,7 @@ static cudaError_t launch_cluster(poy_ctx *ctx, const poy_cm *cm, const poy_pool
     const DevCM *a0 = cm->d; const int4 *a1 = pool->d_rowp, *a2 = pool->d_colp; const int *a3 = pool->d_h0, *a4 = pool->d_g0;
     const unsigned *a5 = pool->d_rowpk;
 #define LAUNCHC(GFV, DIRV) e = cudaLaunchKernelEx(&cfg, k_band2<D, NW, NW, GFV, DIRV, CL>, a0, a1, a2, a3, a4, a5, d_jobs, njobs, d_counter, \
-                                                  d_state, d_ebrow, d_dir)
+                                                  d_state, d_ebrow, d_dir, d_prog)
     if (gapfree) { if (probe) LAUNCHC(true, false); else LAUNCHC(true, true); }
     else { if (probe) LAUNCHC(false, false); else LAUNCHC(false, true); }
 #undef LAUNCHC
@@ -616,7 +716,7 @@ int band2_stride_for(int cls, long long B) {
 // with 2 or 4 diagonals per thread: the per-sub-step dependency chain shrinks accordingly.  The direction-byte
 // layout (byte d/2 of anti-diagonal a) and the stride do not depend on the shape, so the traceback is unchanged.
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
-                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, bool lowlat) {
+                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, bool lowlat, int *d_prog) {
     if (njobs <= 0) return cudaSuccess;
     // Cluster shapes (one pair over 2 or 4 SMs, 4 diagonals per thread): latency-bound rounds with bands of 1280 diagonals
     // and more, where a fill lasts as long as the issue rate of ONE SM allows.  POY_CLUSTER=0 turns them off, 2 forces
@@ -625,11 +725,11 @@ cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, c
         const char *ce = getenv("POY_CLUSTER");
         const bool off = ce && ce[0] == '0', forced = ce && ce[0] == '2';
         if (!off && njobs < 60000 && (forced || (lowlat && cls >= 1280))) {
-            if (cls <= 2048) return launch_cluster<4, 8, 2>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir);
-            if (cls == 4096) return launch_cluster<4, 8, 4>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir);
+            if (cls <= 2048) return launch_cluster<4, 8, 2>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir, d_prog);
+            if (cls == 4096) return launch_cluster<4, 8, 4>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir, d_prog);
         }
     }
-#define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir)
+#define L1(DD, WW) return launch_one<DD, WW>(ctx, cm, pool, d_jobs, njobs, gapfree, probe, d_counter, d_state, d_ebrow, d_dir, d_prog)
     if (lowlat)
         switch (cls) {
             case 128: L1(2, 2);

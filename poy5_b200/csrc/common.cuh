@@ -144,7 +144,16 @@ struct BandJob {          // one band fill of one pair
     int stride;           // bytes per anti-diagonal in the direction arena
     int64_t dir_off;      // byte offset of this pair's direction block in the arena
     int64_t eb_off;       // int offset of this pair's stale-EB row in the state arena
+    // speculative threshold doublings (host.cu, align_impl; swaped bit 7 set): several fills of one pair run at once,
+    // each behind its predecessor.  dep = progress slot of the previous doubling's fill (-1: none), need = the row that
+    // fill must have completed before this one may read the stale EB row (SPEC_DONE: all of it), T / eh00 = threshold
+    // and EH[0][0] of THIS fill (the per-slot PairState then only receives results)
+    int dep, need, T, eh00;
 };
+#define SPEC_DONE 0x40000000      // progress value of a completed fill whose stop rule did not fire
+#define SPEC_STOP 0x40000001      // ... of a completed fill whose stop rule fired: the doublings after it are not needed
+#define SPEC_ABORT 0x40000002     // ... of a fill abandoned because an earlier doubling stopped
+#define SPEC_FAILED (-1)          // ... of one that gave up waiting for its predecessor (the host re-runs it)
 
 struct PairState {        // survives across band fills of the same pair
     int T;                // current threshold
@@ -186,7 +195,8 @@ cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, co
 cudaError_t launch_cost_affine(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const CostJob *d_jobs, int njobs,
                                int *d_counter, int4 *d_bound, size_t bound_stride, int blocks, int *d_cost, int wide);
 cudaError_t launch_band2(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
-                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, bool lowlat = false);
+                         bool gapfree, bool probe, int *d_counter, PairState *d_state, int *d_ebrow, uint8_t *d_dir, bool lowlat = false,
+                         int *d_prog = nullptr);
 int band2_class_for(long long B);
 int band2_stride_for(int cls, long long B);
 cudaError_t launch_band_lin(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs, int cls,
@@ -200,7 +210,7 @@ cudaError_t launch_band_generic(poy_ctx *ctx, const poy_cm *cm, const poy_pool *
                                 PairState *d_state, int *d_ebrow, uint8_t *d_dir, int *d_work, size_t work_stride,
                                 int blocks);
 cudaError_t launch_band_finish(poy_ctx *ctx, const BandJob *d_jobs, int njobs, PairState *d_state, uint8_t *d_done,
-                               const int *d_g0, int gap_open);
+                               const int *d_g0, int gap_open, const int *d_prog = nullptr);
 cudaError_t launch_traceback(poy_ctx *ctx, const poy_cm *cm, const poy_pool *pool, const BandJob *d_jobs, int njobs,
                              const uint8_t *d_done, const uint8_t *d_dir, const int64_t *d_out_off, uint8_t *d_median,
                              uint8_t *d_medianwg, uint8_t *d_resi, uint8_t *d_resj, int *d_out_len);

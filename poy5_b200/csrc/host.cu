@@ -617,6 +617,8 @@ struct HostPair {
     int iterations;
     int64_t cells;
     bool done;
+    bool eh00_inf;     // some earlier fill of this pair had min(k, lasti) >= 2: it left EH[0][0] = INF behind (k_band2)
+    bool state_dirty;  // speculative rounds moved T / EH[0][0] on without the device copy of the pair's state
 };
 
 // number of band cells of one fill (rows 1..lasti, columns max(i-k,0)..min(i+delta+k,lastj))
@@ -651,7 +653,14 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     if (n == 0) return POY_OK;
     const bool want_trace = d_median || d_medianwg || d_resi || d_resj || d_out_len;
     if (want_trace && !d_out_off) return poy_fail(ctx, POY_ERR_ARG, "out_off is required when any traceback output is requested");
-    std::vector<HostPair> hp((size_t)n);
+    // Speculative threshold doublings (latency-bound rounds only, see the round loop): up to SPEC_EXTRA extra fills per
+    // round, each a clone of its pair at a later threshold, appended to hp behind the n real pairs.  Every per-pair
+    // array below is sized for n + SPEC_EXTRA entries.
+    const int SPEC_EXTRA = 160;
+    const size_t nx = (size_t)n + SPEC_EXTRA;
+    std::vector<HostPair> hp;
+    hp.reserve(nx);
+    hp.resize((size_t)n);
     int64_t eb_total = 0, maxsum = 0;
     for (int p = 0; p < n; ++p) {
         const int a = h_si[p], b = h_sj[p];
@@ -663,6 +672,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         if (h.lastj < h.lasti) return poy_fail(ctx, POY_ERR_ORDER, "pass the shorter one as first");
         h.T = (h.lastj - h.lasti + 1) * cm->min_non0;  // algn_fill_plane_3_aff, src/algn.c:2348-2349
         h.iterations = 0; h.cells = 0; h.done = false; h.fullplane = 0; h.probe = 0; h.want_dirs = 0; h.repeat = 0;
+        h.eh00_inf = false; h.state_dirty = false;
         if (linear) {   // algn_nw_limit / algn_fill_plane_2: full plane or Ukkonen band (src/algn.c:2963, 1141-1176)
             const int lenX = h.lasti + 1, lenY = h.lastj + 1;
             int height = (lenX - lenY) + 50 + h_deltawh[p];
@@ -707,18 +717,20 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     }
 
     void *v_state, *v_eb, *v_jobs, *v_jobs_b, *v_misc, *v_pin, *v_pin2;
-    if ((s = poy_scratch(ctx, SL_STATE, sizeof(PairState) * (size_t)n + 3 * (size_t)n, &v_state)) != POY_OK) return s;
+    const size_t nx4 = (nx + 3) & ~(size_t)3;
+    if ((s = poy_scratch(ctx, SL_STATE, sizeof(PairState) * nx + 3 * nx4 + sizeof(int) * nx, &v_state)) != POY_OK) return s;
     if ((s = poy_scratch(ctx, SL_EBROW, sizeof(int) * 2 * (size_t)eb_total + 16, &v_eb)) != POY_OK) return s;   // rows + their snapshots
-    if ((s = poy_scratch(ctx, SL_JOBS, sizeof(BandJob) * (size_t)n, &v_jobs)) != POY_OK) return s;
-    if ((s = poy_scratch(ctx, SL_JOBSB, sizeof(BandJob) * (size_t)n, &v_jobs_b)) != POY_OK) return s;
+    if ((s = poy_scratch(ctx, SL_JOBS, sizeof(BandJob) * (nx + SPEC_EXTRA), &v_jobs)) != POY_OK) return s;     // fills + the traceback jobs of a speculative round
+    if ((s = poy_scratch(ctx, SL_JOBSB, sizeof(BandJob) * (nx + SPEC_EXTRA), &v_jobs_b)) != POY_OK) return s;
     if ((s = poy_scratch(ctx, SL_MISC, 256, &v_misc)) != POY_OK) return s;
-    if ((s = poy_pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (size_t)n, &v_pin)) != POY_OK) return s;
-    if ((s = poy_pinned(ctx, 1, (size_t)n + sizeof(int32_t) * (size_t)n, &v_pin2)) != POY_OK) return s;
+    if ((s = poy_pinned(ctx, 0, std::max(sizeof(BandJob), sizeof(PairState)) * (nx + SPEC_EXTRA), &v_pin)) != POY_OK) return s;
+    if ((s = poy_pinned(ctx, 1, nx + sizeof(int32_t) * nx, &v_pin2)) != POY_OK) return s;
     PairState *d_state = (PairState *)v_state;
-    uint8_t *d_done = (uint8_t *)(d_state + n);
+    uint8_t *d_done = (uint8_t *)(d_state + nx);
     // the verdicts as the traceback of a round must see them: the next round's stop rule overwrites d_done while the
     // traceback of this one may still be running
-    uint8_t *d_done_tb[2] = { d_done + n, d_done + 2 * (size_t)n };
+    uint8_t *d_done_tb[2] = { d_done + nx4, d_done + 2 * nx4 };
+    int *d_prog = (int *)(d_done + 3 * nx4);     // progress words of speculative fills, one per hp entry
     int *d_eb = (int *)v_eb, *d_eb_snap = d_eb + eb_total;
     BandJob *d_jobs_ab[2] = { (BandJob *)v_jobs, (BandJob *)v_jobs_b };
     int *d_counter = (int *)v_misc;
@@ -731,15 +743,17 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         PairState *hs = (PairState *)v_pin;
         for (int p = 0; p < n; ++p) { hs[p].T = hp[p].T; hs[p].eh00 = cm->h.gap_open; hs[p].cost = 0; hs[p].gapnum = 0; hs[p].iterations = 0; hs[p].done = 0; hs[p].cells = 0; }
         CK(cudaMemcpyAsync(d_state, hs, sizeof(PairState) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(d_done, 0, (size_t)n, ctx->stream));
+        CK(cudaMemsetAsync(d_done, 0, nx, ctx->stream));
     }
     CK(launch_fill_int(ctx, d_eb, eb_total, POY_INF));
     CK(cudaStreamSynchronize(ctx->stream));  // pinned staging is reused below
 
     std::vector<int> active((size_t)n);
     for (int p = 0; p < n; ++p) active[p] = p;
-    std::vector<int> order;
+    std::vector<int> order, rjobs;
     std::vector<uint64_t> keys;
+    struct Clone { int real, prev; };   // the pair a speculative fill belongs to, the hp entry of the previous doubling
+    std::vector<Clone> clones;
     const int gen_blocks = ctx->sm_count * 2;
 
     const char *tr = getenv("POY_TRACE");
@@ -756,6 +770,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const bool forced = pe && pe[0] == '2';
     const bool use_probes = !(pe && pe[0] == '0') && (n >= std::min(probe_min, probe_min4) || forced);
     const bool probe_gf = forced || n >= probe_min, probe_4s = forced || n >= probe_min4;
+    const char *spe = getenv("POY_SPEC");   // POY_SPEC=0: one fill per pair and round, always
+    const bool spec_allowed = !linear && !use_probes && !force_generic && !(spe && spe[0] == '0');
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
     // POY_LOWLAT=0 turns the low-latency kernel shapes off, 2 forces them (test hook); default: rounds with at most
@@ -765,8 +781,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         ++rounds;
         const bool lowlat = !(ll && ll[0] == '0') && ((ll && ll[0] == '2') || (int64_t)active.size() <= 2 * (int64_t)ctx->sm_count);
         // band geometry of this round (algn_newkk_increaseT_aff / algn_newkk_test_aff, src/algn.c:2311-2336, 2195-2196)
-        for (int p : active) {
-            HostPair &h = hp[p];
+        auto geometry = [&](HostPair &h) {
             const int delta = h.lastj - h.lasti;
             const int pp = (h.T - delta) / 2;
             if (!linear) h.k = pp >= h.lasti ? h.lasti - 1 : pp;           // src/algn.c:2195-2196 (lenX = last index)
@@ -792,23 +807,91 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 }
             }
             h.dir_bytes = h.probe ? 0 : h.work;
+        };
+        hp.resize((size_t)n);            // (drops the clones of the previous round)
+        for (int p : active) {
+            HostPair &h = hp[p];
+            geometry(h);
             if (h.probe) ++n_probe; else ++n_full;
             if (!h.repeat) h.iterations++;
             h.cells += h.fullplane ? (int64_t)h.lasti * (h.lastj + 1) : band_cells(h.lasti, h.lastj, h.k);
         }
+        // Speculative doublings.  In a latency-bound round most SMs idle while every pair waits for ONE wavefront, and a
+        // pair then goes through 4-8 such rounds.  So the next doublings of each pair are filled in the same round, as
+        // clones of the pair at 2T, 4T, ...: each fill needs from its predecessor only the stale EB entries of columns
+        // 0 .. delta + k (written by the predecessor's two leftmost diagonals within its first delta + k + k' rows) and
+        // EH[0][0] (known beforehand), so it starts a few rows behind it and stays behind (k_band2: progress words).
+        // The first fill of the chain whose stop rule fires is the result, later ones are discarded; the stale row is
+        // shared and written in the order of the doublings, so whatever comes next starts from the same state as in
+        // the one-fill-per-round schedule.  The chain ends at a fill that certainly stops (its doubled band spans the
+        // matrix), when the CTAs no longer fit the GPU at once (the fills wait for each other: all must be resident),
+        // or when the direction bytes no longer fit the arena.  POY_SPEC=0 turns this off.
+        clones.clear();
+        bool spec_round = false;
+        if (spec_allowed && lowlat) {
+            auto ctas_of = [](int cls) { return cls <= 1024 ? 1 : (cls <= 2048 ? 2 : 4); };
+            int budget = ctx->sm_count - 16;
+            int64_t arena_used = 0;
+            bool ok = true;
+            for (int p : active) {
+                const HostPair &h = hp[p];
+                budget -= ctas_of(h.dclass);
+                arena_used += (h.dir_bytes + 255) & ~255ll;
+            }
+            if (budget < 0 || (uint64_t)arena_used * 4 > ctx->arena_limit) ok = false;
+            std::vector<int> tail(active.begin(), active.end());
+            std::vector<char> open(active.size(), 1);
+            for (int lvl = 1; ok && lvl < 8; ++lvl) {
+                bool any = false;
+                for (size_t qi = 0; qi < active.size(); ++qi) {
+                    if (!open[qi]) continue;
+                    open[qi] = 0;
+                    const HostPair prev = hp[tail[qi]];
+                    const int delta = prev.lastj - prev.lasti;
+                    if (prev.lasti == 0 || prev.dclass == 0 || prev.T > (1 << 27)) continue;
+                    if ((2 * prev.T - delta) / 2 - prev.lastj + 1 >= 0) continue;      // prev always stops
+                    HostPair c = prev;
+                    c.T = prev.T * 2; c.want_dirs = 0; c.repeat = 0;
+                    geometry(c);
+                    if (c.dclass == 0) continue;
+                    const int64_t bytes = (c.dir_bytes + 255) & ~255ll;
+                    if (ctas_of(c.dclass) > budget || (uint64_t)(arena_used + bytes) * 4 > ctx->arena_limit ||
+                        (uint64_t)(arena_used + bytes) > (1ull << 30) || (int)clones.size() >= SPEC_EXTRA) continue;
+                    budget -= ctas_of(c.dclass); arena_used += bytes;
+                    clones.push_back({ active[qi], tail[qi] });
+                    hp.push_back(c);
+                    tail[qi] = (int)hp.size() - 1;
+                    open[qi] = 1; any = true;
+                }
+                if (!any) break;
+            }
+            spec_round = !clones.empty();
+        }
+        if (!spec_round)
+            for (int p : active)
+                if (hp[p].state_dirty) {     // back to one fill per round: the device copy of T / EH[0][0] catches up
+                    const int v[2] = { hp[p].T, hp[p].eh00_inf ? POY_INF : cm->h.gap_open };
+                    CK(cudaMemcpyAsync(&d_state[p].T, v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+                    hp[p].state_dirty = false;
+                }
+        rjobs.assign(active.begin(), active.end());
+        for (size_t c = 0; c < clones.size(); ++c) rjobs.push_back(n + (int)c);
+        n_full += (long long)clones.size();
         // order: by kernel class, 4-state pairs before gap-free ones, then by size (largest first, in 1 KiB steps) for
         // load balance; packed into one integer key so the sort touches no other memory
-        keys.resize(active.size());
-        for (size_t q = 0; q < active.size(); ++q) {
-            const HostPair &h = hp[active[q]];
+        // (speculative rounds: narrow classes first, the wider fills of a chain wait for them)
+        keys.resize(rjobs.size());
+        for (size_t q = 0; q < rjobs.size(); ++q) {
+            const HostPair &h = hp[rjobs[q]];
             const uint64_t size_q = (uint64_t)std::min<int64_t>(h.work >> 10, (1 << 17) - 1);
-            keys[q] = ((uint64_t)(4096 - h.dclass) << 51) | ((uint64_t)(h.gapfree ? 1 : 0) << 50) | ((uint64_t)(h.probe ? 1 : 0) << 49) |
-                      ((((uint64_t)1 << 17) - 1 - size_q) << 32) | (uint32_t)active[q];
+            keys[q] = ((uint64_t)(spec_round ? h.dclass : 4096 - h.dclass) << 51) | ((uint64_t)(h.gapfree ? 1 : 0) << 50) | ((uint64_t)(h.probe ? 1 : 0) << 49) |
+                      ((((uint64_t)1 << 17) - 1 - size_q) << 32) | (uint32_t)rjobs[q];
         }
         std::sort(keys.begin(), keys.end());
-        order.resize(active.size());
-        for (size_t q = 0; q < active.size(); ++q) order[q] = (int)(uint32_t)keys[q];
+        order.resize(rjobs.size());
+        for (size_t q = 0; q < rjobs.size(); ++q) order[q] = (int)(uint32_t)keys[q];
         size_t pos = 0;
+        int w_par = 0; bool w_single = false; BandJob *w_jobs = nullptr; uint8_t *w_dir = nullptr;   // the last wave (speculative rounds have one)
         while (pos < order.size()) {
             // one wave: as many pairs as fit in the direction arena
             int64_t used = 0;
@@ -845,14 +928,29 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 const HostPair &h = hp[p];
                 BandJob &j = hj[q];
                 j.off_i = h.off_i; j.off_j = h.off_j; j.lasti = h.lasti; j.lastj = h.lastj; j.k = h.k; j.pair = p;
-                j.swaped = (h_swaped ? (h_swaped[p] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0) | ((!linear && h.gapfree) ? 4 : 0) |
+                j.swaped = (h_swaped ? (h_swaped[p < n ? p : clones[p - n].real] ? 1 : 0) : 0) | (h.fullplane ? 2 : 0) | ((!linear && h.gapfree) ? 4 : 0) |
                            (h.probe ? 8 : 0) | (want_trace ? 0 : 16) | (h.repeat ? 32 : 0) |
                            ((!linear && h.dclass != 0) ? 64 : 0);
                 j.stride = h.stride; j.dir_off = doff; j.eb_off = h.eb_off;
+                j.dep = -1; j.need = 0; j.T = h.T; j.eh00 = 0;
+                if (spec_round && h.dclass != 0 && h.lasti != 0) {
+                    j.swaped |= 128;
+                    // EH[0][0] as the doublings before this one leave it
+                    bool inf = hp[p < n ? p : clones[p - n].real].eh00_inf;
+                    for (int x = p; x >= n; ) { x = clones[x - n].prev; if (std::min(hp[x].k, hp[x].lasti) >= 2) inf = true; }
+                    j.eh00 = inf ? POY_INF : cm->h.gap_open;
+                    if (p >= n && !h.gapfree) {
+                        const HostPair &pv = hp[clones[p - n].prev];
+                        j.dep = clones[p - n].prev;
+                        j.need = (h.lastj - h.lasti) + h.k + pv.k + 2;
+                        if (j.need + 20 >= h.lasti) j.need = SPEC_DONE;     // (the progress word moves in steps of 16 rows)
+                    }
+                }
                 doff += (h.dir_bytes + 255) & ~255ll;
                 if (h.dclass == 0) gen_width = std::max<int64_t>(gen_width, (int64_t)(h.lastj - h.lasti) + 2 * h.k + 1);
             }
             CK(cudaMemcpyAsync(d_jobs, hj, sizeof(BandJob) * (size_t)nj, cudaMemcpyHostToDevice, ctx->stream));
+            if (spec_round) CK(cudaMemsetAsync(d_prog, 0, sizeof(int) * nx, ctx->stream));
             if (!linear && eb_total > 0 && want_trace && use_probes) CK(launch_stale_snapshot(ctx, d_jobs, nj, d_state, d_eb, d_eb_snap));
             // launch per band class (contiguous after the sort).  The launches of a wave are independent: they go to
             // round-robin auxiliary streams (fork / join with events) and each gets its own work counter.
@@ -872,7 +970,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 if (cls != 0) {
                     cudaError_t le;
                     if (linear) le = launch_band_lin(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, d_counter + (nlaunch & 15), d_state, d_dir);
-                    else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, pr != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir, lowlat);
+                    else le = launch_band2(ctx, cm, pool, d_jobs + q0, q1 - q0, cls, gf != 0, pr != 0, d_counter + (nlaunch & 15), d_state, d_eb, d_dir, lowlat, d_prog);
                     if (le != cudaSuccess) { ctx->stream = main_stream; return poy_cuda_fail(ctx, le, "band fill launch"); }
                 } else {
                     void *v_work;
@@ -897,8 +995,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                 }
             // stop rule on the device, then traceback of the pairs that stopped (others return immediately)
             if (linear) CK(launch_lin_finish(ctx, pool, d_jobs, nj, d_state, d_done));
-            else CK(launch_band_finish(ctx, d_jobs, nj, d_state, d_done, pool->d_g0, cm->h.gap_open));
-            if (want_trace) {
+            else CK(launch_band_finish(ctx, d_jobs, nj, d_state, d_done, pool->d_g0, cm->h.gap_open, d_prog));
+            if (want_trace && !spec_round) {
                 const uint8_t *tb_done = d_done;
                 if (single_wave) {
                     CK(cudaMemcpyAsync(d_done_tb[par], d_done, (size_t)n, cudaMemcpyDeviceToDevice, main_stream));
@@ -920,19 +1018,72 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             { const double t = now(); t_wait += t - t_mark; t_mark = t; }
             ++waves;
             pos = end;
+            w_par = par; w_single = single_wave; w_jobs = d_jobs; w_dir = d_dir;
         }
-        CK(cudaMemcpyAsync(h_done, d_done, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_done, d_done, spec_round ? nx : (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (trace_rounds) {
             int hist[4097 / 64 + 1] = {0}, ngf = 0, npr = 0;
-            for (int p : active) { hist[hp[p].dclass / 64]++; ngf += hp[p].gapfree; npr += hp[p].probe; }
-            fprintf(stderr, "[poy5_b200]   round %d: %zu active (%d gap-free, %d probes), %.2f ms since batch start; classes:", rounds,
-                    active.size(), ngf, npr, (t_prep + t_wait) * 1e3);
+            for (int p : rjobs) { hist[hp[p].dclass / 64]++; ngf += hp[p].gapfree; npr += hp[p].probe; }
+            fprintf(stderr, "[poy5_b200]   round %d: %zu active + %zu speculative (%d gap-free, %d probes), %.2f ms since batch start; classes:", rounds,
+                    active.size(), clones.size(), ngf, npr, (t_prep + t_wait) * 1e3);
             for (int c = 0; c <= 4096 / 64; ++c) if (hist[c]) fprintf(stderr, " %d:%d", c * 64, hist[c]);
             fprintf(stderr, "\n");
         }
         std::vector<int> next;
         next.reserve(active.size());
+        if (spec_round) {
+            // per pair: walk its chain in the order of the doublings; the first fill that stopped is the result
+            std::vector<int> nxt(hp.size(), -1), posq(hp.size(), -1);
+            for (size_t c = 0; c < clones.size(); ++c) nxt[clones[c].prev] = n + (int)c;
+            for (size_t q = 0; q < order.size(); ++q) posq[order[q]] = (int)q;
+            BandJob *hj = (BandJob *)v_pin, *htb = hj + nx;
+            int ntb = 0;
+            for (int p : active) {
+                HostPair &h = hp[p];
+                if (h.dclass == 0 || h.lasti == 0) {          // not part of the speculation: the plain verdicts
+                    const int verdict = h_done[p];
+                    if (verdict == 1) { h.done = true; htb[ntb++] = hj[posq[p]]; continue; }
+                    h.T *= 2; h.want_dirs = 0; h.repeat = 0;
+                    next.push_back(p);
+                    continue;
+                }
+                int winner = -1, nextT = h.T;
+                bool first = true;
+                for (int x = p; x >= 0; x = nxt[x]) {
+                    const int verdict = h_done[x];
+                    if (verdict >= 5) { ++n_repeat; break; }        // this fill gave up on its predecessor: next round starts here
+                    if (!first) { h.iterations++; h.cells += band_cells(hp[x].lasti, hp[x].lastj, hp[x].k); }
+                    first = false;
+                    if (std::min(hp[x].k, hp[x].lasti) >= 2) h.eh00_inf = true;
+                    if (verdict == 1) { winner = x; break; }
+                    nextT = hp[x].T * 2;
+                }
+                if (winner < 0) { h.T = nextT; h.want_dirs = 0; h.repeat = 0; h.state_dirty = true; next.push_back(p); continue; }
+                h.done = true;
+                h.T = hp[winner].T; h.k = hp[winner].k; h.dclass = hp[winner].dclass; h.stride = hp[winner].stride;
+                if (winner != p) CK(cudaMemcpyAsync(d_state + p, d_state + winner, sizeof(PairState), cudaMemcpyDeviceToDevice, ctx->stream));
+                htb[ntb] = hj[posq[winner]];
+                htb[ntb].pair = p;
+                ++ntb;
+            }
+            if (want_trace && ntb > 0) {
+                BandJob *d_tb = w_jobs + nx;
+                CK(cudaMemcpyAsync(d_tb, htb, sizeof(BandJob) * (size_t)ntb, cudaMemcpyHostToDevice, ctx->stream));
+                cudaStream_t main_stream = ctx->stream;
+                if (w_single) {
+                    CK(cudaEventRecord(ctx->ev_fin, main_stream));
+                    CK(cudaStreamWaitEvent(ctx->tb_stream, ctx->ev_fin, 0));
+                    ctx->stream = ctx->tb_stream;
+                }
+                cudaError_t te = launch_traceback(ctx, cm, pool, d_tb, ntb, nullptr, w_dir, d_out_off, d_median, d_medianwg, d_resi, d_resj, d_out_len);
+                ctx->stream = main_stream;
+                if (te != cudaSuccess) return poy_cuda_fail(ctx, te, "traceback launch");
+                if (w_single) { CK(cudaEventRecord(ctx->ev_tb_done[w_par], ctx->tb_stream)); ctx->tb_pending[w_par] = true; }
+            }
+            active.swap(next);
+            continue;
+        }
         for (int p : active) {
             const int verdict = h_done[p];   // k_band_finish / k_lin_finish
             if (verdict == 1) { hp[p].done = true; continue; }

@@ -32,11 +32,20 @@ cudaError_t launch_build_cost_jobs(poy_ctx *ctx, const poy_pool *pool, int n, co
 
 // ---- stop rule of algn_newkk_increaseT_aff (src/algn.c:2319-2335) -----------------------------------
 __global__ void k_band_finish(const BandJob *__restrict__ jobs, int njobs, PairState *state, uint8_t *done,
-                              const int *__restrict__ g0, int gap_open) {
+                              const int *__restrict__ g0, int gap_open, const int *prog) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= njobs) return;
     const BandJob J = jobs[t];
     PairState *st = state + J.pair;
+    if (J.swaped & 128) {
+        // speculative fill: threshold from the job, no state carried on the device; 5 = the fill did not run
+        const int pv = prog[J.pair];
+        if (pv != SPEC_DONE && pv != SPEC_STOP) { done[J.pair] = pv == SPEC_ABORT ? 6 : 5; return; }
+        const int delta = J.lastj - J.lasti, T = J.T;
+        const int p = (T - delta) / 2, newp = (2 * T - delta) / 2;
+        done[J.pair] = ((st->gapnum < p) || (newp - J.lastj + 1 >= 0)) ? 1 : 0;
+        return;
+    }
     int fin;
     if (J.lasti == 0) {
         // no rows: final_cost_matrix keeps the value initialize_matrices_affine gave it (src/algn.c:1879-1897);
@@ -65,9 +74,9 @@ __global__ void k_band_finish(const BandJob *__restrict__ jobs, int njobs, PairS
 }
 
 cudaError_t launch_band_finish(poy_ctx *ctx, const BandJob *d_jobs, int njobs, PairState *d_state, uint8_t *d_done,
-                               const int *d_g0, int gap_open) {
+                               const int *d_g0, int gap_open, const int *d_prog) {
     if (njobs <= 0) return cudaSuccess;
-    k_band_finish<<<(njobs + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, njobs, d_state, d_done, d_g0, gap_open);
+    k_band_finish<<<(njobs + 255) / 256, 256, 0, ctx->stream>>>(d_jobs, njobs, d_state, d_done, d_g0, gap_open, d_prog);
     ctx->launches++;
     return cudaGetLastError();
 }
