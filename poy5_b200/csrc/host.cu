@@ -656,7 +656,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     // Speculative threshold doublings (latency-bound rounds only, see the round loop): up to SPEC_EXTRA extra fills per
     // round, each a clone of its pair at a later threshold, appended to hp behind the n real pairs.  Every per-pair
     // array below is sized for n + SPEC_EXTRA entries.
-    const int SPEC_EXTRA = 160;
+    const int SPEC_EXTRA = 288;
     const size_t nx = (size_t)n + SPEC_EXTRA;
     std::vector<HostPair> hp;
     hp.reserve(nx);
@@ -830,7 +830,10 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         bool spec_round = false;
         if (spec_allowed && lowlat) {
             auto ctas_of = [](int cls) { return cls <= 1024 ? 1 : (cls <= 2048 ? 2 : 4); };
-            int budget = ctx->sm_count - 16;
+            // every fill of the round must be resident at once: CTAs of at most 256 threads and 128 registers (the launch
+            // bounds of the 8-warp shapes) fit two to an SM; POY_SPEC_CTAS overrides the budget (tuning / test hook)
+            const char *sb = getenv("POY_SPEC_CTAS");
+            int budget = sb ? atoi(sb) : 2 * ctx->sm_count - 32;
             int64_t arena_used = 0;
             bool ok = true;
             for (int p : active) {
