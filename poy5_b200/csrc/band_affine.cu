@@ -200,7 +200,9 @@ k_band_generic(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, cons
 // One WARP per pair.  The walk itself is a serial pointer chase (lane 0), so what matters is the
 // latency of each step: the warp stages a 64 x 32-byte tile of direction bytes around the current
 // cell in shared memory with one coalesced load (64 anti-diagonals x 64 diagonals), lane 0 walks
-// until it leaves the tile, and the tile is re-centred.  Results are written right to left into the
+// until it leaves the tile recording one move code per step -- nothing but the direction byte and the
+// mode is on that chain -- and the 32 lanes then emit what the steps produce (symbol loads, median
+// look-ups, four output streams) in parallel; the tile is re-centred.  Results are written right to left into the
 // caller's capacity-(leni+lenj+2) slots, i.e. exactly like seq_prepend fills a struct seq.
 #define TB_ROWS 64
 #define TB_COLS 32
@@ -209,6 +211,7 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
             const uint8_t *__restrict__ done, const uint8_t *__restrict__ dir, const int64_t *__restrict__ out_off,
             uint8_t *median, uint8_t *medianwg, uint8_t *resi, uint8_t *resj, int *out_len) {
     __shared__ __align__(16) uint8_t s_tile[4][TB_ROWS * TB_COLS];
+    __shared__ uint8_t s_moves[4][TB_ROWS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int t = blockIdx.x * 4 + w;
     if (t >= njobs) return;
@@ -234,12 +237,14 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
     int i = J.lasti, j = J.lastj;
     int mode = 4;  // 0 vertical, 1 horizontal, 2 diagonal, 3 align, 4 todo
     uint8_t *tile = s_tile[w];
+    uint8_t *mv = s_moves[w];
+    const unsigned lt = (1u << lane) - 1u;
     for (;;) {
         i = __shfl_sync(0xffffffffu, i, 0);
         j = __shfl_sync(0xffffffffu, j, 0);
         if (i == 0 || j == 0) break;
         // tile: anti-diagonals a_hi-63 .. a_hi, direction-byte columns c0 .. c0+31
-        const int a_hi = i + j;
+        const int a_hi = i + j, i_start = i, j_start = j;
         int dcur = j - i + k;
         dcur = dcur < 0 ? 0 : (dcur >= B ? B - 1 : dcur);
         int c0 = ((dcur >> 1) - 12) & ~15;
@@ -252,8 +257,10 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
                 *(uint4 *)(tile + r * TB_COLS + half * 16) = *(const uint4 *)(db + (size_t)a * stride + c0 + half * 16);
         }
         __syncwarp();
+        // phase 1, lane 0: the walk proper -- direction bytes and the mode only, one move code per step (a tile holds at
+        // most 64 steps: every step leaves its anti-diagonal)
+        int nsteps = 0;
         if (lane == 0) {
-            int ic = si[i], jc = sj[j];
             while (i != 0 && j != 0) {
                 const int r = a_hi - (i + j);
                 int d = j - i + k;
@@ -272,32 +279,57 @@ k_traceback(const DevCM *__restrict__ cm, const uint8_t *__restrict__ data, cons
                     b = t | (nx << 2) | ((b & 112u) ^ 112u) | heqv;
                 }
                 if (mode == 4) mode = b & 3;
-                if (mode == 0) {
-                    if (b & 16) mode = 4;
-                    INDEL(ic);
-                    PUT(pi, ni, ic); PUT(pj, nj, POY_GAP);
-                    --i; ic = si[i];
-                } else if (mode == 1) {
-                    if (b & 32) mode = 4;
-                    INDEL(jc);
-                    PUT(pi, ni, POY_GAP); PUT(pj, nj, jc);
-                    --j; jc = sj[j];
-                } else if (mode == 2) {
-                    if (b & 64) mode = 4;
-                    PUT(pi, ni, ic); PUT(pj, nj, jc); PUT(pw, nw, POY_GAP);
-                    --i; --j; ic = si[i]; jc = sj[j];
-                } else {
+                mv[nsteps++] = (uint8_t)mode;
+                if (mode == 0) { if (b & 16) mode = 4; --i; }
+                else if (mode == 1) { if (b & 32) mode = 4; --j; }
+                else if (mode == 2) { if (b & 64) mode = 4; --i; --j; }
+                else {
                     // gap-free pairs store no ALIGN_TO code: it equals the todo code of the cell the walk moves to
                     mode = gf_todo ? 4 : (int)((b >> 2) & 3);
-                    const int prep = cm->median32[((ic & POY_NOGAP) << 5) + (jc & POY_NOGAP)];
-                    PUT_M(prep); PUT(pw, nw, prep);
-                    PUT(pi, ni, ic); PUT(pj, nj, jc);
-                    --i; --j; ic = si[i]; jc = sj[j];
+                    --i; --j;
                 }
             }
         }
+        nsteps = __shfl_sync(0xffffffffu, nsteps, 0);
+        __syncwarp();
+        // phase 2, all lanes: what each step emits (backtrace_aff writes right to left; one element per step into the two
+        // rows and the median with gaps, the median proper only where a symbol survives)
+        int ci = 0, cj = 0;      // rows / columns consumed by the steps before this chunk
+        for (int t0 = 0; t0 < nsteps; t0 += 32) {
+            const int st = t0 + lane;
+            const bool valid = st < nsteps;
+            const int m = valid ? mv[st] : 4;
+            const unsigned bi = __ballot_sync(0xffffffffu, valid && m != 1), bj = __ballot_sync(0xffffffffu, valid && m != 0);
+            int vm = 0, vw = POY_GAP, vi = POY_GAP, vj = POY_GAP;
+            bool em = false;
+            if (valid) {
+                const int it = i_start - ci - __popc(bi & lt), jt = j_start - cj - __popc(bj & lt);
+                const int ic = si[it], jc = sj[jt];
+                if (m == 0) { em = !(ic & POY_GAP); vm = ic | POY_GAP; vw = em ? vm : POY_GAP; vi = ic; }
+                else if (m == 1) { em = !(jc & POY_GAP); vm = jc | POY_GAP; vw = em ? vm : POY_GAP; vj = jc; }
+                else if (m == 2) { vi = ic; vj = jc; }
+                else { em = true; vm = cm->median32[((ic & POY_NOGAP) << 5) + (jc & POY_NOGAP)]; vw = vm; vi = ic; vj = jc; }
+            }
+            const unsigned bm = __ballot_sync(0xffffffffu, em);
+            if (valid) {
+                const int at = ni + st + 1;      // ni == nj == nw: one element per step
+                if (pi) pi[-at] = (uint8_t)vi;
+                if (pj) pj[-at] = (uint8_t)vj;
+                if (pw) pw[-at] = (uint8_t)vw;
+                if (em && pm) pm[-(nm + __popc(bm & lt) + 1)] = (uint8_t)vm;
+            }
+            if (bm) first_m = __shfl_sync(0xffffffffu, vm, 31 - __clz(bm));
+            nm += __popc(bm);
+            ci += __popc(bi); cj += __popc(bj);
+        }
+        ni += nsteps; nj += nsteps; nw += nsteps;
         __syncwarp();
     }
+    // (the pointers of the serial tail below: where the steps above left off)
+    if (pm) pm -= nm;
+    if (pw) pw -= nw;
+    if (pi) pi -= ni;
+    if (pj) pj -= nj;
     if (lane == 0) {
         int ic = si[i], jc = sj[j];
         while (i != 0) {
