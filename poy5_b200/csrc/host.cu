@@ -772,6 +772,8 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const bool probe_gf = forced || n >= probe_min, probe_4s = forced || n >= probe_min4;
     const char *spe = getenv("POY_SPEC");   // POY_SPEC=0: one fill per pair and round, always
     const bool spec_allowed = !linear && !use_probes && !force_generic && !(spe && spe[0] == '0');
+    const char *spt = getenv("POY_SPEC_TEST");
+    const bool spec_test = spt && spt[0] == '1';
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
     // POY_LOWLAT=0 turns the low-latency kernel shapes off, 2 forces them (test hook); default: rounds with at most
@@ -947,6 +949,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                         j.dep = clones[p - n].prev;
                         j.need = (h.lastj - h.lasti) + h.k + pv.k + 2;
                         if (j.need + 20 >= h.lasti) j.need = SPEC_DONE;     // (the progress word moves in steps of 16 rows)
+                        // POY_SPEC_TEST=1 (test hook): every third speculative fill waits for a row its predecessor never
+                        // reports, gives up after the bounded wait and is run again in the next round
+                        if (spec_test && (p - n) % 3 == 1) j.need = SPEC_ABORT + 1;
                     }
                 }
                 doff += (h.dir_bytes + 255) & ~255ll;

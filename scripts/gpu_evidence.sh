@@ -20,10 +20,10 @@ done
 # 3. compute-sanitizer
 SAN=compute-sanitizer
 timeout 1200 $SAN --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_newkk.py -m gpu -x -q \
-    -k "edge_cases or related_pairs or probe_fills or low_latency or linear_edge or columnwise or cuda_matches_golden or generic_fallback" \
+    -k "edge_cases or related_pairs or probe_fills or low_latency or speculative or linear_edge or columnwise or cuda_matches_golden or generic_fallback" \
     > $out/${tag}_sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> $out/${tag}_sanitizer_memcheck.log
 timeout 1500 $SAN --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_newkk.py -m gpu -x -q \
-    -k "edge_cases or low_latency or many_wide_pairs or cuda_matches_golden" \
+    -k "edge_cases or low_latency or speculative or many_wide_pairs or cuda_matches_golden" \
     > $out/${tag}_sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> $out/${tag}_sanitizer_racecheck.log
 tail -3 $out/${tag}_sanitizer_memcheck.log $out/${tag}_sanitizer_racecheck.log
 ls -la $out | grep $tag

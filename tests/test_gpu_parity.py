@@ -228,6 +228,59 @@ def test_low_latency_shapes_do_not_change_results(ctx, port, monkeypatch, rname)
     cm.close(); pool.close()
 
 
+@pytest.mark.parametrize("rname", ["R1", "R3"])
+def test_speculative_doublings_do_not_change_results(ctx, port, monkeypatch, rname):
+    """latency-bound rounds fill the next threshold doublings of a pair in the same round (host.cu, align_impl): with the
+    speculation off, on, on with a small CTA budget (shorter chains, more rounds) and with every third speculative fill
+    forced to give up on its predecessor (the host repeats it), costs, statistics and every traceback output agree;
+    sampled against the oracle"""
+    import poy5_b200 as pb
+    from poy5_b200.sequence import Align
+    cm, full = setup(ctx, REGIMES[rname])
+    pc = port.cm(full)
+    rng = np.random.default_rng(4321)
+    seqs, ia, ib = synth.pair_batch(11, 28, 700, frac_decorated=0.8, jitter=0.3)
+    seqs = list(seqs)
+    ia, ib = list(ia), list(ib)
+    for q in range(10):                      # unrelated and length-skewed pairs: long chains, bands up to the widest classes
+        la = 150 + 60 * q
+        a = synth.random_seq(rng, la)
+        b = np.concatenate([synth.evolve(rng, a, 0.15, 0.02), synth.random_seq(rng, 80 * q)])
+        if q % 3:
+            a = synth.decorate(rng, a); b = synth.decorate(rng, b)
+        if len(a) > len(b):
+            a, b = b, a
+        ia.append(len(seqs)); seqs.append(synth.with_gap(a))
+        ib.append(len(seqs)); seqs.append(synth.with_gap(b))
+    ia = np.asarray(ia, np.int32); ib = np.asarray(ib, np.int32)
+    pool = pb.Pool(ctx, seqs)
+    monkeypatch.setenv("POY_SPEC", "0")
+    r0 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    rounds0 = ctx.stats()["rounds"]
+    monkeypatch.delenv("POY_SPEC")
+    r1 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    rounds1 = ctx.stats()["rounds"] - rounds0
+    assert rounds1 < rounds0 or rounds0 <= 2          # the speculation did run
+    monkeypatch.setenv("POY_SPEC_CTAS", "50")
+    r2 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    monkeypatch.delenv("POY_SPEC_CTAS")
+    rep0 = ctx.stats()["repeated"]
+    monkeypatch.setenv("POY_SPEC_TEST", "1")
+    r3 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    monkeypatch.delenv("POY_SPEC_TEST")
+    assert ctx.stats()["repeated"] > rep0               # fills did give up and were repeated
+    for r in (r1, r2, r3):
+        assert np.array_equal(r0["cost"], r["cost"]) and np.array_equal(r0["stats"], r["stats"])
+        for p in range(len(ia)):
+            for k in ("median", "medianwg", "res_a", "res_b"):
+                assert np.array_equal(r0[k][p], r[k][p]), (k, p)
+    for p in list(range(0, 28, 3)) + list(range(28, len(ia))):
+        oc, om, ow, ra, rb = oracle_align(port, pc, seqs[ia[p]], seqs[ib[p]])
+        assert oc == r1["cost"][p] and np.array_equal(om, r1["median"][p]) and np.array_equal(ow, r1["medianwg"][p])
+        assert np.array_equal(ra, r1["res_a"][p]) and np.array_equal(rb, r1["res_b"][p]), p
+    cm.close(); pool.close()
+
+
 def test_many_wide_pairs_per_cta(ctx, port, monkeypatch):
     """more 4096-class pairs than resident CTAs: every CTA of the 16-warp shape processes several pairs in a row, with
     and without probe fills; sampled against the oracle"""
