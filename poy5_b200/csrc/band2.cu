@@ -444,7 +444,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         const int bar_O_mine = NW + lw, bar_O_left = NW + lw - 1;       // O(w) = id NW + w, w = 0 .. NW-2
         if (NW > 1) {
             if (lane == 0) s_xe[lw] = make_int4(CB[0], EV[0], (int)G[0], 0);
-            if (lane == 31) s_xo[lw] = make_int4(CB[D - 1], EH[D - 1], (int)G[D - 1], 0);
+            if (lane == 31) s_xo[lw] = make_int4(CB[D - 1], EH[D - 1], (int)G[D - 1], 0x7fffffff);
             if (CL > 1 && rem_right && lane == 31) st_mailbox(rem_right_cx_left, CB[D - 1], EH[D - 1], (int)G[D - 1], seqbase);
             __syncthreads();
             if (P2P && warp_in_band && has_right) pair_arrive(bar_O_mine);   // row 0 stands in for "odd sub-step -1"
@@ -463,7 +463,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
         // one loop iteration = anti-diagonals a (even diagonals) and a+1 (odd diagonals)
         auto iteration = [&](auto edge_c) {
             constexpr bool EDGE = decltype(edge_c)::value;
-            if (NW > 1 && spec) astop = *(volatile int *)&s_astop;
+            if (CL > 1 && spec) astop = min(astop, *(volatile int *)&s_astop);     // (inside a CTA the bound travels with the mailboxes)
             // next window entries: issued now, consumed after both sub-steps (hides the L1/L2 latency)
             int4 nrow = make_int4(0, 0, 0, 0), ncol = make_int4(0, 0, 0, 0);
             if (warp_in_band) {
@@ -489,6 +489,9 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                 int sEH = __shfl_up_sync(0xffffffffu, EH[D - 1], 1);
                 unsigned sG = __shfl_up_sync(0xffffffffu, G[D - 1], 1);
                 if (NW > 1 && lane == 0 && lw > 0) { const int4 v = s_xo[lw - 1]; sCB = v.x; sEH = v.y; sG = (unsigned)v.z; }
+                // a speculative fill that is being abandoned: the last anti-diagonal to compute travels from warp to warp
+                // with the hand-over (one warp per iteration, the bound is set 32 iterations ahead)
+                if (NW > 1 && spec && lw > 0) astop = min(astop, s_xo[lw - 1].w);
                 if (CL > 1 && rem_left && lane == 0) {
                     const int4 v = wait_mailbox(&s_cx_left[it & 1], seqbase + it, mb_failed);
                     sCB = v.x; sEH = v.y; sG = (unsigned)v.z;
@@ -565,7 +568,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     }
                 });
                 if (NW > 1) {
-                    if (lane == 31) s_xo[lw] = make_int4(CB[D - 1], EH[D - 1], (int)G[D - 1], 0);
+                    if (lane == 31) s_xo[lw] = make_int4(CB[D - 1], EH[D - 1], (int)G[D - 1], astop);
                     if (CL > 1 && rem_right && lane == 31)
                         st_mailbox(rem_right_cx_left + ((it + 1) & 1), CB[D - 1], EH[D - 1], (int)G[D - 1], seqbase + it + 1);
                     if (P2P) { if (has_right) pair_arrive(bar_O_mine); }
@@ -595,18 +598,16 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                             // far enough ahead that all of them have seen the new bound by then
                             mid_stat = 2;
                             astop = a + (CL > 1 ? 192 : 64);
-                            if (NW > 1) {
-                                *rem_spec = 2;
-                                if constexpr (CL > 1) { for (int r = 0; r < CL; ++r) *(volatile int *)cg::this_cluster().map_shared_rank(&s_astop, r) = astop; }
-                                else *(volatile int *)&s_astop = astop;
-                            }
+                            if (NW > 1) *rem_spec = 2;
+                            if constexpr (CL > 1) { for (int r = 1; r < CL; ++r) *(volatile int *)cg::this_cluster().map_shared_rank(&s_astop, r) = astop; }
                         } else if (v < want) {
                             mid_stat = 1;
                             if (NW > 1) *rem_spec = 1;
                         }
                     }
                 }
-                if (NW == 1) { mid_stat = __shfl_sync(0xffffffffu, mid_stat, 0); astop = __shfl_sync(0xffffffffu, astop, 0); }
+                // (the warp of thread 0 agrees on what its lane 0 decided; the other warps learn the bound from the mailboxes)
+                if (NW == 1 || (lw == 0 && crank == 0)) { mid_stat = __shfl_sync(0xffffffffu, mid_stat, 0); astop = __shfl_sync(0xffffffffu, astop, 0); }
             }
             // the window entries prefetched at the top are first touched here: the load had the whole iteration to land
             asm volatile("" : "+r"(nrow.x), "+r"(nrow.y), "+r"(nrow.w), "+r"(ncol.x), "+r"(ncol.y), "+r"(ncol.w));
