@@ -656,7 +656,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     // Speculative threshold doublings (latency-bound rounds only, see the round loop): up to SPEC_EXTRA extra fills per
     // round, each a clone of its pair at a later threshold, appended to hp behind the n real pairs.  Every per-pair
     // array below is sized for n + SPEC_EXTRA entries.
-    const int SPEC_EXTRA = 288;
+    const int SPEC_EXTRA = 1024;
     const size_t nx = (size_t)n + SPEC_EXTRA;
     std::vector<HostPair> hp;
     hp.reserve(nx);
@@ -781,7 +781,6 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
     const char *ll = getenv("POY_LOWLAT");
     while (!active.empty()) {
         ++rounds;
-        const bool lowlat = !(ll && ll[0] == '0') && ((ll && ll[0] == '2') || (int64_t)active.size() <= 2 * (int64_t)ctx->sm_count);
         // band geometry of this round (algn_newkk_increaseT_aff / algn_newkk_test_aff, src/algn.c:2311-2336, 2195-2196)
         auto geometry = [&](HostPair &h) {
             const int delta = h.lastj - h.lasti;
@@ -818,6 +817,16 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             if (!h.repeat) h.iterations++;
             h.cells += h.fullplane ? (int64_t)h.lasti * (h.lastj + 1) : band_cells(h.lasti, h.lastj, h.k);
         }
+        // A round is latency bound when all its fills are resident at once: then it lasts as long as ONE pair's wavefront
+        // and the shapes with the fewest diagonals per thread are the right ones.  Resident warps: every shape keeps at
+        // least 16 warps on an SM (launch bounds of k_band2), a fill takes 1 ... 8 warps per CTA, cluster shapes 2 or 4 CTAs.
+        // (2-warp CTAs are bound by shared memory -- six per SM -- and count as 3)
+        auto warps_of = [](int cls) { return cls <= 64 ? 1 : cls <= 128 ? 3 : cls <= 256 ? 4 : cls <= 1024 ? 8 : cls <= 2048 ? 16 : 32; };
+        const int warp_capacity = ctx->sm_count * 16 - 256;
+        int64_t warp_demand = 0;
+        for (int p : active) warp_demand += warps_of(hp[p].dclass);
+        const bool lowlat = !(ll && ll[0] == '0') && ((ll && ll[0] == '2') || (int64_t)active.size() <= 2 * (int64_t)ctx->sm_count ||
+                                                      (warp_demand <= warp_capacity && (int)active.size() <= SPEC_EXTRA));
         // Speculative doublings.  In a latency-bound round most SMs idle while every pair waits for ONE wavefront, and a
         // pair then goes through 4-8 such rounds.  So the next doublings of each pair are filled in the same round, as
         // clones of the pair at 2T, 4T, ...: each fill needs from its predecessor only the stale EB entries of columns
@@ -831,19 +840,14 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         clones.clear();
         bool spec_round = false;
         if (spec_allowed && lowlat) {
-            auto ctas_of = [](int cls) { return cls <= 1024 ? 1 : (cls <= 2048 ? 2 : 4); };
-            // every fill of the round must be resident at once: CTAs of at most 256 threads and 128 registers (the launch
-            // bounds of the 8-warp shapes) fit two to an SM; POY_SPEC_CTAS overrides the budget (tuning / test hook)
+            // every fill of the round must be resident at once (they wait for each other): the budget is counted in
+            // resident warps; POY_SPEC_CTAS overrides it, in CTAs of 8 warps (tuning / test hook)
             const char *sb = getenv("POY_SPEC_CTAS");
-            int budget = sb ? atoi(sb) : 2 * ctx->sm_count - 32;
+            int64_t budget = (sb ? (int64_t)atoi(sb) * 8 : (int64_t)warp_capacity) - warp_demand;
             int64_t arena_used = 0;
             bool ok = true;
-            for (int p : active) {
-                const HostPair &h = hp[p];
-                budget -= ctas_of(h.dclass);
-                arena_used += (h.dir_bytes + 255) & ~255ll;
-            }
-            if (budget < 0 || (uint64_t)arena_used * 4 > ctx->arena_limit) ok = false;
+            for (int p : active) arena_used += (hp[p].dir_bytes + 255) & ~255ll;
+            if (budget < 0 || (uint64_t)arena_used * 4 > ctx->arena_limit || (int)active.size() > SPEC_EXTRA) ok = false;
             std::vector<int> tail(active.begin(), active.end());
             std::vector<char> open(active.size(), 1);
             for (int lvl = 1; ok && lvl < 8; ++lvl) {
@@ -860,9 +864,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
                     geometry(c);
                     if (c.dclass == 0) continue;
                     const int64_t bytes = (c.dir_bytes + 255) & ~255ll;
-                    if (ctas_of(c.dclass) > budget || (uint64_t)(arena_used + bytes) * 4 > ctx->arena_limit ||
+                    if (warps_of(c.dclass) > budget || (uint64_t)(arena_used + bytes) * 4 > ctx->arena_limit ||
                         (uint64_t)(arena_used + bytes) > (1ull << 30) || (int)clones.size() >= SPEC_EXTRA) continue;
-                    budget -= ctas_of(c.dclass); arena_used += bytes;
+                    budget -= warps_of(c.dclass); arena_used += bytes;
                     clones.push_back({ active[qi], tail[qi] });
                     hp.push_back(c);
                     tail[qi] = (int)hp.size() - 1;
