@@ -165,8 +165,15 @@ cudaError_t cached_alloc(poy_ctx *ctx, void **out, size_t bytes, size_t *cap_out
 }
 void cached_free(poy_ctx *ctx, void *p, size_t cap) {
     if (!p) return;
-    // bounded by entries AND by total bytes (4 GiB): the cache serves short-lived tree-search pools, not bulk batches
-    if (ctx && ctx->cache_n < 64 && cap <= (512u << 20) && ctx->cache_bytes + cap <= (4ull << 30)) {
+    // bounded by entries AND by total bytes (4 GiB): the cache serves short-lived tree-search pools ...
+    bool keep = ctx && ctx->cache_n < 64 && cap <= (512u << 20) && ctx->cache_bytes + cap <= (4ull << 30);
+    // ... and the per-base parameter arrays of bulk batches (GBs each: cudaFree of such a block idles the device for
+    // 0.1-0.8 s, measured as 0.6-3 s per sweep step of bench.py), but those only while a third of the device stays free
+    if (!keep && ctx && ctx->cache_n < 64 && ctx->cache_bytes + cap <= (48ull << 30)) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr >= tot / 3) keep = true;
+    }
+    if (keep) {
         ctx->cache_ptr[ctx->cache_n] = p; ctx->cache_cap[ctx->cache_n] = cap; ++ctx->cache_n; ctx->cache_bytes += cap;
     } else cudaFree(p);
 }
@@ -825,8 +832,10 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
         const int warp_capacity = ctx->sm_count * 16 - 256;
         int64_t warp_demand = 0;
         for (int p : active) warp_demand += warps_of(hp[p].dclass);
+        // (the demand rule only for batches that may speculate -- small, probe-free batches, i.e. tree passes: there it is
+        // measured; the tail rounds of large batches keep the two-pairs-per-SM rule they were tuned with)
         const bool lowlat = !(ll && ll[0] == '0') && ((ll && ll[0] == '2') || (int64_t)active.size() <= 2 * (int64_t)ctx->sm_count ||
-                                                      (warp_demand <= warp_capacity && (int)active.size() <= SPEC_EXTRA));
+                                                      (spec_allowed && warp_demand <= warp_capacity && (int)active.size() <= SPEC_EXTRA));
         // Speculative doublings.  In a latency-bound round most SMs idle while every pair waits for ONE wavefront, and a
         // pair then goes through 4-8 such rounds.  So the next doublings of each pair are filled in the same round, as
         // clones of the pair at 2T, 4T, ...: each fill needs from its predecessor only the stale EB entries of columns
