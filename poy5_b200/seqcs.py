@@ -157,6 +157,89 @@ def median_3_union(ctx, cm2, pool, parent, aligned_a, aligned_b):
                 aligned_parent=r["res_a"], aligned_union=r["res_b"])
 
 
+def _two_child(ctx, cm, pool, a, b):
+    """readjust_algn_two_child (src/seqCS.ml:783-815, use_ukk = false): the median of one alignment, made unambiguous
+    with Sequence.select_one.  Returns (list of sequences, int64 costs)."""
+    if cm.host.cost_model_type == 1:
+        r = Align.align_affine_3(ctx, cm, pool, a, b, want=("median",))
+        med = r["median"]
+    else:
+        r = Align.align_2(ctx, cm, pool, a, b)
+        med = sequence.median_2(ctx, cm, r["res_a"], r["res_b"], False)
+    return [sequence.select_one(m) for m in med], r["cost"].astype(np.int64)
+
+
+def readjust(ctx, h, pool, ch1, ch2, parent, mine, mine_costs, ch_sum_cost, use_ukk=False):
+    """DOS.readjust (src/seqCS.ml:820-947), `ApproxD mode, DNA (non-custom) alphabet, batched over nodes: the approximate
+    iterative re-optimisation of interior nodes given both children and the parent.
+
+    ch1, ch2, parent, mine: pool indices (int32[n]); mine_costs: int64[n, 3] = (cost2, cost3, sum_cost) of `mine`;
+    ch_sum_cost: int64[n] = ch1.sum_cost + ch2.sum_cost.  Returns dict:
+      changed bool[n]; sequence (list); aligned (list of the row stored three times in aligned_children, or None when
+      the node keeps another record's aligned_children); from_record int8[n] (-1: new record, 0/1/2: the node becomes a
+      copy of ch1 / ch2 / parent with sum_cost replaced, the "two of three are empty" cases);
+      cost2, cost2_max, cost3, sum_cost int64[n] (for from_record >= 0 only sum_cost is replaced in the copied record:
+      cost2 / cost3 here are the 0, 0 the reference returns beside it).
+    The five cases follow the reference's match on (is_empty ch1, is_empty ch2, is_empty parent)."""
+    if use_ukk:
+        raise NotImplementedError("DOS.readjust with use_ukk: route the alignments through sequence.NewkkAlign")
+    from .api import Pool
+    ch1 = np.ascontiguousarray(ch1, np.int32); ch2 = np.ascontiguousarray(ch2, np.int32)
+    parent = np.ascontiguousarray(parent, np.int32); mine = np.ascontiguousarray(mine, np.int32)
+    mc = np.asarray(mine_costs, np.int64).reshape(-1, 3)
+    chs = np.asarray(ch_sum_cost, np.int64)
+    n = len(mine)
+    empty = _is_empty(pool)
+    e1, e2, ep = empty[ch1], empty[ch2], empty[parent]
+    out = dict(changed=np.zeros(n, bool), sequence=[None] * n, aligned=[None] * n, from_record=np.full(n, -1, np.int8),
+               cost2=np.zeros(n, np.int64), cost2_max=np.zeros(n, np.int64), cost3=np.zeros(n, np.int64),
+               sum_cost=np.zeros(n, np.int64))
+    differs = lambda p, s: not np.array_equal(pool.seq(int(mine[p])), s)
+    cm = h.c2_full
+    # -- nobody empty: Sequence.readjust + max_cost_2 of the aligned row with itself
+    idx = np.flatnonzero(~e1 & ~e2 & ~ep)
+    if len(idx):
+        r = sequence.readjust(ctx, cm, pool, ch1[idx], ch2[idx], parent[idx])
+        mx = sequence.aligned_cost(ctx, cm, r["aligned_mp"], r["aligned_mp"], worst=True)
+        for q, p in enumerate(idx):
+            c2, c3 = int(r["cost2"][q]), int(r["cost3"][q])
+            out["sequence"][p] = r["sequence"][q]; out["aligned"][p] = r["aligned_mp"][q]
+            out["cost2"][p] = c2; out["cost3"][p] = c3; out["cost2_max"][p] = int(mx[q]); out["sum_cost"][p] = c2 + chs[p]
+            out["changed"][p] = (c2 + chs[p] != mc[p, 2]) or c3 != mc[p, 1] or c2 != mc[p, 0] or differs(p, r["sequence"][q])
+    # -- at least two of the three empty: the node becomes the record the reference's match binds to `r`
+    for p in np.flatnonzero((e1 & e2) | (e1 & ep) | (e2 & ep)):
+        which = 2 if (e1[p] and e2[p]) else (1 if (e1[p] and ep[p]) else 0)
+        src = (ch1, ch2, parent)[which][p]
+        out["from_record"][p] = which
+        out["sequence"][p] = pool.seq(int(src)).copy()
+        out["sum_cost"][p] = chs[p]
+        out["changed"][p] = chs[p] != mc[p, 2] or mc[p, 1] != 0 or mc[p, 0] != 0 or differs(p, out["sequence"][p])
+    # -- only the parent empty: the two children decide
+    idx = np.flatnonzero(~e1 & ~e2 & ep)
+    if len(idx):
+        med, cost = _two_child(ctx, cm, pool, ch1[idx], ch2[idx])
+        for q, p in enumerate(idx):
+            c2 = int(cost[q])
+            out["sequence"][p] = med[q]; out["cost2"][p] = c2; out["cost3"][p] = c2; out["sum_cost"][p] = c2 + chs[p]
+            out["changed"][p] = (c2 + chs[p] != mc[p, 2]) or c2 != mc[p, 1] or c2 != mc[p, 0] or differs(p, med[q])
+    # -- one child empty: the other child and the parent decide; the costs are DOS.distance to each of them
+    for child, mask in ((ch1, ~e1 & e2 & ~ep), (ch2, e1 & ~e2 & ~ep)):
+        idx = np.flatnonzero(mask)
+        if len(idx) == 0:
+            continue
+        med, _ = _two_child(ctx, cm, pool, child[idx], parent[idx])
+        k = len(idx)
+        tmp = Pool(ctx, [pool.seq(int(x)) for x in child[idx]] + [pool.seq(int(x)) for x in parent[idx]] + list(med))
+        ar = np.arange(k, dtype=np.int32)
+        d = DOS.distance(ctx, h, tmp, np.concatenate([ar, ar + 2 * k]), np.concatenate([ar + 2 * k, ar + k]), 0)
+        tmp.close()
+        for q, p in enumerate(idx):
+            c2 = int(d[q]); c3 = c2 + int(d[k + q])
+            out["sequence"][p] = med[q]; out["cost2"][p] = c2; out["cost3"][p] = c3; out["sum_cost"][p] = c2 + chs[p]
+            out["changed"][p] = (c2 + chs[p] != mc[p, 2]) or c3 != mc[p, 1] or c2 != mc[p, 0] or differs(p, med[q])
+    return out
+
+
 def to_single(ctx, h, pool, parent, mine):
     """DOS.to_single (src/seqCS.ml:950-982): the single-assignment sequence of `mine` given its parent's.  An empty
     `mine` stays empty (cost 0); an empty parent is replaced by `mine` itself; otherwise

@@ -355,6 +355,13 @@ def readjust(ctx, cm, pool, a, b, parent):
     return {"cost3": cost2 + cost[2 * n:], "cost2": cost2, "sequence": list(new), "aligned_mp": r["res_b"][2 * n:]}
 
 
+def select_one(seq):
+    """Sequence.select_one (src/sequence.ml:2065-2085) for the bitset alphabets of this path (combine = 1, no levels):
+    every symbol is replaced by the smallest element of its set, i.e. its lowest set bit."""
+    s = np.asarray(seq, np.uint8)
+    return (s & (~s + 1)).astype(np.uint8)
+
+
 class NewkkAlign:
     """Sequence.NewkkAlign (src/sequence.ml:1831-2062): the diagonal-storage Ukkonen alignment of src/newkkonen.c,
     affine cost model (the reference's non-affine entry point is broken, see include/poy5_b200.h)."""

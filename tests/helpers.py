@@ -98,3 +98,41 @@ def oracle_readjust(P, cmo, pc, m, a, b, parent, linear_align=None):
     _, _, c2 = align_2(b, new)
     _, amp, c3 = align_2(parent, new)
     return c1 + c2 + c3, c1 + c2, new, amp
+
+
+def oracle_dos_readjust(P, cmo, pc, m, ch1, ch2, parent, mine, mine_costs, ch_sum, distance, linear_align=None):
+    """SeqCS.DOS.readjust (src/seqCS.ml:820-947; `ApproxD, DNA alphabet, use_ukk = false) restated on top of the oracle,
+    one node.  `distance(a, b)` = DOS.distance with missing_distance 0.
+    -> (changed, sequence, from_record, cost2, cost2_max, cost3, sum_cost, aligned row or None)"""
+    is_empty = lambda x: bool((np.asarray(x) == 16).all())
+    e1, e2, ep = is_empty(ch1), is_empty(ch2), is_empty(parent)
+    mc2, mc3, msum = (int(x) for x in mine_costs)
+    same = lambda x: len(x) == len(mine) and bool((np.asarray(x) == np.asarray(mine)).all())
+
+    def two_child(a, b):
+        if m.cost_model_type == 1:
+            c, med, _, _, _ = oracle_align(P, pc, a, b)
+        else:
+            c, r1, r2 = linear_align(a, b)
+            med = P.median_2(pc, r1, r2, False)
+        med = np.asarray(med, np.uint8)
+        return (med & (~med + 1)).astype(np.uint8), int(c)
+    if not (e1 or e2 or ep):
+        c3, c2, new, amp = oracle_readjust(P, cmo, pc, m, ch1, ch2, parent, linear_align)
+        mx = int(P.worst_2(pc, amp, amp))
+        ch = (c2 + ch_sum != msum) or c3 != mc3 or c2 != mc2 or not same(new)
+        return ch, new, -1, c2, mx, c3, c2 + ch_sum, amp
+    if (e1 and e2) or (e1 and ep) or (e2 and ep):
+        which = 2 if (e1 and e2) else (1 if (e1 and ep) else 0)
+        r = (ch1, ch2, parent)[which]
+        ch = ch_sum != msum or mc3 != 0 or mc2 != 0 or not same(r)
+        return ch, np.asarray(r, np.uint8), which, 0, 0, 0, ch_sum, None
+    if ep:
+        new, c2 = two_child(ch1, ch2)
+        ch = (c2 + ch_sum != msum) or c2 != mc3 or c2 != mc2 or not same(new)
+        return ch, new, -1, c2, 0, c2, c2 + ch_sum, None
+    child = ch1 if e2 else ch2
+    new, _ = two_child(child, parent)
+    c2 = int(distance(child, new)); c3 = c2 + int(distance(new, parent))
+    ch = (c2 + ch_sum != msum) or c3 != mc3 or c2 != mc2 or not same(new)
+    return ch, new, -1, c2, 0, c3, c2 + ch_sum, None

@@ -511,6 +511,68 @@ def test_closest_and_to_single(ctx, port, go):
 
 
 @pytest.mark.parametrize("go", [None, 3])
+def test_dos_readjust(ctx, port, go):
+    """SeqCS.DOS.readjust (src/seqCS.ml:820-947, `ApproxD): the five cases of (is_empty ch1, is_empty ch2, is_empty parent),
+    the `changed` verdict against matching and non-matching previous costs, batched; one node at a time on the oracle"""
+    import poy5_b200 as pb
+    from poy5_b200 import seqcs
+    from poy5_b200.cost_matrix import Two_D
+    from tests.helpers import oracle_dos_readjust
+    t2d = Two_D.of_transformations_and_gaps(1, 1, go)
+    full, _ = cmo.dna_matrices(1, 1, go)
+    cm = pb.CostModel(ctx, t2d.full)
+    h = seqcs.Heuristic(cm, cm)
+    pf = port.cm(full)
+    rng = np.random.default_rng(17)
+    gapseq = lambda: synth.with_gap(np.zeros(0, np.uint8))
+    seqs, n = [], 42
+    for t in range(n):
+        anc = synth.random_seq(rng, int(rng.integers(5, 100)))
+        quad = [synth.evolve(rng, anc, 0.1, 0.04) for _ in range(4)]           # ch1, ch2, parent, mine
+        if t % 4 == 0:
+            quad[0] = synth.decorate(rng, quad[0], 0.1, 0.1)
+        quad = [synth.with_gap(x) for x in quad]
+        # which of (ch1, ch2, parent) are empty: every pattern, half of the nodes complete
+        empt = [(), (0,), (1,), (2,), (0, 1), (0, 2), (1, 2)][t % 7] if t % 14 < 7 else ((0, 1, 2) if t % 14 == 13 else ())
+        for slot in empt:
+            quad[slot] = gapseq()
+        seqs += quad
+    pool = pb.Pool(ctx, seqs)
+    ia = np.arange(0, 4 * n, 4, dtype=np.int32)
+    ch_sum = rng.integers(0, 50, n).astype(np.int64)
+    lin = lambda x, y: _oracle_linear(port, pf, x, y)
+
+    def dist(a, b):
+        if bool((np.asarray(a) == 16).all()) or bool((np.asarray(b) == 16).all()):
+            return 0
+        if go is not None:
+            return int(port.cost_affine(pf, a, b)) if len(a) <= len(b) else int(port.cost_affine(pf, b, a))
+        return int(_oracle_linear(port, pf, a, b, deltaw=max(abs(len(a) - len(b)), 8))[0])
+    # pass 1 with arbitrary previous costs, pass 2 with the costs / sequences pass 1 produced (nothing may change then)
+    prev = np.stack([rng.integers(0, 30, n), rng.integers(0, 60, n), rng.integers(0, 90, n)], 1).astype(np.int64)
+    got = seqcs.readjust(ctx, h, pool, ia, ia + 1, ia + 2, ia + 3, prev, ch_sum)
+    for t in range(n):
+        q = [seqs[ia[t] + k] for k in range(4)]
+        ch, new, rec, c2, mx, c3, sm, amp = oracle_dos_readjust(port, cmo, pf, full, q[0], q[1], q[2], q[3], prev[t], int(ch_sum[t]), dist, lin)
+        assert bool(got["changed"][t]) == bool(ch) and got["from_record"][t] == rec, ("verdict", t)
+        assert np.array_equal(got["sequence"][t], new), ("sequence", t)
+        assert (got["cost2"][t], got["cost2_max"][t], got["cost3"][t], got["sum_cost"][t]) == (c2, mx, c3, sm), ("costs", t)
+        assert (amp is None and got["aligned"][t] is None) or np.array_equal(got["aligned"][t], amp), ("aligned", t)
+    seqs2 = list(seqs)
+    for t in range(n):
+        seqs2[ia[t] + 3] = got["sequence"][t]
+    pool2 = pb.Pool(ctx, seqs2)
+    prev2 = np.stack([got["cost2"], got["cost3"], got["sum_cost"]], 1)
+    again = seqcs.readjust(ctx, h, pool2, ia, ia + 1, ia + 2, ia + 3, prev2, ch_sum)
+    stable = [t for t in range(n) if again["from_record"][t] < 0]
+    # (a node that copies a record keeps cost2 = cost3 = 0 in the verdict, see the reference's match)
+    for t in stable:
+        if np.array_equal(again["sequence"][t], got["sequence"][t]) and again["cost2"][t] == got["cost2"][t] and again["cost3"][t] == got["cost3"][t]:
+            assert not again["changed"][t], ("fixed point", t)
+    pool.close(); pool2.close(); cm.close()
+
+
+@pytest.mark.parametrize("go", [None, 3])
 def test_readjust(ctx, port, go):
     """Sequence.readjust (src/sequence.ml:2097-2156): approximate three-way re-optimisation of an interior node,
     a batched composition of 9 alignments + closest per node"""
