@@ -859,7 +859,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             if (budget < 0 || (uint64_t)arena_used * 4 > ctx->arena_limit || (int)active.size() > SPEC_EXTRA) ok = false;
             std::vector<int> tail(active.begin(), active.end());
             std::vector<char> open(active.size(), 1);
-            for (int lvl = 1; ok && lvl < 8; ++lvl) {
+            for (int lvl = 1; ok && lvl < 12; ++lvl) {   // (a 10 kb pair of distant sequences takes up to ~12 doublings)
                 bool any = false;
                 for (size_t qi = 0; qi < active.size(); ++qi) {
                     if (!open[qi]) continue;
