@@ -184,3 +184,29 @@ def implied_alignment(tree, root, seqs, cost, align2):
             out[row, n - remap[recode[code]]] = li.seq[pos]
     out[out == 0] = GAP
     return out, leaves, redone
+
+
+# ---- output: the symbols of Alphabet.nucleotides (src/alphabet.ml:270-315; the FIRST name bound to a code is the one
+# printed: T not U, N not X, * not ?) and a fasta writer for the matrix returned by implied_alignment --------------------
+NUCLEOTIDE_SYMBOLS = {1: "A", 2: "C", 4: "G", 8: "T", 3: "M", 5: "R", 9: "W", 6: "S", 10: "Y", 12: "K", 7: "V", 11: "H", 13: "D",
+                      14: "B", 15: "N", 16: "-", 17: "1", 18: "2", 19: "3", 20: "4", 21: "5", 22: "6", 23: "7", 24: "8", 25: "9",
+                      26: "0", 27: "!", 28: "^", 29: "$", 30: "#", 31: "*"}
+_SYM = np.array([ord(NUCLEOTIDE_SYMBOLS.get(c, "?")) for c in range(32)], np.uint8)
+
+
+def to_strings(matrix):
+    """rows of an implied-alignment matrix as strings; column 0 (the leading gap every sequence carries) is dropped"""
+    m = np.asarray(matrix, np.uint8)
+    return [_SYM[row[1:] & 31].tobytes().decode("ascii") for row in m]
+
+
+def write_fasta(fh, matrix, names, width=0):
+    """one record per taxon, in row order (report (implied_alignments) of the reference writes the same content through
+    its fasta formatter; the line layout here is not pinned to it).  width > 0 wraps the sequence lines."""
+    for name, row in zip(names, to_strings(matrix)):
+        fh.write(">%s\n" % name)
+        if width and width > 0:
+            for k in range(0, len(row), width):
+                fh.write(row[k:k + width] + "\n")
+        else:
+            fh.write(row + "\n")

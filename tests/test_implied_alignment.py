@@ -102,3 +102,15 @@ def test_gpu_composition_equals_checker(ctx, port):
     assert l1 == l2 and np.array_equal(m1, m2)
     check_properties(m1, l1, taxa, tree, root, seqs, None, full.cost)
     cm.close()
+
+
+def test_symbols_and_fasta():
+    """Alphabet.nucleotides code -> symbol (src/alphabet.ml:270-315) and the fasta writer"""
+    import io
+    from poy5_b200 import implied_alignment as ia
+    m = np.array([[16, 1, 2, 16, 8, 15], [16, 4, 16, 16, 10, 17]], np.uint8)
+    assert ia.to_strings(m) == ["AC-TN", "G--Y1"]
+    assert ia.NUCLEOTIDE_SYMBOLS[8] == "T" and ia.NUCLEOTIDE_SYMBOLS[31] == "*" and ia.NUCLEOTIDE_SYMBOLS[26] == "0"
+    out = io.StringIO()
+    ia.write_fasta(out, m, ["t1", "t2"], width=3)
+    assert out.getvalue() == ">t1\nAC-\nTN\n>t2\nG--\nY1\n"
