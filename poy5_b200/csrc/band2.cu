@@ -196,9 +196,14 @@ __device__ __forceinline__ void spec_publish(int *p, int v) {
     __threadfence();
     *(volatile int *)p = v;
 }
-__device__ __forceinline__ int spec_wait(const int *p, int need) {     // returns the last value read: >= need unless it gave up
+// Two bounds.  BEFORE a fill starts (max_spin = 2^18, ~0.1 s) giving up is harmless: nothing was written, the host repeats
+// the doubling.  IN MID-RUN the fill has already stored into the pair's stale row, so giving up would leave a state the
+// plain schedule never produces; there the predecessor is known to be running (it reported progress), it can only be
+// waiting for ITS predecessor, and the head of a chain waits for nobody -- the wait always ends, and the bound (2^26 polls,
+// tens of seconds) is only a net under a bug.
+__device__ __forceinline__ int spec_wait(const int *p, int need, int max_spin) {     // returns the last value read: >= need unless it gave up
     int v = *(const volatile int *)p;
-    for (int spin = 0; v >= 0 && v < need && spin < (1 << 18); ++spin) { __nanosleep(200); v = *(const volatile int *)p; }
+    for (int spin = 0; v >= 0 && v < need && spin < max_spin; ++spin) { __nanosleep(200); v = *(const volatile int *)p; }
     __threadfence();
     return v;
 }
@@ -354,14 +359,14 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
             int st0 = 0;                      // 1 = gave up, 2 = an earlier doubling stopped: nothing to do
             auto judge = [&](int v) { return v >= SPEC_STOP ? 2 : (v < J.need ? 1 : 0); };
             if (NW == 1) {
-                if (lane == 0) st0 = judge(spec_wait(prog + J.dep, J.need));
+                if (lane == 0) st0 = judge(spec_wait(prog + J.dep, J.need, 1 << 18));
                 st0 = __shfl_sync(0xffffffffu, st0, 0);
             } else if constexpr (CL > 1) {
-                if (tid == 0) s_spec = judge(spec_wait(prog + J.dep, J.need));
+                if (tid == 0) s_spec = judge(spec_wait(prog + J.dep, J.need, 1 << 18));
                 cg::this_cluster().sync();
                 st0 = *rem_spec;
             } else {
-                if (tid == 0) s_spec = judge(spec_wait(prog + J.dep, J.need));
+                if (tid == 0) s_spec = judge(spec_wait(prog + J.dep, J.need, 1 << 18));
                 __syncthreads();
                 st0 = s_spec;
             }
@@ -592,7 +597,7 @@ k_band2(const DevCM *__restrict__ cm, const int4 *__restrict__ rowp, const int4 
                     spec_publish(prog + J.pair, i0);
                     if (J.dep >= 0) {
                         const int want = (i0 + 18 >= istar) ? SPEC_DONE : i0 + 18;
-                        const int v = spec_wait(prog + J.dep, want);
+                        const int v = spec_wait(prog + J.dep, want, 1 << 26);
                         if (v >= SPEC_STOP) {
                             // an earlier doubling is the result: every warp leaves the loop after the same anti-diagonal,
                             // far enough ahead that all of them have seen the new bound by then
