@@ -1,3 +1,5 @@
+"""BASELINE configs[4] downpass alone (1000 taxa x 10 kb, random tree: 999 medians, most levels one to four pairs), twice;
+POY_TRACE=1 prints one line per level batch.  Run on a GPU box from the repo root: python scripts/probe_cfg5_downpass.py"""
 import sys, os, time
 sys.path.insert(0, os.getcwd())
 import numpy as np
