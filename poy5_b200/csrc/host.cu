@@ -1063,6 +1063,7 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             for (int p : active) {
                 HostPair &h = hp[p];
                 if (h.dclass == 0 || h.lasti == 0) {          // not part of the speculation: the plain verdicts
+                    if (std::min(h.k, h.lasti) >= 2) h.eh00_inf = true;
                     const int verdict = h_done[p];
                     if (verdict == 1) { h.done = true; htb[ntb++] = hj[posq[p]]; continue; }
                     h.T *= 2; h.want_dirs = 0; h.repeat = 0;
@@ -1106,6 +1107,9 @@ static poy_status align_impl(poy_ctx *ctx, const poy_cm *cm, const poy_pool *poo
             continue;
         }
         for (int p : active) {
+            // (EH[0][0] as this fill leaves it, for a later speculative round: k_band2 / k_band_generic set it to INF
+            // under this condition, probe fills and repeated fills alike)
+            if (std::min(hp[p].k, hp[p].lasti) >= 2) hp[p].eh00_inf = true;
             const int verdict = h_done[p];   // k_band_finish / k_lin_finish
             if (verdict == 1) { hp[p].done = true; continue; }
             if (verdict == 2) { hp[p].want_dirs = 1; hp[p].repeat = 1; ++n_repeat; }   // same threshold again, with directions

@@ -263,13 +263,17 @@ def test_speculative_doublings_do_not_change_results(ctx, port, monkeypatch, rna
     assert rounds1 < rounds0 or rounds0 <= 2          # the speculation did run
     monkeypatch.setenv("POY_SPEC_CTAS", "50")
     r2 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
+    # a budget so small that the first rounds run the plain schedule and only the last stragglers speculate: the state
+    # the plain rounds left on the device (T, EH[0][0]) must be what the speculative fills start from, and vice versa
+    monkeypatch.setenv("POY_SPEC_CTAS", "2")
+    r4 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
     monkeypatch.delenv("POY_SPEC_CTAS")
     rep0 = ctx.stats()["repeated"]
     monkeypatch.setenv("POY_SPEC_TEST", "1")
     r3 = Align.align_affine_3(ctx, cm, pool, ia, ib, stats=True)
     monkeypatch.delenv("POY_SPEC_TEST")
     assert ctx.stats()["repeated"] > rep0               # fills did give up and were repeated
-    for r in (r1, r2, r3):
+    for r in (r1, r2, r3, r4):
         assert np.array_equal(r0["cost"], r["cost"]) and np.array_equal(r0["stats"], r["stats"])
         for p in range(len(ia)):
             for k in ("median", "medianwg", "res_a", "res_b"):
